@@ -1,0 +1,112 @@
+"""ctypes binding of libcds_b200.so -- the only way the Python host reaches the CUDA kernels.
+
+The prototypes are read from ``include/cds_b200.h`` so the header stays the single source of truth
+for the C ABI.  There is NO fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the product path never routes through torch ops or the CPU oracle).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import torch
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(PKG), "include", "cds_b200.h")
+LIB_PATH = os.path.join(PKG, "libcds_b200.so")
+
+CDS_F32, CDS_F16 = 0, 1
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+
+_CTYPES = {
+    "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
+    "cudaStream_t": ctypes.c_void_p, "void": None,
+}
+
+
+def _ctype_of(decl: str):
+    decl = decl.strip()
+    if "*" in decl:
+        return ctypes.c_void_p
+    base = re.sub(r"\bconst\b", "", decl).strip()
+    base = re.sub(r"\s+\w+$", "", base).strip() if base not in _CTYPES else base
+    if base not in _CTYPES:
+        raise ValueError(f"unmapped C type in header: {decl!r}")
+    return _CTYPES[base]
+
+
+def parse_header(path: str = HEADER) -> dict:
+    """{name: (restype, [argtypes])} for every prototype declared in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"^\s*(const char\*|int)\s+(cds_\w+)\s*\(([^)]*)\)\s*;", text, flags=re.M):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int
+        argtypes = [] if args in ("", "void") else [_ctype_of(a) for a in args.split(",")]
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self._device_checked = False
+
+    def load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA library is the product and there is no fallback. "
+                "Build it with `python -m cds_mvsnet_b200.build` (or __graft_entry__.build()).")
+        dll = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in parse_header().items():
+            fn = getattr(dll, name)  # AttributeError here = header/library mismatch
+            fn.restype = restype
+            fn.argtypes = argtypes
+        self._dll = dll
+        return dll
+
+    def call(self, name: str, *args):
+        dll = self.load()
+        if not self._device_checked:
+            if not torch.cuda.is_available():
+                raise RuntimeError("cds_b200 needs a CUDA device (B200, sm_100a); none is visible")
+            rc = dll.cds_check_device()
+            if rc != 0:
+                raise RuntimeError(dll.cds_last_error_string().decode())
+            self._device_checked = True
+        rc = getattr(dll, name)(*args)
+        if rc != 0:
+            raise RuntimeError(f"{name} failed (code {rc}): {dll.cds_last_error_string().decode()}")
+
+
+LIB = _Lib()
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+LAUNCHES = 0   # C-ABI calls issued by this process (every one enqueues exactly one kernel)
+
+
+def call(name, *args):
+    global LAUNCHES
+    LIB.call(name, *args, stream())
+    LAUNCHES += 1
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float16:
+        return CDS_F16
+    if dt == torch.float32:
+        return CDS_F32
+    raise ValueError(f"storage dtype must be float16 or float32, got {dt}")

@@ -1,0 +1,275 @@
+"""Host-side driver of the fused depth-inference cascade (the CUDA path of ``CDSMVSNet.forward``).
+
+Everything numerical happens in libcds_b200.so; this module owns buffers and launch order only.
+Reference flow being replaced: models/model.py:140-223 (cascade), :16-94 (stage), models/module.py:
+236-267 (feature extractor), :305-315 (regulariser).  Layout of the feature-extractor batch: item
+(side, v, b) with side 0 = the reference image seen with pair v's epipole, side 1 = source image v
+(the reference recomputes the ref features per pair, models/model.py:154-161); so the first V*B
+items are exactly the ``ref_fea [V,B,...]`` the cost-volume kernels want and the rest ``src_fea``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, call, ptr
+from .weights import ModelWeights
+
+STAGE_SCALE = (4, 2, 1)   # models/model.py:115-125
+STAGE_CHANNELS = (32, 16, 8)
+
+
+class Buffers:
+    """Named persistent device buffers (static addresses => CUDA-graph friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._t = {}
+
+    def get(self, name, shape, dtype):
+        shape = tuple(int(s) for s in shape)
+        t = self._t.get(name)
+        if t is None or t.shape != shape or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._t[name] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self._t.values())
+
+
+def _ksizes(ks):
+    return (ctypes.c_int * len(ks))(*ks)
+
+
+class FeatureExtractor:
+    """FeatureNet (models/module.py:201-267) for a batch of n images in ~17 launches."""
+
+    N_STATS = 13
+
+    def __init__(self, fw, storage=torch.float16):
+        self.fw = fw
+        self.storage = storage
+        self.dt = _lib.dtype_code(storage)
+
+    def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
+             nc_mode, nc_abs, norm_curv=None):
+        w = self.fw.dyn[name]
+        call("cds_dynamic_conv", ptr(x), in_mode, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
+             ptr(w.w_att), ptr(w.w_conv), ptr(w.bias), ptr(w.gate), n, w.cin, w.cout, H, W, len(w.ksizes),
+             _ksizes(w.ksizes), float(T), self.dt, ptr(out), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode,
+             ptr(nc_abs))
+
+    def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature):
+        """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
+        Returns {stage: (fea [n,h,w,C] storage dtype, nc_sq [n,h,w] fp32, nc_abs [n,h,w] fp32)}."""
+        st, dt = self.storage, self.dt
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        stats = buf.get("f.stats", (self.N_STATS, n, 32, 2), torch.float64)
+        stats.zero_()
+        # the kernels index statistics densely as [n][C][2]: give each layer its own dense view
+        sviews = {}
+
+        def sv(i, c):
+            if i not in sviews:
+                sviews[i] = stats[i].reshape(-1)[: n * c * 2].view(n, c, 2)
+            return sviews[i]
+
+        f32 = torch.float32
+        raw00 = buf.get("f.raw00", (n, H, W, 8), st)
+        raw01 = buf.get("f.raw01", (n, H, W, 8), st)
+        rawd1 = buf.get("f.rawd1", (n, H2, W2, 16), st)
+        raw10 = buf.get("f.raw10", (n, H2, W2, 16), st)
+        raw11 = buf.get("f.raw11", (n, H2, W2, 16), st)
+        rawd2 = buf.get("f.rawd2", (n, H4, W4, 32), st)
+        raw20 = buf.get("f.raw20", (n, H4, W4, 32), st)
+        raw21 = buf.get("f.raw21", (n, H4, W4, 32), st)
+        rawo1 = buf.get("f.rawo1", (n, H4, W4, 32), st)
+        fea1 = buf.get("f.fea1", (n, H4, W4, 32), st)
+        rawi1 = buf.get("f.rawi1", (n, H2, W2, 16), st)
+        rawo2 = buf.get("f.rawo2", (n, H2, W2, 16), st)
+        fea2 = buf.get("f.fea2", (n, H2, W2, 16), st)
+        rawi2 = buf.get("f.rawi2", (n, H, W, 8), st)
+        rawo3 = buf.get("f.rawo3", (n, H, W, 8), st)
+        fea3 = buf.get("f.fea3", (n, H, W, 8), st)
+        ncsq = [buf.get(f"f.ncsq{i}", (n, h, w), f32) for i, (h, w) in enumerate(((H4, W4), (H2, W2), (H, W)))]
+        ncab = [buf.get(f"f.ncabs{i}", (n, h, w), f32) for i, (h, w) in enumerate(((H4, W4), (H2, W2), (H, W)))]
+        T = temperature
+        fw = self.fw
+        # full resolution
+        self._dyn("conv00", imgs, 1, img_index, None, ACT_NONE, epipoles, 1.0, n, H, W, T, raw00, sv(0, 8), ncsq[2], 0, None)
+        self._dyn("conv01", raw00, 0, None, sv(0, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, raw01, sv(1, 8), ncsq[2], 1, None)
+        # 1/2 resolution
+        call("cds_conv2d_3x3s2", ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.downsample1), n, 8, 16, H, W, dt, ptr(rawd1), ptr(sv(2, 16)))
+        self._dyn("conv10", rawd1, 0, None, sv(2, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw10, sv(3, 16), ncsq[1], 0, None)
+        self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11, sv(4, 16), ncsq[1], 1, None)
+        # 1/4 resolution
+        call("cds_conv2d_3x3s2", ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.downsample2), n, 16, 32, H2, W2, dt, ptr(rawd2), ptr(sv(5, 32)))
+        self._dyn("conv20", rawd2, 0, None, sv(5, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw20, sv(6, 32), ncsq[0], 0, None)
+        self._dyn("conv21", raw20, 0, None, sv(6, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw21, sv(7, 32), ncsq[0], 1, None)
+        # stage-1 output
+        self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1, sv(8, 32), ncsq[0], 2, ncab[0])
+        call("cds_instnorm_act", ptr(rawo1), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
+        # stage-2 output: inner1 over cat(up2(conv21), conv11)
+        call("cds_conv2d_1x1_cat", ptr(raw21), ptr(sv(7, 32)), ACT_LRELU, ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.inner1),
+             n, 32, 16, 16, H2, W2, dt, ptr(rawi1), ptr(sv(9, 16)))
+        self._dyn("out2", rawi1, 0, None, sv(9, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, rawo2, sv(10, 16), ncsq[1], 2, ncab[1])
+        call("cds_instnorm_act", ptr(rawo2), ptr(sv(10, 16)), ACT_TANH, n, 16, H2, W2, dt, ptr(fea2))
+        # stage-3 output: inner2 over cat(up2(stage-2 feature), conv01)
+        call("cds_conv2d_1x1_cat", ptr(fea2), None, ACT_NONE, ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.inner2),
+             n, 16, 8, 8, H, W, dt, ptr(rawi2), ptr(sv(11, 8)))
+        self._dyn("out3", rawi2, 0, None, sv(11, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, rawo3, sv(12, 8), ncsq[2], 2, ncab[2])
+        call("cds_instnorm_act", ptr(rawo3), ptr(sv(12, 8)), ACT_TANH, n, 8, H, W, dt, ptr(fea3))
+        return {0: (fea1, ncsq[0], ncab[0]), 1: (fea2, ncsq[1], ncab[1]), 2: (fea3, ncsq[2], ncab[2])}
+
+
+class Regulariser:
+    """CostRegNet (models/module.py:270-315) + prob head on a channels-last volume."""
+
+    def __init__(self, cw, storage=torch.float16):
+        self.cw = cw
+        self.storage = storage
+        self.dt = _lib.dtype_code(storage)
+
+    def _conv(self, name, x, B, D, H, W, stride, out):
+        l = self.cw.layers[name]
+        call("cds_conv3d_k3", ptr(x), ptr(l.w), ptr(l.bias), B, l.cin, l.cout, D, H, W, stride, 1, self.dt, ptr(out))
+
+    def _deconv(self, name, x, skip, B, D, H, W, out):
+        l = self.cw.layers[name]
+        call("cds_deconv3d_k3s2", ptr(x), ptr(l.w), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, self.dt, ptr(out))
+
+    def run(self, buf: Buffers, tag, volume, B, D, H, W):
+        """volume [B,D,H,W,C] -> fp32 logits [B,D,H,W]."""
+        if D % 8 or H % 8 or W % 8:
+            raise RuntimeError(f"CostRegNet needs D, H, W divisible by 8 (got {D}x{H}x{W}); the reference fails the "
+                               "same way at its skip additions (models/module.py:310-312)")
+        st = self.storage
+        b = self.cw.layers["conv0"].cout
+        D2, H2, W2, D4, H4, W4, D8, H8, W8 = D // 2, H // 2, W // 2, D // 4, H // 4, W // 4, D // 8, H // 8, W // 8
+        g = lambda n, s: buf.get(f"{tag}.{n}", s, st)
+        c0 = g("c0", (B, D, H, W, b))
+        c1 = g("c1", (B, D2, H2, W2, 2 * b))
+        c2 = g("c2", (B, D2, H2, W2, 2 * b))
+        c3 = g("c3", (B, D4, H4, W4, 4 * b))
+        c4 = g("c4", (B, D4, H4, W4, 4 * b))
+        c5 = g("c5", (B, D8, H8, W8, 8 * b))
+        c6 = g("c6", (B, D8, H8, W8, 8 * b))
+        u7 = g("u7", (B, D4, H4, W4, 4 * b))
+        u9 = g("u9", (B, D2, H2, W2, 2 * b))
+        u11 = g("u11", (B, D, H, W, b))
+        logits = buf.get(f"{tag}.logits", (B, D, H, W), torch.float32)
+        self._conv("conv0", volume, B, D, H, W, 1, c0)
+        self._conv("conv1", c0, B, D, H, W, 2, c1)
+        self._conv("conv2", c1, B, D2, H2, W2, 1, c2)
+        self._conv("conv3", c2, B, D2, H2, W2, 2, c3)
+        self._conv("conv4", c3, B, D4, H4, W4, 1, c4)
+        self._conv("conv5", c4, B, D4, H4, W4, 2, c5)
+        self._conv("conv6", c5, B, D8, H8, W8, 1, c6)
+        self._deconv("conv7", c6, c4, B, D8, H8, W8, u7)
+        self._deconv("conv9", u7, c2, B, D4, H4, W4, u9)
+        self._deconv("conv11", u9, c0, B, D2, H2, W2, u11)
+        call("cds_prob_conv", ptr(u11), ptr(self.cw.prob), B, b, D, H, W, self.dt, ptr(logits))
+        return logits
+
+
+class CascadeEngine:
+    """The whole CDSMVSNet.forward (refine=False, eval) on the CUDA kernels."""
+
+    def __init__(self, weights: ModelWeights, ndepths, ratios, storage=torch.float16, device=None):
+        self.w = weights
+        self.ndepths = tuple(int(d) for d in ndepths)
+        self.ratios = tuple(float(r) for r in ratios)
+        self.storage = storage
+        self.dt = _lib.dtype_code(storage)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.buf = Buffers(self.device)
+        self.features = FeatureExtractor(weights.feature, storage)
+        self.regs = [Regulariser(cw, storage) for cw in weights.costreg]
+        self.launches = 0
+
+    # -- pieces -------------------------------------------------------------------------------
+    def camera_setup(self, proj_matrices, B, N):
+        n_st = len(self.ndepths)
+        keys = [f"stage{s + 1}" for s in range(n_st)]
+        epi_key = "stage3"   # models/model.py:152 always uses the stage-3 cameras for the epipoles
+        mats = [proj_matrices[k] for k in keys]
+        if epi_key in keys:
+            epi_idx = keys.index(epi_key)
+        else:
+            mats.append(proj_matrices[epi_key])
+            epi_idx = len(mats) - 1
+        mats = [m.to(device=self.device, dtype=torch.float32).contiguous() for m in mats]
+        for m in mats:
+            if tuple(m.shape) != (B, N, 2, 4, 4):
+                raise AssertionError(f"proj_matrices entries must be [B,N,2,4,4], got {tuple(m.shape)}")
+        V = N - 1
+        coef = self.buf.get("cam.coef", (len(mats), B, V, 12), torch.float32)
+        epi = self.buf.get("cam.epi", (2, V, B, 2), torch.float32)
+        arr = (ctypes.c_void_p * len(mats))(*[m.data_ptr() for m in mats])
+        call("cds_camera_setup", arr, len(mats), epi_idx, B, N, ptr(coef), ptr(epi))
+        self._keep = mats
+        return coef, epi
+
+    def stage(self, s, feats_s, coef_s, depth_values, prev_depth, B, V, H, W):
+        """One StageNet.forward (models/model.py:16-94) at stage index s."""
+        D, scale, C = self.ndepths[s], STAGE_SCALE[s], STAGE_CHANNELS[s]
+        h, w = H // scale, W // scale
+        buf, f32 = self.buf, torch.float32
+        fea, ncsq, ncabs = feats_s
+        VB = V * B
+        samples = buf.get(f"s{s}.samples", (B, D, h, w), f32)
+        hp, wp = (prev_depth.shape[1], prev_depth.shape[2]) if prev_depth is not None else (0, 0)
+        call("cds_depth_hypotheses", ptr(depth_values), depth_values.shape[1], ptr(prev_depth), hp, wp, B, D, self.ratios[s], H, W,
+             scale, ptr(samples))
+        ref_fea, src_fea = fea[:VB], fea[VB:]
+        entropy = buf.get(f"s{s}.entropy", (V, B, h, w), f32)
+        call("cds_costvol_entropy", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, self.dt, ptr(entropy))
+        vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
+        call("cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]), VB, h, w, ptr(vis))
+        volume = buf.get(f"s{s}.volume", (B, D, h, w, C), self.storage)
+        call("cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
+             ptr(volume))
+        nc = buf.get(f"s{s}.nc", (B, 1, h, w), f32)
+        call("cds_nc_mean", ptr(ncsq[:VB]), ptr(ncsq[VB:]), V, B * h * w, ptr(nc))
+        logits = self.regs[s].run(buf, f"s{s}.cr", volume, B, D, h, w)
+        depth = buf.get(f"s{s}.depth", (B, h, w), f32)
+        conf = buf.get(f"s{s}.conf", (B, h, w), f32)
+        call("cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w, ptr(depth), ptr(conf), None)
+        return {"depth": depth, "photometric_confidence": conf, "norm_curv": nc}
+
+    # -- whole forward --------------------------------------------------------------------------
+    def forward(self, imgs, proj_matrices, depth_values, temperature=0.001):
+        if imgs.dim() != 5 or imgs.shape[2] != 3:
+            raise AssertionError(f"imgs must be [B,N,3,H,W], got {tuple(imgs.shape)}")
+        B, N, _, H, W = imgs.shape
+        if N < 2:
+            raise AssertionError("need at least one source view")
+        if H % 32 or W % 32:
+            raise RuntimeError(f"H and W must be divisible by 32 (got {H}x{W}); see SURVEY.md 8c fixture 6")
+        V = N - 1
+        dev = self.device
+        imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
+        depth_values = depth_values.to(device=dev, dtype=torch.float32).contiguous()
+        coef, epi = self.camera_setup(proj_matrices, B, N)
+        n = 2 * V * B
+        key = ("imgidx", B, N)
+        if getattr(self, "_imgidx_key", None) != key:
+            idx = torch.empty(2, V, B, dtype=torch.int32)
+            for v in range(V):
+                for b in range(B):
+                    idx[0, v, b] = b * N
+                    idx[1, v, b] = b * N + v + 1
+            self._imgidx = idx.reshape(-1).to(dev)
+            self._imgidx_key = key
+        feats = self.features.run(self.buf, imgs, self._imgidx, epi, n, H, W, temperature)
+        outputs, depth = {}, None
+        for s in range(len(self.ndepths)):
+            o = self.stage(s, feats[s], coef[s], depth_values, depth, B, V, H, W)
+            depth = o["depth"]
+            outputs[f"stage{s + 1}"] = o
+            outputs.update(o)
+        outputs["refined_depth"] = depth
+        return outputs

@@ -1,0 +1,415 @@
+"""Drop-in replacements for the reference's hot-path call surface.
+
+Same names, constructor arguments, forward signatures, output keys, error behaviour and
+state-dict keys/shapes as the reference, so they can be rebound inside an imported reference
+``models.model`` / ``models.module`` (see ``patch``) or used on their own:
+
+    homo_warping_3D(src_fea, src_proj, ref_proj, depth_values)          models/utils/warping.py:69
+    depth_regression(p, depth_values) / conf_regression(p, n=4)          models/module.py:373,382
+    DynamicConv(in_c, out_c, size_kernels, stride, bias, thresh_scale)   models/dynamic_conv.py:81
+    FeatureNet(base_channels, num_stage, stride, arch_mode)              models/module.py:201
+    CostRegNet(in_channels, base_channels, last_layer, full_res)         models/module.py:270
+    StageNet(num_mvs_stages)                                             models/model.py:11
+    CDSMVSNet(refine, ndepths, depth_interals_ratio, share_cr, ...)      models/model.py:97
+
+The torch ``nn`` sub-modules inside these classes are parameter CONTAINERS only (they give the
+state dict the reference's key names); they are never called.  Every forward runs the CUDA kernels
+of libcds_b200.so through the C ABI and raises if the library or a B200 is missing.  Public tensors
+are fp32 NCHW / NCDHW like the reference's; the fused paths keep channels-last fp16 internally.
+Inference only (eval mode): training-mode forwards raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib, weights as W
+from ._lib import ACT_NONE, ACT_TANH, call, ptr
+from .engine import STAGE_CHANNELS, Buffers, CascadeEngine, FeatureExtractor, Regulariser
+
+DEFAULT_STORAGE = torch.float16
+
+
+def _dev(t: torch.Tensor) -> torch.device:
+    if not t.is_cuda:
+        raise RuntimeError("cds_b200 ops run on a CUDA device (B200) only; got a CPU tensor. There is no CPU fallback.")
+    return t.device
+
+
+def _f32c(t):
+    return t.to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# functions
+# ------------------------------------------------------------------------------------------------
+def homo_warping_3D(src_fea, src_proj, ref_proj, depth_values):
+    """[B,C,H,W], [B,4,4], [B,4,4], [B,D] | [B,D,H,W] -> [B,C,D,H,W] (models/utils/warping.py:69-104)."""
+    dev = _dev(src_fea)
+    B, C, H, Wd = src_fea.shape
+    D = depth_values.shape[1]
+    per_pixel = depth_values.dim() == 4
+    if per_pixel and tuple(depth_values.shape) != (B, D, H, Wd):
+        raise RuntimeError(f"depth_values {tuple(depth_values.shape)} does not match features {tuple(src_fea.shape)}")
+    coef = torch.empty(B, 12, dtype=torch.float32, device=dev)
+    call("cds_warp_coeffs", ptr(_f32c(src_proj)), ptr(_f32c(ref_proj)), B, ptr(coef))
+    out = torch.empty(B, C, D, H, Wd, dtype=torch.float32, device=dev)
+    src, dep = _f32c(src_fea), _f32c(depth_values)
+    call("cds_homo_warp", ptr(src), ptr(coef), ptr(dep), int(per_pixel), B, C, D, H, Wd, ptr(out))
+    return out
+
+
+def depth_regression(p, depth_values):
+    """sum_d p_d * depth_d (models/module.py:373-379); depth_values [B,D] or [B,D,H,W]."""
+    dev = _dev(p)
+    B, D, H, Wd = p.shape
+    out = torch.empty(B, H, Wd, dtype=torch.float32, device=dev)
+    pc, dv = _f32c(p), _f32c(depth_values)
+    if dv.dim() == 1:
+        dv = dv.unsqueeze(0).expand(B, D).contiguous()
+    call("cds_softmax_regress", ptr(pc), ptr(dv), int(dv.dim() == 4), 1, B, D, H, Wd, ptr(out), None, None)
+    return out
+
+
+def conf_regression(p, n=4):
+    """p[d-1]+p[d]+p[d+1]+p[d+2] at d = clamp(trunc(sum_k k p_k)) (models/module.py:382-391)."""
+    if n != 4:
+        raise NotImplementedError("conf_regression: only the reference's n=4 window is implemented")
+    dev = _dev(p)
+    B, D, H, Wd = p.shape
+    out = torch.empty(B, H, Wd, dtype=torch.float32, device=dev)
+    pc = _f32c(p)
+    call("cds_softmax_regress", ptr(pc), None, 0, 1, B, D, H, Wd, None, ptr(out), None)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-cache plumbing shared by the modules
+# ------------------------------------------------------------------------------------------------
+class _CachedModule(nn.Module):
+    """Rebuilds the derived (folded / re-laid-out) weights when parameters may have changed."""
+
+    def _invalidate(self):
+        object.__setattr__(self, "_cache", None)
+
+    def __init__(self):
+        super().__init__()
+        self._invalidate()
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self._invalidate())
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode: bool = True):
+        self._invalidate()
+        return super().train(mode)
+
+    def _require_eval(self):
+        if self.training:
+            raise NotImplementedError(f"{type(self).__name__}: the CUDA path is inference-only; call .eval() first "
+                                      "(training-mode BatchNorm / autograd are out of scope, SURVEY.md 8f-3)")
+
+    def _sd(self, prefix=""):
+        return {prefix + k: v for k, v in self.state_dict().items()}
+
+
+def _nhwc(x, storage):
+    """fp32 NCHW -> channels-last storage tensor via the library's converter."""
+    B, C, H, Wd = x.shape
+    out = torch.empty(B, H, Wd, C, dtype=storage, device=x.device)
+    call("cds_nchw_to_nhwc", ptr(_f32c(x)), B, C, H, Wd, _lib.dtype_code(storage), ptr(out))
+    return out
+
+
+def _nchw(x):
+    B, H, Wd, C = x.shape
+    out = torch.empty(B, C, H, Wd, dtype=torch.float32, device=x.device)
+    call("cds_nhwc_to_nchw", ptr(x), B, C, H, Wd, _lib.dtype_code(x.dtype), ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# DynamicConv
+# ------------------------------------------------------------------------------------------------
+class DynamicConv(_CachedModule):
+    def __init__(self, in_c, out_c, size_kernels=(3, 5, 7), stride=1, bias=True, thresh_scale=0.01, **kwargs):
+        super().__init__()
+        if stride != 1:
+            raise NotImplementedError("DynamicConv: stride must be 1 (the reference's att_convs ignore stride, "
+                                      "models/dynamic_conv.py:85-86, so any other value breaks there too)")
+        self.size_kernels = tuple(size_kernels)
+        self.thresh_scale = thresh_scale
+        self.in_c, self.out_c = in_c, out_c
+        self.storage = kwargs.pop("storage", DEFAULT_STORAGE)
+        self.att_convs = nn.ModuleList([nn.Conv2d(in_c, 3, k, padding=(k - 1) // 2, bias=False) for k in size_kernels])
+        self.convs = nn.ModuleList([nn.Conv2d(in_c, out_c, k, padding=(k - 1) // 2, stride=stride, bias=bias)
+                                    for k in size_kernels])
+        hidden = kwargs.get("hidden_dim", 4)
+        if hidden != 4:
+            raise NotImplementedError("DynamicConv: hidden_dim must be 4")
+        self.att_weights = nn.Sequential(nn.Conv2d(len(size_kernels), hidden, 1, bias=False), nn.BatchNorm2d(hidden),
+                                         nn.ReLU(inplace=True), nn.Conv2d(hidden, len(size_kernels), 1, bias=False))
+        for p in self.att_convs.parameters():
+            torch.nn.init.normal_(p, std=0.1)
+
+    def forward(self, feature_vol, epipole=None, temperature=0.001):
+        self._require_eval()
+        dev = _dev(feature_vol)
+        if epipole is None:
+            raise TypeError("DynamicConv.forward needs the epipole (the reference dereferences it unconditionally)")
+        B, C, H, Wd = feature_vol.shape
+        if self._cache is None:
+            object.__setattr__(self, "_cache", W.pack_dynamic_conv(self._sd("x."), "x", self.in_c, self.out_c,
+                                                                   self.size_kernels, dev))
+        w = self._cache
+        dt = _lib.dtype_code(self.storage)
+        if C == 3:
+            x, mode = _f32c(feature_vol), 1
+        else:
+            x, mode = _nhwc(feature_vol, self.storage), 0
+        raw = torch.empty(B, H, Wd, self.out_c, dtype=self.storage, device=dev)
+        nc = torch.empty(B, 1, H, Wd, dtype=torch.float32, device=dev)
+        ks = (ctypes.c_int * len(w.ksizes))(*w.ksizes)
+        call("cds_dynamic_conv", ptr(x), mode, None, None, ACT_NONE, ptr(_f32c(epipole)), 1.0, ptr(w.w_att), ptr(w.w_conv),
+             ptr(w.bias), ptr(w.gate), B, self.in_c, self.out_c, H, Wd, len(w.ksizes), ks, float(temperature), dt,
+             ptr(raw), None, ptr(nc), None, 0, None)
+        return _nchw(raw), nc
+
+
+# ------------------------------------------------------------------------------------------------
+# FeatureNet
+# ------------------------------------------------------------------------------------------------
+class _Conv2dHolder(nn.Module):
+    """Parameter container with the reference Conv2d wrapper's key layout (``.conv.*``)."""
+
+    def __init__(self, conv):
+        super().__init__()
+        self.conv = conv
+
+
+class FeatureNet(_CachedModule):
+    def __init__(self, base_channels, num_stage=3, stride=4, arch_mode="unet", storage=DEFAULT_STORAGE):
+        super().__init__()
+        assert arch_mode in ["unet", "fpn"], "mode must be in 'unet' or 'fpn', but get:{}".format(arch_mode)
+        if base_channels != 8:
+            raise NotImplementedError("FeatureNet: the CUDA kernels are instantiated for base_channels=8 (the only "
+                                      "value the reference uses, models/model.py:127)")
+        self.arch_mode, self.stride, self.base_channels, self.num_stage = arch_mode, stride, base_channels, num_stage
+        self.storage = storage
+        b = base_channels
+        dyn = lambda ci, co, ks, bias: DynamicConv(ci, co, size_kernels=ks, bias=bias)
+        self.conv00 = _Conv2dHolder(dyn(3, b, (3, 7, 11), False))
+        self.conv01 = _Conv2dHolder(dyn(b, b, (3, 5, 7), False))
+        self.downsample1 = _Conv2dHolder(nn.Conv2d(b, 2 * b, 3, stride=2, padding=1, bias=False))
+        self.conv10 = _Conv2dHolder(dyn(2 * b, 2 * b, (3, 5), False))
+        self.conv11 = _Conv2dHolder(dyn(2 * b, 2 * b, (3, 5), False))
+        self.downsample2 = _Conv2dHolder(nn.Conv2d(2 * b, 4 * b, 3, stride=2, padding=1, bias=False))
+        self.conv20 = _Conv2dHolder(dyn(4 * b, 4 * b, (1, 3), False))
+        self.conv21 = _Conv2dHolder(dyn(4 * b, 4 * b, (1, 3), False))
+        self.out1 = dyn(4 * b, 4 * b, (1, 3), True)
+        self.inner1 = _Conv2dHolder(nn.Conv2d(6 * b, 2 * b, 1, bias=False))
+        self.inner2 = _Conv2dHolder(nn.Conv2d(3 * b, b, 1, bias=False))
+        self.out2 = dyn(2 * b, 2 * b, (1, 3), True)
+        self.out3 = dyn(b, b, (1, 3), True)
+        self.out_channels = [4 * b, 2 * b, b]
+
+    def forward(self, x, epipole=None, temperature=0.001):
+        self._require_eval()
+        dev = _dev(x)
+        if epipole is None:
+            raise TypeError("FeatureNet.forward needs the epipole")
+        B, C, H, Wd = x.shape
+        if H % 4 or Wd % 4:
+            raise RuntimeError(f"FeatureNet: H, W must be divisible by 4 (got {H}x{Wd})")
+        if self._cache is None:
+            object.__setattr__(self, "_cache", (FeatureExtractor(W.pack_feature(self._sd("feature."), dev), self.storage),
+                                                Buffers(dev)))
+        fx, buf = self._cache
+        idx = torch.arange(B, dtype=torch.int32, device=dev)
+        feats = fx.run(buf, _f32c(x), idx, _f32c(epipole), B, H, Wd, temperature)
+        out = {}
+        for s in range(3):
+            fea, ncsq, ncabs = feats[s]
+            out[f"stage{s + 1}"] = (_nchw(fea), ncsq.unsqueeze(1).clone(), ncabs.unsqueeze(1).clone())
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CostRegNet
+# ------------------------------------------------------------------------------------------------
+class _ConvBn3d(nn.Module):
+    def __init__(self, conv, ch):
+        super().__init__()
+        self.conv = conv
+        self.bn = nn.BatchNorm3d(ch, momentum=0.1)
+
+
+class CostRegNet(_CachedModule):
+    def __init__(self, in_channels, base_channels, last_layer=True, full_res=False, storage=DEFAULT_STORAGE):
+        super().__init__()
+        if full_res:
+            raise NotImplementedError("CostRegNet(full_res=True) is never constructed by the reference model "
+                                      "(models/model.py:130-134) and is not implemented")
+        if not last_layer:
+            raise NotImplementedError("CostRegNet(last_layer=False) is not implemented")
+        if base_channels != 8 or in_channels not in (8, 16, 32):
+            raise NotImplementedError("CostRegNet: kernels are instantiated for base_channels=8, in_channels in {8,16,32}")
+        self.last_layer, self.in_channels, self.storage = last_layer, in_channels, storage
+        b = base_channels
+        c3 = lambda ci, co, s: _ConvBn3d(nn.Conv3d(ci, co, 3, stride=s, padding=1, bias=False), co)
+        d3 = lambda ci, co: _ConvBn3d(nn.ConvTranspose3d(ci, co, 3, stride=2, padding=1, output_padding=1, bias=False), co)
+        self.conv0 = c3(in_channels, b, 1)
+        self.conv1, self.conv2 = c3(b, 2 * b, 2), c3(2 * b, 2 * b, 1)
+        self.conv3, self.conv4 = c3(2 * b, 4 * b, 2), c3(4 * b, 4 * b, 1)
+        self.conv5, self.conv6 = c3(4 * b, 8 * b, 2), c3(8 * b, 8 * b, 1)
+        self.conv7, self.conv9, self.conv11 = d3(8 * b, 4 * b), d3(4 * b, 2 * b), d3(2 * b, b)
+        self.prob = nn.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
+
+    def _engine(self, dev):
+        if self._cache is None:
+            object.__setattr__(self, "_cache", (Regulariser(W.pack_costreg(self._sd("cr."), "cr", dev), self.storage), Buffers(dev)))
+        return self._cache
+
+    def forward(self, x):
+        """[B,C,D,H,W] fp32 -> [B,1,D,H,W] fp32 logits (models/module.py:305-315)."""
+        self._require_eval()
+        dev = _dev(x)
+        B, C, D, H, Wd = x.shape
+        reg, buf = self._engine(dev)
+        # NCDHW -> NDHWC: D is folded into the image-batch axis of the 2-D converter per batch item
+        vol = torch.empty(B, D, H, Wd, C, dtype=self.storage, device=dev)
+        call("cds_nchw_to_nhwc", ptr(_f32c(x)), B, C, D * H, Wd, _lib.dtype_code(self.storage), ptr(vol))
+        logits = reg.run(buf, "cr", vol, B, D, H, Wd)
+        return logits.unsqueeze(1).clone()
+
+
+# ------------------------------------------------------------------------------------------------
+# StageNet
+# ------------------------------------------------------------------------------------------------
+class _ConvBnReLU2d(nn.Module):
+    def __init__(self, ci, co):
+        super().__init__()
+        self.conv = nn.Conv2d(ci, co, 3, stride=1, padding=1, bias=False)
+        self.bn = nn.BatchNorm2d(co)
+
+
+class StageNet(_CachedModule):
+    def __init__(self, num_mvs_stages=3, storage=DEFAULT_STORAGE):
+        super().__init__()
+        self.storage = storage
+        self.vis = nn.ModuleList([nn.Sequential(_ConvBnReLU2d(2, 16), _ConvBnReLU2d(16, 16), _ConvBnReLU2d(16, 16),
+                                                nn.Conv2d(16, 1, 1), nn.Sigmoid()) for _ in range(num_mvs_stages)])
+
+    def forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization, prob_volume_init=None,
+                stage_idx=0, gt_depth=None):
+        """Reference signature (models/model.py:16-17).  features: list of N-1 dicts
+        {"ref": (fea[B,C,h,w], nc_sum[B,1,h,w], nc_abs[B,1,h,w]), "src": (...)}; proj_matrices [B,N,2,4,4];
+        depth_values [B,D,h,w].  Returns {"depth", "photometric_confidence", "norm_curv"}."""
+        self._require_eval()
+        if prob_volume_init is not None or gt_depth is not None:
+            raise NotImplementedError("StageNet: prob_volume_init / gt_depth belong to the training path (out of scope)")
+        assert len(features) == proj_matrices.shape[1] - 1, "Different number of images and projection matrices"
+        assert depth_values.shape[1] == num_depth, "depth_values.shape[1]:{}  num_depth:{}".format(depth_values.shape[1], num_depth)
+        if not isinstance(cost_regularization, CostRegNet):
+            raise TypeError("StageNet: cost_regularization must be the cds_mvsnet_b200 CostRegNet")
+        ref0 = features[0]["ref"][0]
+        dev = _dev(ref0)
+        B, C, h, w = ref0.shape
+        V, D = len(features), num_depth
+        dt = _lib.dtype_code(self.storage)
+        if self._cache is None:
+            sd = self._sd("stage_net.")
+            object.__setattr__(self, "_cache", ([W.pack_visnet(sd, f"stage_net.vis.{s}", dev) for s in range(len(self.vis))],
+                                                Buffers(dev)))
+        vis_w, buf = self._cache
+        f32 = torch.float32
+        ref_fea = torch.stack([_nhwc(f["ref"][0], self.storage) for f in features])     # [V,B,h,w,C]
+        src_fea = torch.stack([_nhwc(f["src"][0], self.storage) for f in features])
+        ref_ncsq = torch.stack([_f32c(f["ref"][1]).reshape(B, h, w) for f in features])
+        src_ncsq = torch.stack([_f32c(f["src"][1]).reshape(B, h, w) for f in features])
+        ref_ncabs = torch.stack([_f32c(f["ref"][2]).reshape(B, h, w) for f in features])
+        pm = _f32c(proj_matrices)
+        coef = torch.empty(1, B, V, 12, dtype=f32, device=dev)
+        arr = (ctypes.c_void_p * 1)(pm.data_ptr())
+        call("cds_camera_setup", arr, 1, 0, B, V + 1, ptr(coef), None)
+        samples = _f32c(depth_values)
+        entropy = torch.empty(V, B, h, w, dtype=f32, device=dev)
+        call("cds_costvol_entropy", ptr(ref_fea), ptr(src_fea), ptr(coef), ptr(samples), V, B, C, D, h, w, dt, ptr(entropy))
+        vis = torch.empty(V, B, h, w, dtype=f32, device=dev)
+        call("cds_visnet", ptr(entropy), ptr(ref_ncabs), ptr(vis_w[stage_idx]), V * B, h, w, ptr(vis))
+        volume = torch.empty(B, D, h, w, C, dtype=self.storage, device=dev)
+        call("cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef), ptr(samples), ptr(vis), V, B, C, D, h, w, dt, ptr(volume))
+        nc = torch.empty(B, 1, h, w, dtype=f32, device=dev)
+        call("cds_nc_mean", ptr(ref_ncsq), ptr(src_ncsq), V, B * h * w, ptr(nc))
+        reg, rbuf = cost_regularization._engine(dev)
+        logits = reg.run(rbuf, "cr", volume, B, D, h, w)
+        depth = torch.empty(B, h, w, dtype=f32, device=dev)
+        conf = torch.empty(B, h, w, dtype=f32, device=dev)
+        call("cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w, ptr(depth), ptr(conf), None)
+        return {"depth": depth, "photometric_confidence": conf, "norm_curv": nc}
+
+
+# ------------------------------------------------------------------------------------------------
+# CDSMVSNet
+# ------------------------------------------------------------------------------------------------
+class CDSMVSNet(_CachedModule):
+    def __init__(self, refine=False, ndepths=(48, 32, 8), depth_interals_ratio=(4, 2, 1), share_cr=False,
+                 grad_method="detach", arch_mode="fpn", cr_base_chs=(8, 8, 8), storage=DEFAULT_STORAGE):
+        super().__init__()
+        if refine:
+            raise NotImplementedError("CDSMVSNet(refine=True): the Refinement network is outside the hot path "
+                                      "(SURVEY.md 8f-4); construct with refine=False")
+        assert len(ndepths) == len(depth_interals_ratio)
+        if len(ndepths) > 3:
+            raise NotImplementedError("at most 3 stages (the reference defines scales for stage1..3 only)")
+        self.refine, self.share_cr, self.ndepths = refine, share_cr, tuple(ndepths)
+        self.depth_interals_ratio, self.grad_method = tuple(depth_interals_ratio), grad_method
+        self.arch_mode, self.cr_base_chs, self.num_stage = arch_mode, tuple(cr_base_chs), len(ndepths)
+        self.storage = storage
+        self.stage_infos = {"stage1": {"scale": 4.0}, "stage2": {"scale": 2.0}, "stage3": {"scale": 1.0}}
+        self.feature = FeatureNet(base_channels=8, arch_mode=arch_mode, storage=storage)
+        self.stage_net = StageNet(num_mvs_stages=len(ndepths), storage=storage)
+        if share_cr:
+            raise NotImplementedError("share_cr=True cannot work in the reference either: one CostRegNet cannot take "
+                                      "32-, 16- and 8-channel volumes (models/model.py:130)")
+        self.cost_regularization = nn.ModuleList([CostRegNet(in_channels=self.feature.out_channels[i],
+                                                             base_channels=self.cr_base_chs[i], storage=storage)
+                                                  for i in range(self.num_stage)])
+
+    def engine(self, dev) -> CascadeEngine:
+        if self._cache is None:
+            mw = W.pack_model(self.state_dict(), self.num_stage, dev)
+            object.__setattr__(self, "_cache", CascadeEngine(mw, self.ndepths, self.depth_interals_ratio, self.storage, dev))
+        return self._cache
+
+    def forward(self, imgs, proj_matrices, depth_values, gt_depths=None, temperature=0.001):
+        """imgs [B,N,3,H,W], proj_matrices {"stageK": [B,N,2,4,4]}, depth_values [B,Dtot] -> the reference's output
+        dict (models/model.py:140-223): per-stage dicts + top-level copies of the last stage + refined_depth."""
+        self._require_eval()
+        if gt_depths is not None:
+            raise NotImplementedError("gt_depths is a training input (out of scope)")
+        dev = _dev(imgs)
+        out = self.engine(dev).forward(imgs, proj_matrices, depth_values, temperature)
+        # fresh tensors: the engine's buffers are reused by the next call
+        res = {}
+        for k, v in out.items():
+            res[k] = {kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone()
+        return res
+
+
+# ------------------------------------------------------------------------------------------------
+def patch(models_model=None, models_module=None):
+    """Rebind the hot-path names inside an imported reference ``models.model`` / ``models.module`` so that
+    the reference's own driver code constructs and calls the CUDA implementations."""
+    if models_model is not None:
+        for name, obj in (("homo_warping_3D", homo_warping_3D), ("depth_regression", depth_regression),
+                          ("conf_regression", conf_regression), ("CostRegNet", CostRegNet), ("StageNet", StageNet),
+                          ("FeatureNet", FeatureNet), ("CDSMVSNet", CDSMVSNet)):
+            setattr(models_model, name, obj)
+    if models_module is not None:
+        for name, obj in (("DynamicConv", DynamicConv), ("depth_regression", depth_regression),
+                          ("conf_regression", conf_regression), ("CostRegNet", CostRegNet), ("FeatureNet", FeatureNet)):
+            setattr(models_module, name, obj)

@@ -1,0 +1,154 @@
+"""Derived weight caches for the CUDA kernels.
+
+The stored parameters keep the reference's names/shapes (so its checkpoints load unchanged); what
+the kernels consume -- BatchNorm folded into conv weight/bias, tap-major channels-last weight
+layouts, packed gate MLPs -- is derived here from a state dict and must be rebuilt whenever the
+parameters change (``load_state_dict`` / ``.to()``).  All folding is done in fp64, stored fp32.
+
+Reference layouts being re-laid-out:
+  nn.Conv2d weight [Cout,Cin,k,k], nn.Conv3d [Cout,Cin,3,3,3], nn.ConvTranspose3d [Cin,Cout,3,3,3]
+  (models/module.py:102,146 ), BatchNorm eval fold (models/module.py:104,148,194).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+
+BN_EPS = 1e-5
+
+# FeatureNet layer table (models/module.py:211-234): name -> (Cin, Cout, kernel sizes, state-dict prefix)
+DYN_LAYERS = {
+    "conv00": (3, 8, (3, 7, 11), "feature.conv00.conv"), "conv01": (8, 8, (3, 5, 7), "feature.conv01.conv"),
+    "conv10": (16, 16, (3, 5), "feature.conv10.conv"), "conv11": (16, 16, (3, 5), "feature.conv11.conv"),
+    "conv20": (32, 32, (1, 3), "feature.conv20.conv"), "conv21": (32, 32, (1, 3), "feature.conv21.conv"),
+    "out1": (32, 32, (1, 3), "feature.out1"), "out2": (16, 16, (1, 3), "feature.out2"),
+    "out3": (8, 8, (1, 3), "feature.out3"),
+}
+COSTREG_CONVS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
+COSTREG_DECONVS = ("conv7", "conv9", "conv11")
+
+
+def _bn_fold(sd, prefix):
+    g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
+    m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
+    scale = g / torch.sqrt(v + BN_EPS)
+    return scale, b - m * scale
+
+
+@dataclass
+class DynWeights:
+    cin: int
+    cout: int
+    ksizes: tuple
+    w_att: torch.Tensor    # [sum k*k, Cin, 4]
+    w_conv: torch.Tensor   # [sum k*k, Cin, Cout]
+    bias: torch.Tensor | None  # [K, Cout]
+    gate: torch.Tensor     # 4K + 4 + 4K floats
+
+
+def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
+    att, conv, bias = [], [], []
+    for i, k in enumerate(ksizes):
+        a = sd[f"{prefix}.att_convs.{i}.weight"].double()          # [3,Cin,k,k]
+        a = a.permute(2, 3, 1, 0).reshape(k * k, cin, 3)
+        att.append(torch.cat((a, torch.zeros(k * k, cin, 1, dtype=torch.float64, device=a.device)), 2))
+        w = sd[f"{prefix}.convs.{i}.weight"].double()               # [Cout,Cin,k,k]
+        conv.append(w.permute(2, 3, 1, 0).reshape(k * k, cin, cout))
+        bk = f"{prefix}.convs.{i}.bias"
+        if bk in sd:
+            bias.append(sd[bk].double())
+    K = len(ksizes)
+    scale, shift = _bn_fold(sd, f"{prefix}.att_weights.1")
+    w1 = sd[f"{prefix}.att_weights.0.weight"].double().reshape(4, K) * scale.reshape(4, 1)
+    w2 = sd[f"{prefix}.att_weights.3.weight"].double().reshape(K, 4)
+    gate = torch.cat((w1.reshape(-1), shift.reshape(-1), w2.reshape(-1)))
+    f32 = dict(dtype=torch.float32, device=device)
+    return DynWeights(cin, cout, tuple(ksizes), torch.cat(att).to(**f32).contiguous(), torch.cat(conv).to(**f32).contiguous(),
+                      torch.stack(bias).to(**f32).contiguous() if bias else None, gate.to(**f32).contiguous())
+
+
+def pack_conv2d(sd, key, device) -> torch.Tensor:
+    w = sd[key].double()                                            # [Cout,Cin,k,k]
+    co, ci, k, _ = w.shape
+    return w.permute(2, 3, 1, 0).reshape(k * k, ci, co).to(dtype=torch.float32, device=device).contiguous()
+
+
+def pack_visnet(sd, prefix, device) -> torch.Tensor:
+    parts = []
+    for j in range(3):
+        scale, shift = _bn_fold(sd, f"{prefix}.{j}.bn")
+        w = sd[f"{prefix}.{j}.conv.weight"].double() * scale.reshape(-1, 1, 1, 1)   # [16,Cin,3,3]
+        parts += [w.permute(2, 3, 1, 0).reshape(-1), shift.reshape(-1)]
+    parts += [sd[f"{prefix}.3.weight"].double().reshape(-1), sd[f"{prefix}.3.bias"].double().reshape(-1)]
+    return torch.cat(parts).to(dtype=torch.float32, device=device).contiguous()
+
+
+@dataclass
+class Conv3dWeights:
+    cin: int
+    cout: int
+    w: torch.Tensor      # [27, Cin, Cout] fp32, BN scale folded
+    bias: torch.Tensor   # [Cout]
+    extra: dict = field(default_factory=dict)   # tensor-core re-layouts live here
+
+
+def pack_conv3d(sd, prefix, transposed, device) -> Conv3dWeights:
+    scale, shift = _bn_fold(sd, prefix + ".bn")
+    w = sd[prefix + ".conv.weight"].double()
+    if transposed:   # [Cin,Cout,3,3,3]
+        ci, co = w.shape[:2]
+        w = (w * scale.reshape(1, -1, 1, 1, 1)).permute(2, 3, 4, 0, 1)
+    else:            # [Cout,Cin,3,3,3]
+        co, ci = w.shape[:2]
+        w = (w * scale.reshape(-1, 1, 1, 1, 1)).permute(2, 3, 4, 1, 0)
+    f32 = dict(dtype=torch.float32, device=device)
+    return Conv3dWeights(ci, co, w.reshape(27, ci, co).to(**f32).contiguous(), shift.to(**f32).contiguous())
+
+
+@dataclass
+class CostRegWeights:
+    layers: dict          # name -> Conv3dWeights
+    prob: torch.Tensor    # [27, 8]
+
+
+def pack_costreg(sd, prefix, device) -> CostRegWeights:
+    layers = {n: pack_conv3d(sd, f"{prefix}.{n}", False, device) for n in COSTREG_CONVS}
+    layers.update({n: pack_conv3d(sd, f"{prefix}.{n}", True, device) for n in COSTREG_DECONVS})
+    p = sd[prefix + ".prob.weight"].double()                        # [1,8,3,3,3]
+    prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(dtype=torch.float32, device=device).contiguous()
+    return CostRegWeights(layers, prob)
+
+
+@dataclass
+class FeatureWeights:
+    dyn: dict             # name -> DynWeights
+    downsample1: torch.Tensor
+    downsample2: torch.Tensor
+    inner1: torch.Tensor  # [48,16]
+    inner2: torch.Tensor  # [24,8]
+
+
+def pack_feature(sd, device) -> FeatureWeights:
+    dyn = {n: pack_dynamic_conv(sd, pre, ci, co, ks, device) for n, (ci, co, ks, pre) in DYN_LAYERS.items()}
+    return FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
+                          pack_conv2d(sd, "feature.downsample2.conv.weight", device),
+                          pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16).contiguous(),
+                          pack_conv2d(sd, "feature.inner2.conv.weight", device).reshape(24, 8).contiguous())
+
+
+@dataclass
+class ModelWeights:
+    feature: FeatureWeights
+    vis: list
+    costreg: list
+
+
+def pack_model(sd, n_stages: int, device, share_cr: bool = False) -> ModelWeights:
+    sd = {k: v.detach() for k, v in sd.items()}
+    vis = [pack_visnet(sd, f"stage_net.vis.{s}", device) for s in range(n_stages)]
+    if share_cr:
+        cr = [pack_costreg(sd, "cost_regularization", device)] * n_stages
+    else:
+        cr = [pack_costreg(sd, f"cost_regularization.{s}", device) for s in range(n_stages)]
+    return ModelWeights(pack_feature(sd, device), vis, cr)

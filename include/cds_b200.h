@@ -1,0 +1,152 @@
+/* cds_b200.h -- C ABI of libcds_b200.so: the CDS-MVSNet depth-inference hot path on B200 (sm_100a).
+ *
+ * The reference (TruongKhang/cds-mvsnet) has no FFI/plugin layer: its hot path is Python calling
+ * ATen/cuDNN.  This header is the boundary a replacement binds instead -- plain pointers, sizes and
+ * a CUDA stream, no torch types.  Each entry names the reference code it replaces (file:line into
+ * the reference tree).  The Python shims in cds_mvsnet_b200/ (ctypes) are the intended callers;
+ * INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative CDS_E* argument
+ *     code; cds_last_error_string() describes the last failure on the calling thread
+ *   - all pointers are DEVICE pointers unless stated; the caller owns every buffer, nothing is
+ *     allocated or freed inside, inputs are never written
+ *   - work is enqueued on `stream` and is CUDA-graph capturable (no host sync inside)
+ *   - thread-safe / re-entrant: no mutable global state
+ *   - activation tensors are channels-last ([n,H,W,C] / [B,D,H,W,C]) in the storage type `dtype`
+ *     (CDS_F16: fp16 storage with fp32 accumulation -- the production setting; CDS_F32: fp32
+ *     storage for tight parity checks); per-pixel maps, hypotheses and outputs are fp32
+ */
+#ifndef CDS_B200_H
+#define CDS_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDS_F32 0
+#define CDS_F16 1
+
+#define CDS_ACT_NONE 0
+#define CDS_ACT_LRELU 1 /* LeakyReLU(0.1), models/module.py:69 */
+#define CDS_ACT_TANH 2  /* models/module.py:223,230,232 */
+
+#define CDS_EARG (-1)
+#define CDS_ESHAPE (-2)
+#define CDS_EUNSUPPORTED (-3)
+
+int cds_version(void);
+const char* cds_last_error_string(void);
+/* 0 iff the current device is sm_100 (the only target this library is built for). */
+int cds_check_device(void);
+
+/* ---- camera algebra ------------------------------------------------------------------------ */
+/* coef[b] = {R row-major 9, t 3} of src_proj[b] @ inv(ref_proj[b]); 4x4 row-major fp32 inputs.
+ * Replaces models/utils/warping.py:80-82 (torch.inverse + matmul), evaluated in fp64. */
+int cds_warp_coeffs(const float* src_proj, const float* ref_proj, int B, float* coef, cudaStream_t stream);
+
+/* For the whole cascade at once: proj_stages is a HOST array of n_stages device pointers to the data
+ * layer's [B,N,2,4,4] matrices.  Writes coef [n_stages,B,N-1,12] (projection composed as
+ * K[:3,:3] @ E[:3,:4], models/model.py:40-43, then the warp coefficients above) and, if non-null,
+ * epipoles [2,N-1,B,2] = xy of the epipole in (0: the ref image, 1: the src image) from stage `epi_stage`'s cameras
+ * (models/dynamic_conv.py:19-47 compute_Fmatrix/compute_epipole, called at models/model.py:152-158). */
+int cds_camera_setup(const float* const* proj_stages, int n_stages, int epi_stage, int B, int N, float* coef,
+                     float* epipoles, cudaStream_t stream);
+
+/* ---- A1: plane-sweep warp, exact reference contract ---------------------------------------- */
+/* homo_warping_3D (models/utils/warping.py:69-104) with the 4x4 algebra already reduced to coef:
+ * src_fea [B,C,h,w] fp32 NCHW, depth [B,D] (depth_per_pixel=0) or [B,D,h,w] (=1),
+ * out [B,C,D,h,w] fp32.  Bilinear, zero padding, align_corners=True pixel coordinates. */
+int cds_homo_warp(const float* src_fea, const float* coef, const float* depth, int depth_per_pixel, int B, int C, int D,
+                  int h, int w, float* out, cudaStream_t stream);
+
+/* ---- A9: depth hypotheses ------------------------------------------------------------------- */
+/* depth_values [B,Dtot].  prev_depth == NULL: D planes uniformly spanning [dv[0], dv[-1]]
+ * (models/module.py:425-433).  Otherwise prev_depth [B,hp,wp] is bilinearly up-sampled to (H,W)
+ * (models/model.py:177-182), hypotheses cur - ((D-1)/2)*step + d*step with
+ * step = ratio * (dv[1]-dv[0]) are clamped to [dv[0], dv[-1]] (models/module.py:398-417) and resized
+ * to the stage grid (models/model.py:191-193).  out [B,D,H/scale,W/scale] fp32, scale in {1,2,4}. */
+int cds_depth_hypotheses(const float* depth_values, int Dtot, const float* prev_depth, int hp, int wp, int B, int D,
+                         float ratio, int H, int W, int scale, float* out, cudaStream_t stream);
+
+/* ---- A2: fused warp + cost volume (two sweeps around the visibility net) --------------------- */
+/* ref_fea/src_fea [V,B,h,w,C] channels-last (one ref map per source view: the ref features depend on
+ * the pair's epipole, models/model.py:154-161), coef [B,V,12], depth [B,D,h,w].
+ * entropy[v,b,y,x] = H(softmax_d(sum_c ref*warp_d))  (models/model.py:44-50). C in {8,16,32}. */
+int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* coef, const float* depth, int V, int B,
+                        int C, int D, int h, int w, int dtype, float* entropy, cudaStream_t stream);
+/* volume[b,d,y,x,:] = sum_v vis_v * ref_v (.) warp_{v,d} / (sum_v vis_v + 1e-6), vis [V,B,h,w]
+ * (models/model.py:57-59,74); volume [B,D,h,w,C] channels-last. */
+int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float* coef, const float* depth,
+                          const float* vis, int V, int B, int C, int D, int h, int w, int dtype, void* volume,
+                          cudaStream_t stream);
+/* out[i] = sum_v (ref_nc_sum[v,i] + src_nc_sum[v,i]) / 2 / V   (models/model.py:60,79) */
+int cds_nc_mean(const float* ref_nc_sum, const float* src_nc_sum, int V, long long n, float* out, cudaStream_t stream);
+
+/* ---- A3: visibility net ----------------------------------------------------------------------- */
+/* StageNet.vis[s] (models/model.py:14,51; ConvBnReLU models/module.py:169-198), BN folded, as one
+ * kernel.  entropy, curv, vis: [n,h,w] fp32.  wpack: cds_visnet_weight_floats() floats laid out as
+ * L1[9][2][16] b1[16] L2[9][16][16] b2[16] L3[9][16][16] b3[16] w4[16] b4[1]. */
+int cds_visnet_weight_floats(void);
+int cds_visnet(const float* entropy, const float* curv, const float* wpack, int n, int h, int w, float* vis,
+               cudaStream_t stream);
+
+/* ---- A4: 3-D regulariser blocks --------------------------------------------------------------- */
+/* Conv3d block (models/module.py:80-122): k3 p1, stride 1|2, BN folded into wgt [27][Cin][Cout] fp32
+ * (tap = (kd*3+kh)*3+kw) and bias [Cout], optional ReLU.  in [B,D,H,W,Cin] -> out [B,ceil(D/s),..,Cout]. */
+int cds_conv3d_k3(const void* in, const float* wgt, const float* bias, int B, int Cin, int Cout, int D, int H, int W,
+                  int stride, int relu, int dtype, void* out, cudaStream_t stream);
+/* Deconv3d block (models/module.py:125-166): ConvTranspose3d k3 s2 p1 op1 + BN + ReLU, then `+ skip`
+ * (models/module.py:310-312; skip may be NULL).  wgt [27][Cin][Cout]; out/skip [B,2D,2H,2W,Cout]. */
+int cds_deconv3d_k3s2(const void* in, const float* wgt, const float* bias, const void* skip, int B, int Cin, int Cout,
+                      int D, int H, int W, int dtype, void* out, cudaStream_t stream);
+/* prob head: plain Conv3d(8,1,3,p=1,bias=False) (models/module.py:303) -> fp32 logits [B,D,H,W]. */
+int cds_prob_conv(const void* in, const float* wgt, int B, int Cin, int D, int H, int W, int dtype, float* logits,
+                  cudaStream_t stream);
+
+/* ---- A5: softmax over D + soft-argmin depth + 4-plane confidence ------------------------------ */
+/* logits [B,D,h,w] fp32 (input_is_prob=1: already probabilities, as depth_regression/conf_regression
+ * receive them, models/module.py:373-391).  depth [B,D] or [B,D,h,w].  Any of depth_out [B,h,w],
+ * conf_out [B,h,w], prob_out [B,D,h,w] may be NULL.  (models/model.py:90-92) */
+int cds_softmax_regress(const float* logits, const float* depth, int depth_per_pixel, int input_is_prob, int B, int D,
+                        int h, int w, float* depth_out, float* conf_out, float* prob_out, cudaStream_t stream);
+
+/* ---- A6/A7: DynamicConv and the feature extractor's 2-D plumbing ------------------------------ */
+/* DynamicConv.forward (models/dynamic_conv.py:97-122) for n images in one launch.
+ *   x: in_mode 0 -> [n,H,W,Cin] channels-last `dtype`; in_mode 1 -> planar fp32 images [*,3,H,W], item i
+ *      reads image img_index[i] (NULL: i)
+ *   in_stats/in_act: InstanceNorm statistics ([n,Cin,2] fp64 sum, sum of squares) + activation applied
+ *      to x while loading (the producer's norm, models/module.py:66-69); NULL = x is used as is
+ *   epipole [n,2] full-resolution (x,y), multiplied by epi_scale (1, 1/2, 1/4: models/module.py:239,242)
+ *   w_att per branch [k*k][Cin][4] (a,b,c,0); w_conv per branch [k*k][Cin][Cout]; bias [K][Cout] or NULL
+ *   gate: W1 [4][K] and b1 [4] with BatchNorm2d folded, W2 [K][4] (models/dynamic_conv.py:89-92)
+ *   kernel_sizes: HOST array of num_kernels odd sizes <= 11
+ *   out_raw [n,H,W,Cout] (pre-norm), out_stats [n,Cout,2] fp64 ACCUMULATED (zero them first)
+ *   norm_curv / nc_abs [n,H,W] optional; nc_sq accumulates the stage curvature term
+ *      (nc_a^2+nc_b^2+nc_c^2)/3 (models/module.py:250,257,264): nc_mode 0 = write, 1 = add, 2 = add and /3 */
+int cds_dynamic_conv(const void* x, int in_mode, const int* img_index, const double* in_stats, int in_act,
+                     const float* epipole, float epi_scale, const float* w_att, const float* w_conv, const float* bias,
+                     const float* gate, int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes,
+                     float temperature, int dtype, void* out_raw, double* out_stats, float* norm_curv, float* nc_sq,
+                     int nc_mode, float* nc_abs, cudaStream_t stream);
+/* FeatureNet.downsample1/2 (models/module.py:214,218): 3x3 stride 2 pad 1, wgt [9][Cin][Cout]. */
+int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
+                     int W, int dtype, void* out, double* out_stats, cudaStream_t stream);
+/* FeatureNet.inner1/2 (models/module.py:253-254,260-261): 1x1 conv over cat(nearest-up2(a), b);
+ * a [n,H/2,W/2,Ca], b [n,H,W,Cb], wgt [Ca+Cb][Cout]. */
+int cds_conv2d_1x1_cat(const void* a, const double* a_stats, int a_act, const void* b, const double* b_stats, int b_act,
+                       const float* wgt, int n, int Ca, int Cb, int Cout, int H, int W, int dtype, void* out,
+                       double* out_stats, cudaStream_t stream);
+/* InstanceNorm2d(affine=False, eps 1e-5, biased variance) + activation, materialised. */
+int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C, int H, int W, int dtype, void* out,
+                     cudaStream_t stream);
+/* fp32 NCHW <-> channels-last storage type, for the op-level drop-ins' public signatures. */
+int cds_nchw_to_nhwc(const float* in, int n, int C, int H, int W, int dtype, void* out, cudaStream_t stream);
+int cds_nhwc_to_nchw(const void* in, int n, int C, int H, int W, int dtype, float* out, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDS_B200_H */

@@ -1,0 +1,121 @@
+"""End-to-end parity of the fused cascade (drop-in CDSMVSNet) against golden outputs of the live reference
+and against the CPU oracle.  The bar is north_star's: depth within 1e-3 relative L1 of the reference."""
+import os
+
+import pytest
+import torch
+
+import cds_mvsnet_b200 as C
+from cds_mvsnet_b200 import synthetic
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+T = 0.01
+DEV = "cuda"
+DEPTH_REL_L1 = 1e-3      # north_star tolerance (fp16 storage, fp32 accumulate)
+DEPTH_REL_L1_F32 = 2e-5  # fp32-storage build: re-association noise only
+torch.set_grad_enabled(False)
+
+
+def build(sd, nd, ratios, storage):
+    m = C.CDSMVSNet(refine=False, ndepths=nd, depth_interals_ratio=ratios, storage=storage)
+    m.load_state_dict({k: v for k, v in sd.items() if k in m.state_dict()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def cfg_of(g):
+    W, H, N, B, Dtot = (int(v) for v in g["cfg"][:5])
+    nd = tuple(int(v) for v in g["cfg"][5:])
+    return dict(W=W, H=H, N=N, B=B, Dtot=Dtot, ndepths=nd, ratios=tuple(float(r) for r in g["ratios"]),
+                interval=float(g["interval"]))
+
+
+def run(model, s):
+    return model(s.imgs.to(DEV), {k: v.to(DEV) for k, v in s.proj_matrices.items()}, s.depth_values.to(DEV), temperature=T)
+
+
+@pytest.mark.parametrize("storage", [torch.float32, torch.float16])
+@pytest.mark.parametrize("tag,family", [("e2e_cfg1_noise", "noise"), ("e2e_small3_plane", "plane"), ("e2e_small3_noise", "noise")])
+def test_cascade_golden(golden, pretrained_sd, tag, family, storage):
+    g = golden(tag)
+    cfg = cfg_of(g)
+    s = synthetic.make_sample(cfg, family, seed=0)
+    model = build(pretrained_sd, cfg["ndepths"], cfg["ratios"], storage)
+    out = run(model, s)
+    assert set(out) >= {"depth", "photometric_confidence", "norm_curv", "refined_depth", "stage1"}
+    tol = DEPTH_REL_L1_F32 if storage == torch.float32 else DEPTH_REL_L1
+    for st in range(len(cfg["ndepths"])):
+        nm = f"stage{st + 1}"
+        ref_d, ref_c, ref_n = g[f"{nm}_depth"], g[f"{nm}_photometric_confidence"], g[f"{nm}_norm_curv"]
+        d = out[nm]["depth"].cpu()
+        assert d.shape == ref_d.shape
+        rel = O.rel_l1(d, ref_d)
+        conf_err = (out[nm]["photometric_confidence"].cpu() - ref_c).abs().mean().item()
+        print(f"{tag} {nm} storage={storage}: depth rel-L1 {rel:.3e}  conf |err| {conf_err:.3e}")
+        assert rel < tol, (nm, rel)
+        assert conf_err < (1e-3 if storage == torch.float32 else 2e-2)
+        assert O.rel_l1(out[nm]["norm_curv"].cpu(), ref_n) < (1e-4 if storage == torch.float32 else 1e-2)
+    assert torch.equal(out["refined_depth"], out["depth"])
+    if family == "plane":
+        assert (out["depth"].cpu() - s.gt_depth).abs().mean() < 8.0     # known answer: the plane is recovered
+
+
+def test_cascade_random_weights_vs_oracle():
+    """Weights the golden files do not cover: random init with randomised BN statistics, oracle computed here."""
+    cfg = dict(W=128, H=96, N=3, ndepths=(16, 8, 8), ratios=(4.0, 1.5, 0.75), B=1, Dtot=192, interval=2.65)
+    sd = synthetic.random_state_dict(cfg["ndepths"])
+    s = synthetic.make_sample(cfg, "plane", seed=2)
+    ref = O.cdsmvsnet_forward(sd, s.imgs, s.proj_matrices, s.depth_values, cfg["ndepths"], cfg["ratios"], T)
+    out = run(build(sd, cfg["ndepths"], cfg["ratios"], torch.float32), s)
+    for st in (1, 2, 3):
+        assert O.rel_l1(out[f"stage{st}"]["depth"].cpu(), ref[f"stage{st}"]["depth"]) < 1e-4
+    out16 = run(build(sd, cfg["ndepths"], cfg["ratios"], torch.float16), s)
+    assert O.rel_l1(out16["depth"].cpu(), ref["depth"]) < DEPTH_REL_L1
+
+
+def test_stagenet_dropin_vs_oracle(pretrained_sd):
+    """StageNet with the reference's own signature, fed reference-layout (NCHW fp32) features."""
+    torch.manual_seed(7)
+    B, V, D, h, w, Cc, st = 1, 2, 8, 32, 40, 16, 1
+    s = synthetic.make_sample(dict(W=2 * w, H=2 * h, N=V + 1, ndepths=(8,), ratios=(1.0,), B=B, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage3"]
+    feats = [{k: (torch.tanh(torch.randn(B, Cc, h, w)), torch.rand(B, 1, h, w) * 0.01, torch.rand(B, 1, h, w) * 0.1)
+              for k in ("ref", "src")} for _ in range(V)]
+    dv = (425 + 60 * torch.arange(D).float()).reshape(1, D, 1, 1) + 5 * torch.rand(B, D, h, w)
+    ref = O.stage_net(feats, pm, dv, pretrained_sd, st)
+    net = C.StageNet(3, storage=torch.float32)
+    net.load_state_dict({k[10:]: v for k, v in pretrained_sd.items() if k.startswith("stage_net.")})
+    cr = C.CostRegNet(Cc, 8, storage=torch.float32)
+    pre = f"cost_regularization.{st}."
+    cr.load_state_dict({k[len(pre):]: v for k, v in pretrained_sd.items() if k.startswith(pre)})
+    net, cr = net.to(DEV).eval(), cr.to(DEV).eval()
+    feats_c = [{k: tuple(t.to(DEV) for t in v) for k, v in f.items()} for f in feats]
+    out = net(feats_c, pm.to(DEV), dv.to(DEV), D, cr, stage_idx=st)
+    assert set(out) == {"depth", "photometric_confidence", "norm_curv"}
+    assert O.rel_l1(out["depth"].cpu(), ref["depth"]) < 2e-5
+    assert O.rel_l1(out["norm_curv"].cpu(), ref["norm_curv"]) < 1e-5
+    with pytest.raises(AssertionError):
+        net(feats_c[:1], pm.to(DEV), dv.to(DEV), D, cr, stage_idx=st)
+
+
+def test_repeatable_and_input_not_mutated(pretrained_sd):
+    cfg = synthetic.CONFIGS["cfg1"]
+    s = synthetic.make_sample("cfg1", "noise", seed=4)
+    model = build(pretrained_sd, cfg["ndepths"], cfg["ratios"], torch.float16)
+    imgs = s.imgs.to(DEV)
+    keep = imgs.clone()
+    a = run(model, s)["depth"]
+    b = run(model, s)["depth"]
+    assert torch.equal(imgs, keep)
+    # InstanceNorm statistics are accumulated with fp64 atomics: run-to-run differences stay at rounding level
+    assert O.rel_l1(a.cpu(), b.cpu()) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present on this box")
+def test_patch_rebinds_reference_names(pretrained_sd):
+    import sys
+    sys.path.insert(0, "/root/reference")
+    import models.model as rm
+    import models.module as rmod
+    C.patch(rm, rmod)
+    assert rm.homo_warping_3D is C.homo_warping_3D and rmod.DynamicConv is C.DynamicConv

@@ -1,0 +1,283 @@
+"""Parity tests proper: every CUDA op, called through the C ABI / drop-in surface, against the golden
+vectors generated from the live reference and against the CPU oracle on the same seeded inputs.
+
+Tolerances: the fp32-storage build of each kernel must sit at the fp32 re-association floor (the
+reference itself moves by ~1e-6 relative between thread counts, SURVEY.md 8c fixture 5); the fp16-
+storage production setting is bounded by fp16 rounding of operands (2^-11 relative per element) and
+checked end-to-end against north_star's 1e-3 relative-L1 bar in test_gpu_e2e.py.
+"""
+import pytest
+import torch
+
+import cds_mvsnet_b200 as C
+from cds_mvsnet_b200 import _lib, weights as W
+from cds_mvsnet_b200._lib import call, ptr
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+T = 0.01
+DEV = "cuda"
+torch.set_grad_enabled(False)
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def close(a, b, atol, rtol=1e-5):
+    torch.testing.assert_close(a.float().cpu(), b.float().cpu(), atol=atol, rtol=rtol)
+
+
+# ---------------------------------------------------------------------------------------- A1
+def test_homo_warp_golden(golden):
+    g = golden("warp")
+    out = C.homo_warping_3D(cu(g["src_fea"]), cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth_planes"]))
+    close(out, g["out_planes"], 1e-5)
+    out = C.homo_warping_3D(cu(g["src_fea"]), cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth_pix"]))
+    close(out, g["out_pix"], 1e-5)
+    assert out[:, :, 0].abs().max() == 0          # far-out-of-frustum plane: zero padding
+
+
+def test_homo_warp_oracle_random():
+    torch.manual_seed(1)
+    from cds_mvsnet_b200 import synthetic
+    s = synthetic.make_sample(dict(W=64, H=64, N=2, ndepths=(8,), ratios=(1.0,), B=3, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage1"]
+    fea = torch.randn(3, 5, 16, 16)          # odd channel count: the op-level kernel has no C % 8 restriction
+    dv = 425 + 500 * torch.rand(3, 7, 16, 16)
+    refP, srcP = O.compose_projection(pm[:, 0]), O.compose_projection(pm[:, 1])
+    close(C.homo_warping_3D(cu(fea), cu(srcP), cu(refP), cu(dv)), O.homo_warp(fea, srcP, refP, dv), 2e-5)
+
+
+def test_homo_warp_rejects_bad_shapes():
+    with pytest.raises(RuntimeError):
+        C.homo_warping_3D(torch.zeros(1, 8, 4, 4, device=DEV), torch.eye(4, device=DEV)[None], torch.eye(4, device=DEV)[None],
+                          torch.ones(1, 2, 5, 5, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------- A8
+def test_camera_setup_golden(golden):
+    g = golden("epipole")
+    B = g["cam_ref"].shape[0]
+    pm = cu(torch.stack((g["cam_ref"], g["cam_src"]), 1).contiguous())   # [B,2,2,4,4]
+    coef = torch.empty(1, B, 1, 12, device=DEV)
+    epi = torch.empty(2, 1, B, 2, device=DEV)
+    import ctypes
+    call("cds_camera_setup", (ctypes.c_void_p * 1)(pm.data_ptr()), 1, 0, B, 2, ptr(coef), ptr(epi))
+    close(epi[0, 0], g["e_ref"], 2e-2, 2e-5)
+    close(epi[1, 0], g["e_src"], 2e-2, 2e-5)
+    rot, trans = O.warp_coefficients(O.compose_projection(g["cam_src"]), O.compose_projection(g["cam_ref"]))
+    close(coef[0, :, 0, :9].reshape(B, 3, 3), rot, 1e-5, 1e-5)
+    close(coef[0, :, 0, 9:], trans, 1e-3, 1e-5)
+
+
+# ---------------------------------------------------------------------------------------- A9
+@pytest.mark.parametrize("tag,D,ratio,scale", [("s1", 48, 4.0, 4), ("s2", 32, 1.5, 2), ("s3", 8, 0.75, 1)])
+def test_hypotheses_golden(golden, tag, D, ratio, scale):
+    g = golden("hypotheses")
+    dv = cu(g["depth_values"])
+    ref = g[f"{tag}_out"]
+    B, _, h, w = ref.shape
+    out = torch.empty(B, D, h, w, device=DEV)
+    prev = None if tag == "s1" else cu(g[f"{tag}_prev"]).contiguous()
+    hp, wp = (0, 0) if prev is None else prev.shape[1:]
+    call("cds_depth_hypotheses", ptr(dv), dv.shape[1], ptr(prev), hp, wp, B, D, ratio, h * scale, w * scale, scale, ptr(out))
+    close(out, ref, 5e-4, 0)
+
+
+# ---------------------------------------------------------------------------------------- A5
+def test_tail_golden(golden):
+    g = golden("tail")
+    logits, dsm = cu(g["logits"]), cu(g["depth_samples"])
+    B, D, h, w = logits.shape
+    depth, conf, prob = (torch.empty(B, h, w, device=DEV), torch.empty(B, h, w, device=DEV), torch.empty(B, D, h, w, device=DEV))
+    call("cds_softmax_regress", ptr(logits), ptr(dsm), 1, 0, B, D, h, w, ptr(depth), ptr(conf), ptr(prob))
+    close(prob, torch.softmax(g["logits"], 1), 1e-6)
+    close(depth, g["depth"], 2e-3, 1e-6)
+    # the window index is a truncation: allow the rare pixel whose expectation sits on an integer
+    bad = ((conf.cpu() - g["conf"]).abs() > 1e-5).float().mean()
+    assert bad < 0.002
+    # drop-in functions on probabilities
+    p = torch.softmax(logits, 1)
+    close(C.depth_regression(p, dsm), g["depth"], 2e-3, 1e-6)
+    assert ((C.conf_regression(p).cpu() - g["conf"]).abs() > 1e-5).float().mean() < 0.002
+    planes = torch.linspace(400, 900, D, device=DEV)[None].repeat(B, 1)
+    close(C.depth_regression(p, planes), O.depth_regression(p.cpu(), planes.cpu()), 2e-3, 1e-6)
+
+
+# ---------------------------------------------------------------------------------------- A6
+@pytest.mark.parametrize("storage,atol", [(torch.float32, 2e-4), (torch.float16, 2e-2)])
+@pytest.mark.parametrize("name", ["conv00", "conv01", "conv10", "conv20", "out1", "out3"])
+def test_dynamic_conv_golden(golden, pretrained_sd, name, storage, atol):
+    g = golden("dynconv")
+    cin, cout, ks, pre = W.DYN_LAYERS[name]
+    m = C.DynamicConv(cin, cout, size_kernels=ks, bias=name.startswith("out"), storage=storage)
+    m.load_state_dict({k[len(pre) + 1:]: v for k, v in pretrained_sd.items() if k.startswith(pre + ".")})
+    m = m.to(DEV).eval()
+    y, nc = m(cu(g[f"{name}_x"]), epipole=cu(g[f"{name}_epi"]), temperature=T)
+    ref_y, ref_nc = g[f"{name}_y"], g[f"{name}_nc"]
+    # the gate is softmax(g / 0.01): compare in relative-L1 (a handful of pixels sit on a gate edge)
+    assert O.rel_l1(y.cpu(), ref_y) < (2e-5 if storage == torch.float32 else 3e-3)
+    assert O.rel_l1(nc.cpu(), ref_nc) < (2e-5 if storage == torch.float32 else 3e-3)
+    assert (y.cpu() - ref_y).abs().max() < 50 * atol
+
+
+def test_dynamic_conv_refuses_training_and_stride():
+    with pytest.raises(NotImplementedError):
+        C.DynamicConv(8, 8, stride=2)
+    m = C.DynamicConv(8, 8).to(DEV)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 8, 16, 16, device=DEV), epipole=torch.zeros(1, 2, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------- A7
+@pytest.mark.parametrize("storage,tol", [(torch.float32, 5e-5), (torch.float16, 4e-3)])
+def test_feature_net_golden(golden, pretrained_sd, storage, tol):
+    g = golden("featurenet")
+    m = C.FeatureNet(8, storage=storage)
+    m.load_state_dict({k[8:]: v for k, v in pretrained_sd.items() if k.startswith("feature.")})
+    m = m.to(DEV).eval()
+    out = m(cu(g["img"]), epipole=cu(g["epi"]), temperature=T)
+    for st in ("stage1", "stage2", "stage3"):
+        fea, ncs, nca = out[st]
+        assert fea.shape == g[f"{st}_fea"].shape and ncs.shape == g[f"{st}_nc_sum"].shape
+        assert O.rel_l1(fea.cpu(), g[f"{st}_fea"]) < tol, st
+        assert O.rel_l1(ncs.cpu(), g[f"{st}_nc_sum"]) < 4 * tol, st
+        assert O.rel_l1(nca.cpu(), g[f"{st}_nc_abs"]) < 2 * tol, st
+
+
+def test_feature_net_batch_equals_single(pretrained_sd):
+    """Several images with different epipoles in one launch == one at a time (the cascade batches 2(N-1) images)."""
+    torch.manual_seed(3)
+    m = C.FeatureNet(8, storage=torch.float32)
+    m.load_state_dict({k[8:]: v for k, v in pretrained_sd.items() if k.startswith("feature.")})
+    m = m.to(DEV).eval()
+    img = torch.rand(3, 3, 64, 96, device=DEV)
+    epi = torch.tensor([[250.0, -40.0], [-500.0, 30.0], [48.0, 32.0]], device=DEV)
+    both = m(img, epipole=epi, temperature=T)
+    keep = {k: tuple(t.clone() for t in v) for k, v in both.items()}
+    for i in range(3):
+        one = m(img[i:i + 1], epipole=epi[i:i + 1], temperature=T)
+        for st in keep:
+            for a, b in zip(keep[st], one[st]):
+                close(a[i:i + 1], b, 1e-5, 1e-5)
+
+
+# ---------------------------------------------------------------------------------------- A3 / A4
+@pytest.mark.parametrize("st", [0, 1, 2])
+def test_visnet_golden(golden, pretrained_sd, st):
+    g = golden("nets3d")
+    x = cu(g[f"vis{st}_x"])
+    n, _, h, w = x.shape
+    wp = W.pack_visnet(pretrained_sd, f"stage_net.vis.{st}", DEV)
+    out = torch.empty(n, h, w, device=DEV)
+    call("cds_visnet", ptr(x[:, 0].contiguous()), ptr(x[:, 1].contiguous()), ptr(wp), n, h, w, ptr(out))
+    close(out.unsqueeze(1), g[f"vis{st}_y"], 5e-6)
+
+
+def test_visnet_tile_borders(pretrained_sd):
+    """Sizes that are not multiples of the 32x16 tile, and several maps per launch."""
+    torch.manual_seed(5)
+    x = torch.cat((2.5 * torch.rand(3, 1, 37, 75), 0.3 * torch.rand(3, 1, 37, 75)), 1)
+    wp = W.pack_visnet(pretrained_sd, "stage_net.vis.1", DEV)
+    out = torch.empty(3, 37, 75, device=DEV)
+    xc = cu(x)
+    call("cds_visnet", ptr(xc[:, 0].contiguous()), ptr(xc[:, 1].contiguous()), ptr(wp), 3, 37, 75, ptr(out))
+    close(out.unsqueeze(1), O.vis_net(x, pretrained_sd, "stage_net.vis.1"), 5e-6)
+
+
+@pytest.mark.parametrize("storage,tol", [(torch.float32, 2e-5), (torch.float16, 5e-3)])
+@pytest.mark.parametrize("st", [0, 1, 2])
+def test_costregnet_golden(golden, pretrained_sd, st, storage, tol):
+    g = golden("nets3d")
+    cin = (32, 16, 8)[st]
+    m = C.CostRegNet(cin, 8, storage=storage)
+    pre = f"cost_regularization.{st}."
+    m.load_state_dict({k[len(pre):]: v for k, v in pretrained_sd.items() if k.startswith(pre)})
+    m = m.to(DEV).eval()
+    y = m(cu(g[f"cr{st}_x"]))
+    ref = g[f"cr{st}_y"]
+    assert y.shape == ref.shape
+    assert O.rel_l1(y.cpu(), ref) < tol
+
+
+def test_costregnet_rejects_indivisible():
+    m = C.CostRegNet(8, 8).to(DEV).eval()
+    with pytest.raises(RuntimeError, match="divisible by 8"):
+        m(torch.zeros(1, 8, 8, 12, 16, device=DEV))
+
+
+@pytest.mark.parametrize("cin,cout,stride", [(8, 16, 2), (16, 16, 1), (64, 64, 1), (32, 64, 2)])
+def test_conv3d_block_vs_torch(cin, cout, stride):
+    """Single Conv3d block against the published operator (odd sizes exercise ceil(n/2) and borders)."""
+    torch.manual_seed(cin + cout)
+    x = torch.randn(2, cin, 5, 9, 11)
+    w = torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5
+    b = torch.randn(cout)
+    ref = torch.relu(torch.nn.functional.conv3d(x, w, b, stride=stride, padding=1))
+    xc = cu(x.permute(0, 2, 3, 4, 1).contiguous())
+    wc = cu(w.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous())
+    out = torch.empty(*ref.permute(0, 2, 3, 4, 1).shape, device=DEV)
+    call("cds_conv3d_k3", ptr(xc), ptr(wc), ptr(cu(b)), 2, cin, cout, 5, 9, 11, stride, 1, _lib.CDS_F32, ptr(out))
+    close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, 1e-4)
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 8), (32, 16), (64, 32)])
+def test_deconv3d_block_vs_torch(cin, cout):
+    torch.manual_seed(cin)
+    x = torch.randn(2, cin, 3, 5, 7)
+    w = torch.randn(cin, cout, 3, 3, 3) / (8 * cin) ** 0.5
+    b = torch.randn(cout)
+    skip = torch.randn(2, cout, 6, 10, 14)
+    ref = skip + torch.relu(torch.nn.functional.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1))
+    xc = cu(x.permute(0, 2, 3, 4, 1).contiguous())
+    wc = cu(w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout).contiguous())
+    sc = cu(skip.permute(0, 2, 3, 4, 1).contiguous())
+    out = torch.empty_like(sc)
+    call("cds_deconv3d_k3s2", ptr(xc), ptr(wc), ptr(cu(b)), ptr(sc), 2, cin, cout, 3, 5, 7, _lib.CDS_F32, ptr(out))
+    close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, 1e-4)
+
+
+# ---------------------------------------------------------------------------------------- A2
+@pytest.mark.parametrize("C_", [8, 16, 32])
+@pytest.mark.parametrize("storage,tol", [(torch.float32, 1e-5), (torch.float16, 2e-3)])
+def test_costvol_vs_oracle(C_, storage, tol):
+    from cds_mvsnet_b200 import synthetic
+    torch.manual_seed(C_)
+    B, V, D, h, w = 2, 3, 6, 24, 40
+    s = synthetic.make_sample(dict(W=4 * w, H=4 * h, N=V + 1, ndepths=(8,), ratios=(1.0,), B=B, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage1"]
+    ref_fea = torch.tanh(torch.randn(V, B, C_, h, w))
+    src_fea = torch.tanh(torch.randn(V, B, C_, h, w))
+    if storage == torch.float16:       # compare like with like: the oracle sees the fp16-rounded features
+        ref_fea, src_fea = ref_fea.half().float(), src_fea.half().float()
+    dv = 425 + 500 * torch.rand(B, D, h, w)
+    vis = torch.rand(V, B, h, w)
+    refP = O.compose_projection(pm[:, 0])
+    ents, vol = [], 0.0
+    for v in range(V):
+        warped = O.homo_warp(src_fea[v], O.compose_projection(pm[:, v + 1]), refP, dv)
+        prod, ent = O.similarity_entropy(ref_fea[v], warped)
+        ents.append(ent[:, 0])
+        vol = vol + prod * vis[v].unsqueeze(1).unsqueeze(1)
+    vol = vol / (vis.sum(0).unsqueeze(1).unsqueeze(1) + 1e-6)
+    import ctypes
+    pmc = cu(pm)
+    coef = torch.empty(1, B, V, 12, device=DEV)
+    call("cds_camera_setup", (ctypes.c_void_p * 1)(pmc.data_ptr()), 1, 0, B, V + 1, ptr(coef), None)
+    rf = cu(ref_fea.permute(0, 1, 3, 4, 2).contiguous()).to(storage)
+    sf = cu(src_fea.permute(0, 1, 3, 4, 2).contiguous()).to(storage)
+    dvc, visc = cu(dv), cu(vis)
+    ent_out = torch.empty(V, B, h, w, device=DEV)
+    dt = _lib.dtype_code(storage)
+    call("cds_costvol_entropy", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), V, B, C_, D, h, w, dt, ptr(ent_out))
+    close(ent_out, torch.stack(ents), 2e-4, 1e-4)
+    vol_out = torch.empty(B, D, h, w, C_, device=DEV, dtype=storage)
+    call("cds_costvol_aggregate", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), ptr(visc), V, B, C_, D, h, w, dt, ptr(vol_out))
+    assert O.rel_l1(vol_out.float().cpu().permute(0, 4, 1, 2, 3), vol) < tol
+
+
+def test_costvol_rejects_too_many_views():
+    z = torch.zeros(16, device=DEV)
+    with pytest.raises(RuntimeError, match="V="):
+        call("cds_costvol_entropy", ptr(z), ptr(z), ptr(z), ptr(z), 9, 1, 8, 4, 8, 8, 1, ptr(z))
