@@ -98,9 +98,50 @@ def stream():
 LAUNCHES = 0   # C-ABI calls issued by this process (every one enqueues exactly one kernel)
 
 
+class LaunchProfile:
+    """Optional per-launch CUDA-event timing (bench.py): ``with LaunchProfile() as p: ...; p.summary()``."""
+
+    def __init__(self):
+        self.records = []   # (name, tag, meta, start_event, end_event)
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+
+    def summary(self):
+        """{(name, tag): dict(ms_total, launches, meta)} -- call after a device synchronize."""
+        out = {}
+        for name, tag, meta, a, b in self.records:
+            d = out.setdefault((name, tag), dict(ms_total=0.0, launches=0, meta=meta))
+            d["ms_total"] += a.elapsed_time(b)
+            d["launches"] += 1
+        return out
+
+
+_PROFILE = None
+_TAG = [None, None]   # (tag, meta) attached to the launches issued next; set by the engine
+
+
+def set_tag(tag, meta=None):
+    _TAG[0], _TAG[1] = tag, meta
+
+
 def call(name, *args):
     global LAUNCHES
-    LIB.call(name, *args, stream())
+    prof = _PROFILE
+    if prof is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        LIB.call(name, *args, stream())
+        b.record()
+        prof.records.append((name, _TAG[0], _TAG[1], a, b))
+    else:
+        LIB.call(name, *args, stream())
     LAUNCHES += 1
 
 

@@ -54,7 +54,8 @@ def homo_warping_3D(src_fea, src_proj, ref_proj, depth_values):
     if per_pixel and tuple(depth_values.shape) != (B, D, H, Wd):
         raise RuntimeError(f"depth_values {tuple(depth_values.shape)} does not match features {tuple(src_fea.shape)}")
     coef = torch.empty(B, 12, dtype=torch.float32, device=dev)
-    call("cds_warp_coeffs", ptr(_f32c(src_proj)), ptr(_f32c(ref_proj)), B, ptr(coef))
+    sp, rp = _f32c(src_proj), _f32c(ref_proj)   # named: temporaries must outlive the launch's pointer use
+    call("cds_warp_coeffs", ptr(sp), ptr(rp), B, ptr(coef))
     out = torch.empty(B, C, D, H, Wd, dtype=torch.float32, device=dev)
     src, dep = _f32c(src_fea), _f32c(depth_values)
     call("cds_homo_warp", ptr(src), ptr(coef), ptr(dep), int(per_pixel), B, C, D, H, Wd, ptr(out))
@@ -120,7 +121,8 @@ def _nhwc(x, storage):
     """fp32 NCHW -> channels-last storage tensor via the library's converter."""
     B, C, H, Wd = x.shape
     out = torch.empty(B, H, Wd, C, dtype=storage, device=x.device)
-    call("cds_nchw_to_nhwc", ptr(_f32c(x)), B, C, H, Wd, _lib.dtype_code(storage), ptr(out))
+    xc = _f32c(x)
+    call("cds_nchw_to_nhwc", ptr(xc), B, C, H, Wd, _lib.dtype_code(storage), ptr(out))
     return out
 
 
@@ -173,7 +175,8 @@ class DynamicConv(_CachedModule):
         raw = torch.empty(B, H, Wd, self.out_c, dtype=self.storage, device=dev)
         nc = torch.empty(B, 1, H, Wd, dtype=torch.float32, device=dev)
         ks = (ctypes.c_int * len(w.ksizes))(*w.ksizes)
-        call("cds_dynamic_conv", ptr(x), mode, None, None, ACT_NONE, ptr(_f32c(epipole)), 1.0, ptr(w.w_att), ptr(w.w_conv),
+        epi = _f32c(epipole)
+        call("cds_dynamic_conv", ptr(x), mode, None, None, ACT_NONE, ptr(epi), 1.0, ptr(w.w_att), ptr(w.w_conv),
              ptr(w.bias), ptr(w.gate), B, self.in_c, self.out_c, H, Wd, len(w.ksizes), ks, float(temperature), dt,
              ptr(raw), None, ptr(nc), None, 0, None)
         return _nchw(raw), nc
@@ -281,7 +284,8 @@ class CostRegNet(_CachedModule):
         reg, buf = self._engine(dev)
         # NCDHW -> NDHWC: D is folded into the image-batch axis of the 2-D converter per batch item
         vol = torch.empty(B, D, H, Wd, C, dtype=self.storage, device=dev)
-        call("cds_nchw_to_nhwc", ptr(_f32c(x)), B, C, D * H, Wd, _lib.dtype_code(self.storage), ptr(vol))
+        xc = _f32c(x)
+        call("cds_nchw_to_nhwc", ptr(xc), B, C, D * H, Wd, _lib.dtype_code(self.storage), ptr(vol))
         logits = reg.run(buf, "cr", vol, B, D, H, Wd)
         return logits.unsqueeze(1).clone()
 

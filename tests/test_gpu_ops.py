@@ -32,9 +32,10 @@ def close(a, b, atol, rtol=1e-5):
 def test_homo_warp_golden(golden):
     g = golden("warp")
     out = C.homo_warping_3D(cu(g["src_fea"]), cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth_planes"]))
-    close(out, g["out_planes"], 1e-5)
+    # coefficients come from an fp64 inverse here, an fp32 torch.inverse there: ~1e-4 px of coordinate noise
+    close(out, g["out_planes"], 2e-4)
     out = C.homo_warping_3D(cu(g["src_fea"]), cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth_pix"]))
-    close(out, g["out_pix"], 1e-5)
+    close(out, g["out_pix"], 2e-4)
     assert out[:, :, 0].abs().max() == 0          # far-out-of-frustum plane: zero padding
 
 
@@ -171,7 +172,8 @@ def test_visnet_golden(golden, pretrained_sd, st):
     n, _, h, w = x.shape
     wp = W.pack_visnet(pretrained_sd, f"stage_net.vis.{st}", DEV)
     out = torch.empty(n, h, w, device=DEV)
-    call("cds_visnet", ptr(x[:, 0].contiguous()), ptr(x[:, 1].contiguous()), ptr(wp), n, h, w, ptr(out))
+    ent, cur = x[:, 0].contiguous(), x[:, 1].contiguous()   # keep the temporaries alive across the launch
+    call("cds_visnet", ptr(ent), ptr(cur), ptr(wp), n, h, w, ptr(out))
     close(out.unsqueeze(1), g[f"vis{st}_y"], 5e-6)
 
 
@@ -182,7 +184,8 @@ def test_visnet_tile_borders(pretrained_sd):
     wp = W.pack_visnet(pretrained_sd, "stage_net.vis.1", DEV)
     out = torch.empty(3, 37, 75, device=DEV)
     xc = cu(x)
-    call("cds_visnet", ptr(xc[:, 0].contiguous()), ptr(xc[:, 1].contiguous()), ptr(wp), 3, 37, 75, ptr(out))
+    ent, cur = xc[:, 0].contiguous(), xc[:, 1].contiguous()
+    call("cds_visnet", ptr(ent), ptr(cur), ptr(wp), 3, 37, 75, ptr(out))
     close(out.unsqueeze(1), O.vis_net(x, pretrained_sd, "stage_net.vis.1"), 5e-6)
 
 
@@ -218,7 +221,8 @@ def test_conv3d_block_vs_torch(cin, cout, stride):
     xc = cu(x.permute(0, 2, 3, 4, 1).contiguous())
     wc = cu(w.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous())
     out = torch.empty(*ref.permute(0, 2, 3, 4, 1).shape, device=DEV)
-    call("cds_conv3d_k3", ptr(xc), ptr(wc), ptr(cu(b)), 2, cin, cout, 5, 9, 11, stride, 1, _lib.CDS_F32, ptr(out))
+    bc = cu(b)
+    call("cds_conv3d_k3", ptr(xc), ptr(wc), ptr(bc), 2, cin, cout, 5, 9, 11, stride, 1, _lib.CDS_F32, ptr(out))
     close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, 1e-4)
 
 
@@ -234,7 +238,8 @@ def test_deconv3d_block_vs_torch(cin, cout):
     wc = cu(w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout).contiguous())
     sc = cu(skip.permute(0, 2, 3, 4, 1).contiguous())
     out = torch.empty_like(sc)
-    call("cds_deconv3d_k3s2", ptr(xc), ptr(wc), ptr(cu(b)), ptr(sc), 2, cin, cout, 3, 5, 7, _lib.CDS_F32, ptr(out))
+    bc = cu(b)
+    call("cds_deconv3d_k3s2", ptr(xc), ptr(wc), ptr(bc), ptr(sc), 2, cin, cout, 3, 5, 7, _lib.CDS_F32, ptr(out))
     close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, 1e-4)
 
 
