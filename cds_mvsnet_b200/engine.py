@@ -44,6 +44,16 @@ def _ksizes(ks):
     return (ctypes.c_int * len(ks))(*ks)
 
 
+def kcall(tag, flops, nbytes, name, *args):
+    """Launch `name` with a profiling tag and its ALGORITHMIC cost (flops, bytes) -- see DESIGN.md section 5."""
+    _lib.set_tag(tag, (float(flops), float(nbytes)))
+    call(name, *args)
+
+
+def _esize(dt):
+    return 2 if dt == torch.float16 else 4
+
+
 class FeatureExtractor:
     """FeatureNet (models/module.py:201-267) for a batch of n images in ~17 launches."""
 
@@ -57,6 +67,11 @@ class FeatureExtractor:
     def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
              nc_mode, nc_abs, norm_curv=None):
         w = self.fw.dyn[name]
+        e = _esize(self.storage)
+        px = n * H * W
+        flops = 2.0 * sum(k * k for k in w.ksizes) * w.cin * (w.cout + 3) * px
+        nbytes = px * (w.cin * (4 if in_mode == 1 else e) + w.cout * e + 8)
+        _lib.set_tag("feat." + name, (flops, float(nbytes)))
         call("cds_dynamic_conv", ptr(x), in_mode, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
              ptr(w.w_att), ptr(w.w_conv), ptr(w.bias), ptr(w.gate), n, w.cin, w.cout, H, W, len(w.ksizes),
              _ksizes(w.ksizes), float(T), self.dt, ptr(out), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode,
@@ -67,6 +82,7 @@ class FeatureExtractor:
         Returns {stage: (fea [n,h,w,C] storage dtype, nc_sq [n,h,w] fp32, nc_abs [n,h,w] fp32)}."""
         st, dt = self.storage, self.dt
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        e = _esize(st)
         stats = buf.get("f.stats", (self.N_STATS, n, 32, 2), torch.float64)
         stats.zero_()
         # the kernels index statistics densely as [n][C][2]: give each layer its own dense view
@@ -102,26 +118,30 @@ class FeatureExtractor:
         self._dyn("conv00", imgs, 1, img_index, None, ACT_NONE, epipoles, 1.0, n, H, W, T, raw00, sv(0, 8), ncsq[2], 0, None)
         self._dyn("conv01", raw00, 0, None, sv(0, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, raw01, sv(1, 8), ncsq[2], 1, None)
         # 1/2 resolution
-        call("cds_conv2d_3x3s2", ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.downsample1), n, 8, 16, H, W, dt, ptr(rawd1), ptr(sv(2, 16)))
+        kcall("feat.downsample1", 2.0 * 9 * 8 * 16 * n * H2 * W2, n * (H * W * 8 + H2 * W2 * 16) * e,
+              "cds_conv2d_3x3s2", ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.downsample1), n, 8, 16, H, W, dt, ptr(rawd1), ptr(sv(2, 16)))
         self._dyn("conv10", rawd1, 0, None, sv(2, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw10, sv(3, 16), ncsq[1], 0, None)
         self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11, sv(4, 16), ncsq[1], 1, None)
         # 1/4 resolution
-        call("cds_conv2d_3x3s2", ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.downsample2), n, 16, 32, H2, W2, dt, ptr(rawd2), ptr(sv(5, 32)))
+        kcall("feat.downsample2", 2.0 * 9 * 16 * 32 * n * H4 * W4, n * (H2 * W2 * 16 + H4 * W4 * 32) * e,
+              "cds_conv2d_3x3s2", ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.downsample2), n, 16, 32, H2, W2, dt, ptr(rawd2), ptr(sv(5, 32)))
         self._dyn("conv20", rawd2, 0, None, sv(5, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw20, sv(6, 32), ncsq[0], 0, None)
         self._dyn("conv21", raw20, 0, None, sv(6, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw21, sv(7, 32), ncsq[0], 1, None)
         # stage-1 output
         self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1, sv(8, 32), ncsq[0], 2, ncab[0])
-        call("cds_instnorm_act", ptr(rawo1), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
+        kcall("feat.act1", 0, 2 * n * H4 * W4 * 32 * e, "cds_instnorm_act", ptr(rawo1), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
         # stage-2 output: inner1 over cat(up2(conv21), conv11)
-        call("cds_conv2d_1x1_cat", ptr(raw21), ptr(sv(7, 32)), ACT_LRELU, ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.inner1),
+        kcall("feat.inner1", 2.0 * 48 * 16 * n * H2 * W2, n * (H4 * W4 * 32 + 2 * H2 * W2 * 16) * e,
+              "cds_conv2d_1x1_cat", ptr(raw21), ptr(sv(7, 32)), ACT_LRELU, ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.inner1),
              n, 32, 16, 16, H2, W2, dt, ptr(rawi1), ptr(sv(9, 16)))
         self._dyn("out2", rawi1, 0, None, sv(9, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, rawo2, sv(10, 16), ncsq[1], 2, ncab[1])
-        call("cds_instnorm_act", ptr(rawo2), ptr(sv(10, 16)), ACT_TANH, n, 16, H2, W2, dt, ptr(fea2))
+        kcall("feat.act2", 0, 2 * n * H2 * W2 * 16 * e, "cds_instnorm_act", ptr(rawo2), ptr(sv(10, 16)), ACT_TANH, n, 16, H2, W2, dt, ptr(fea2))
         # stage-3 output: inner2 over cat(up2(stage-2 feature), conv01)
-        call("cds_conv2d_1x1_cat", ptr(fea2), None, ACT_NONE, ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.inner2),
+        kcall("feat.inner2", 2.0 * 24 * 8 * n * H * W, n * (H2 * W2 * 16 + 2 * H * W * 8) * e,
+              "cds_conv2d_1x1_cat", ptr(fea2), None, ACT_NONE, ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.inner2),
              n, 16, 8, 8, H, W, dt, ptr(rawi2), ptr(sv(11, 8)))
         self._dyn("out3", rawi2, 0, None, sv(11, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, rawo3, sv(12, 8), ncsq[2], 2, ncab[2])
-        call("cds_instnorm_act", ptr(rawo3), ptr(sv(12, 8)), ACT_TANH, n, 8, H, W, dt, ptr(fea3))
+        kcall("feat.act3", 0, 2 * n * H * W * 8 * e, "cds_instnorm_act", ptr(rawo3), ptr(sv(12, 8)), ACT_TANH, n, 8, H, W, dt, ptr(fea3))
         return {0: (fea1, ncsq[0], ncab[0]), 1: (fea2, ncsq[1], ncab[1]), 2: (fea3, ncsq[2], ncab[2])}
 
 
@@ -135,10 +155,16 @@ class Regulariser:
 
     def _conv(self, name, x, B, D, H, W, stride, out):
         l = self.cw.layers[name]
+        e = _esize(self.storage)
+        m_in, m_out = B * D * H * W, out.numel() // l.cout
+        _lib.set_tag(f"{self.tag}.{name}", (2.0 * 27 * l.cin * l.cout * m_out, float((l.cin * m_in + l.cout * m_out) * e)))
         call("cds_conv3d_k3", ptr(x), ptr(l.w), ptr(l.bias), B, l.cin, l.cout, D, H, W, stride, 1, self.dt, ptr(out))
 
     def _deconv(self, name, x, skip, B, D, H, W, out):
         l = self.cw.layers[name]
+        e = _esize(self.storage)
+        m_in = B * D * H * W
+        _lib.set_tag(f"{self.tag}.{name}", (2.0 * 27 * l.cin * l.cout * m_in, float((l.cin * m_in + 2 * l.cout * 8 * m_in) * e)))
         call("cds_deconv3d_k3s2", ptr(x), ptr(l.w), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, self.dt, ptr(out))
 
     def run(self, buf: Buffers, tag, volume, B, D, H, W):
@@ -147,6 +173,7 @@ class Regulariser:
             raise RuntimeError(f"CostRegNet needs D, H, W divisible by 8 (got {D}x{H}x{W}); the reference fails the "
                                "same way at its skip additions (models/module.py:310-312)")
         st = self.storage
+        self.tag = tag
         b = self.cw.layers["conv0"].cout
         D2, H2, W2, D4, H4, W4, D8, H8, W8 = D // 2, H // 2, W // 2, D // 4, H // 4, W // 4, D // 8, H // 8, W // 8
         g = lambda n, s: buf.get(f"{tag}.{n}", s, st)
@@ -171,7 +198,9 @@ class Regulariser:
         self._deconv("conv7", c6, c4, B, D8, H8, W8, u7)
         self._deconv("conv9", u7, c2, B, D4, H4, W4, u9)
         self._deconv("conv11", u9, c0, B, D2, H2, W2, u11)
-        call("cds_prob_conv", ptr(u11), ptr(self.cw.prob), B, b, D, H, W, self.dt, ptr(logits))
+        m = B * D * H * W
+        kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_prob_conv", ptr(u11), ptr(self.cw.prob), B, b, D, H,
+              W, self.dt, ptr(logits))
         return logits
 
 
@@ -209,7 +238,7 @@ class CascadeEngine:
         coef = self.buf.get("cam.coef", (len(mats), B, V, 12), torch.float32)
         epi = self.buf.get("cam.epi", (2, V, B, 2), torch.float32)
         arr = (ctypes.c_void_p * len(mats))(*[m.data_ptr() for m in mats])
-        call("cds_camera_setup", arr, len(mats), epi_idx, B, N, ptr(coef), ptr(epi))
+        kcall("camera_setup", 0, 0, "cds_camera_setup", arr, len(mats), epi_idx, B, N, ptr(coef), ptr(epi))
         self._keep = mats
         return coef, epi
 
@@ -222,22 +251,27 @@ class CascadeEngine:
         VB = V * B
         samples = buf.get(f"s{s}.samples", (B, D, h, w), f32)
         hp, wp = (prev_depth.shape[1], prev_depth.shape[2]) if prev_depth is not None else (0, 0)
-        call("cds_depth_hypotheses", ptr(depth_values), depth_values.shape[1], ptr(prev_depth), hp, wp, B, D, self.ratios[s], H, W,
-             scale, ptr(samples))
+        e, P = _esize(self.storage), B * h * w
+        kcall(f"s{s}.hypotheses", 0, 4 * D * P + 4 * B * hp * wp, "cds_depth_hypotheses", ptr(depth_values), depth_values.shape[1],
+              ptr(prev_depth), hp, wp, B, D, self.ratios[s], H, W, scale, ptr(samples))
         ref_fea, src_fea = fea[:VB], fea[VB:]
         entropy = buf.get(f"s{s}.entropy", (V, B, h, w), f32)
-        call("cds_costvol_entropy", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, self.dt, ptr(entropy))
+        kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P, "cds_costvol_entropy",
+              ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, self.dt, ptr(entropy))
         vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
-        call("cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]), VB, h, w, ptr(vis))
+        kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]), VB, h, w,
+              ptr(vis))
         volume = buf.get(f"s{s}.volume", (B, D, h, w, C), self.storage)
-        call("cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
-             ptr(volume))
+        kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P + C * D * P * e,
+              "cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
+              ptr(volume))
         nc = buf.get(f"s{s}.nc", (B, 1, h, w), f32)
-        call("cds_nc_mean", ptr(ncsq[:VB]), ptr(ncsq[VB:]), V, B * h * w, ptr(nc))
+        kcall(f"s{s}.nc_mean", 0, 4 * P * (2 * V + 1), "cds_nc_mean", ptr(ncsq[:VB]), ptr(ncsq[VB:]), V, B * h * w, ptr(nc))
         logits = self.regs[s].run(buf, f"s{s}.cr", volume, B, D, h, w)
         depth = buf.get(f"s{s}.depth", (B, h, w), f32)
         conf = buf.get(f"s{s}.conf", (B, h, w), f32)
-        call("cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w, ptr(depth), ptr(conf), None)
+        kcall(f"s{s}.softmax_regress", 0, 8 * D * P + 8 * P, "cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w,
+              ptr(depth), ptr(conf), None)
         return {"depth": depth, "photometric_confidence": conf, "norm_curv": nc}
 
     # -- whole forward --------------------------------------------------------------------------

@@ -119,6 +119,12 @@ def bilinear_gather_zeros(fea: torch.Tensor, u: torch.Tensor, v: torch.Tensor) -
     return out
 
 
+# bench.py's CPU legs set this: the gather then goes through ATen's grid_sample exactly as the reference's
+# own code does (warping.py:100-101), so the timed port costs what the reference costs.  Tests keep the
+# explicit restatement above (the two agree to 5e-7, tests/test_oracle_golden.py::test_fast_gather).
+FAST_GATHER = False
+
+
 def homo_warp(src_fea, src_proj, ref_proj, depth_values):
     """homo_warping_3D (warping.py:69-104): [B,C,h,w] -> [B,C,D,h,w]."""
     B, C, h, w = src_fea.shape
@@ -130,6 +136,10 @@ def homo_warp(src_fea, src_proj, ref_proj, depth_values):
     dep = depth_values.reshape(B, 1, D, -1)                                         # [B,1,D,1|P]
     p = ray.unsqueeze(2) * dep + trans.reshape(B, 3, 1, 1)                          # [B,3,D,P]
     z = p[:, 2] + 1e-6
+    if FAST_GATHER:
+        grid = torch.stack(((p[:, 0] / z) / ((w - 1) / 2) - 1, (p[:, 1] / z) / ((h - 1) / 2) - 1), dim=3)
+        out = F.grid_sample(src_fea, grid.reshape(B, D * h, w, 2), mode="bilinear", padding_mode="zeros", align_corners=True)
+        return out.reshape(B, C, D, h, w)
     u = (p[:, 0] / z).reshape(B, -1)
     v = (p[:, 1] / z).reshape(B, -1)
     return bilinear_gather_zeros(src_fea, u, v).reshape(B, C, D, h, w)

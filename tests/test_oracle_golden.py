@@ -26,6 +26,16 @@ def test_warp(golden):
     assert g["out_pix"][:, :, 0].abs().max() == 0
 
 
+def test_fast_gather(golden):
+    """The grid_sample shortcut bench.py times on the CPU is the same function."""
+    g = golden("warp")
+    O.FAST_GATHER = True
+    try:
+        close(O.homo_warp(g["src_fea"], g["src_proj"], g["ref_proj"], g["depth_pix"]), g["out_pix"], 2e-6)
+    finally:
+        O.FAST_GATHER = False
+
+
 def test_compose_projection(golden):
     g = golden("warp")
     close(O.compose_projection(g["cams"][:, 1]), g["src_proj"], 0, 0)
