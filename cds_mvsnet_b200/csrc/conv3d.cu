@@ -6,7 +6,9 @@
 // Reference: models/module.py:80-166 (Conv3d / Deconv3d blocks: conv -> BatchNorm3d -> ReLU),
 // :270-315 (CostRegNet wiring, skip added AFTER the deconv's ReLU), :373-391 (regression).
 // BatchNorm (eval, running stats) is folded by the host: weights arrive as [27][Cin][Cout] fp32
-// already scaled, plus a per-channel bias.  Activations are channels-last [B, D, H, W, C].
+// already scaled, plus a per-channel bias.  Activations are channel-BLOCKED channels-last:
+// [B][C/8][D][H][W][8] (for C = 8 this is plain NDHWC), so that one 8-channel slab of a row of voxels is
+// contiguous -- the unit the TMA / tcgen05 kernels in conv3d_tc.cu consume.
 #include "cds_common.cuh"
 
 namespace {
@@ -46,11 +48,12 @@ __global__ void __launch_bounds__(128) conv3d_kernel(const T* __restrict__ in, c
         for (int v = 0; v < VPT; ++v) {
             int id = od[v] * stride - 1 + kd, ih = oh[v] * stride - 1 + kh, iw = ow[v] * stride - 1 + kw;
             if (!live[v] || id < 0 || id >= Di || ih < 0 || ih >= Hi || iw < 0 || iw >= Wi) continue;
-            const T* ip = in + ((((size_t)ob[v] * Di + id) * Hi + ih) * Wi + iw) * CIN;
+            const size_t Min = (size_t)Di * Hi * Wi;
+            const T* ip = in + ((size_t)ob[v] * (CIN / 8) * Min + ((size_t)id * Hi + ih) * Wi + iw) * 8;
 #pragma unroll
             for (int c8 = 0; c8 < CIN / 8; ++c8) {
                 float x[8];
-                Vec8<T>::load(ip + c8 * 8, x);
+                Vec8<T>::load(ip + (size_t)c8 * Min * 8, x);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4* wp = reinterpret_cast<const float4*>(w_s + (c8 * 8 + j) * COUT);
@@ -69,7 +72,9 @@ __global__ void __launch_bounds__(128) conv3d_kernel(const T* __restrict__ in, c
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         if (!live[v]) continue;
-        T* op = out + (size_t)(base + (long long)v * 128) * COUT;
+        const size_t Mout = (size_t)Do * Ho * Wo;
+        const size_t ov = ((size_t)od[v] * Ho + oh[v]) * Wo + ow[v];
+        T* op = out + ((size_t)ob[v] * (COUT / 8) * Mout + ov) * 8;
 #pragma unroll
         for (int c8 = 0; c8 < COUT / 8; ++c8) {
             float y[8];
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(128) conv3d_kernel(const T* __restrict__ in, c
                 float t = acc[v][c8 * 8 + j] + __ldg(bias + c8 * 8 + j);
                 y[j] = relu ? fmaxf(t, 0.f) : t;
             }
-            Vec8<T>::store(op + c8 * 8, y);
+            Vec8<T>::store(op + (size_t)c8 * Mout * 8, y);
         }
     }
 }
@@ -117,11 +122,12 @@ __global__ void __launch_bounds__(128) deconv3d_kernel(const T* __restrict__ in,
             __syncthreads();
             int jd = id + sd, jh = ih + sh, jw = iw + sw;
             if (!live || jd >= Di || jh >= Hi || jw >= Wi) continue;
-            const T* ip = in + ((((size_t)b * Di + jd) * Hi + jh) * Wi + jw) * CIN;
+            const size_t Min = (size_t)Di * Hi * Wi;
+            const T* ip = in + ((size_t)b * (CIN / 8) * Min + ((size_t)jd * Hi + jh) * Wi + jw) * 8;
 #pragma unroll
             for (int c8 = 0; c8 < CIN / 8; ++c8) {
                 float x[8];
-                Vec8<T>::load(ip + c8 * 8, x);
+                Vec8<T>::load(ip + (size_t)c8 * Min * 8, x);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4* wp = reinterpret_cast<const float4*>(w_s + (c8 * 8 + j) * COUT);
@@ -137,17 +143,18 @@ __global__ void __launch_bounds__(128) deconv3d_kernel(const T* __restrict__ in,
             }
         }
         if (live) {
-            size_t o = ((((size_t)b * Do + 2 * id + pd) * Ho + 2 * ih + ph) * Wo + 2 * iw + pw) * COUT;
+            const size_t Mout = (size_t)Do * Ho * Wo;
+            size_t o = ((size_t)b * (COUT / 8) * Mout + ((size_t)(2 * id + pd) * Ho + 2 * ih + ph) * Wo + 2 * iw + pw) * 8;
 #pragma unroll
             for (int c8 = 0; c8 < COUT / 8; ++c8) {
                 float y[8], s[8];
-                if (skip) Vec8<T>::load(skip + o + c8 * 8, s);
+                if (skip) Vec8<T>::load(skip + o + (size_t)c8 * Mout * 8, s);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float t = fmaxf(acc[c8 * 8 + j] + __ldg(bias + c8 * 8 + j), 0.f);
                     y[j] = skip ? s[j] + t : t;
                 }
-                Vec8<T>::store(out + o + c8 * 8, y);
+                Vec8<T>::store(out + o + (size_t)c8 * Mout * 8, y);
             }
         }
     }

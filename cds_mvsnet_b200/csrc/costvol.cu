@@ -2,7 +2,7 @@
 // never materialised.  Two sweeps around the visibility net (A3):
 //   pass 1  per source view: similarity sum_c ref*warp per plane -> online softmax entropy over D
 //   pass 2  visibility-weighted mean over views of ref (.) warp, all C channels kept, written as
-//           a channels-last [B, D, h, w, C] volume
+//           a channel-blocked channels-last [B, C/8, D, h, w, 8] volume
 // Reference: models/model.py:34-60,74 (loop), models/utils/warping.py:84-101 (coordinates, gather).
 //
 // Layout: features are channels-last [V, B, h, w, C] (one ref and one src map per source view,
@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const T* __restrict__ re
     }
     float inv = 1.f / (vsum + 1e-6f);
     const float* dp = depth + (size_t)b * D * P + pofs;
-    T* outp = volume + ((size_t)b * D * P + pofs) * C + chunk * 8;
+    // channel-blocked volume [B][C/8][D][h][w][8]: one 8-channel slab of a row is contiguous (what conv0's TMA wants)
+    T* outp = volume + (((size_t)b * LPP + chunk) * D * P + pofs) * 8;
 
     for (int d = 0; d < D; ++d) {
         float dep = __ldg(dp + (size_t)d * P);
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const T* __restrict__ re
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] *= inv;
-        Vec8<T>::store(outp + (size_t)d * P * C, acc);
+        Vec8<T>::store(outp + (size_t)d * P * 8, acc);
     }
 }
 

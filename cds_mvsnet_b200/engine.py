@@ -148,16 +148,22 @@ class FeatureExtractor:
 class Regulariser:
     """CostRegNet (models/module.py:270-315) + prob head on a channels-last volume."""
 
-    def __init__(self, cw, storage=torch.float16):
+    def __init__(self, cw, storage=torch.float16, use_tc=True):
         self.cw = cw
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
+        self.use_tc = use_tc   # tensor-core (tcgen05) kernels where a layer shape is covered
+        self.tag = "cr"
 
     def _conv(self, name, x, B, D, H, W, stride, out):
         l = self.cw.layers[name]
         e = _esize(self.storage)
         m_in, m_out = B * D * H * W, out.numel() // l.cout
         _lib.set_tag(f"{self.tag}.{name}", (2.0 * 27 * l.cin * l.cout * m_out, float((l.cin * m_in + l.cout * m_out) * e)))
+        if (self.use_tc and stride == 1 and self.storage == torch.float16 and "tc" in l.extra
+                and _lib.LIB.load().cds_conv3d_k3_tc_supported(l.cin, l.cout, D, H, W, stride)):
+            call("cds_conv3d_k3_tc", ptr(x), ptr(l.extra["tc"]), ptr(l.bias), B, l.cin, l.cout, D, H, W, 1, ptr(out))
+            return
         call("cds_conv3d_k3", ptr(x), ptr(l.w), ptr(l.bias), B, l.cin, l.cout, D, H, W, stride, 1, self.dt, ptr(out))
 
     def _deconv(self, name, x, skip, B, D, H, W, out):
@@ -168,7 +174,7 @@ class Regulariser:
         call("cds_deconv3d_k3s2", ptr(x), ptr(l.w), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, self.dt, ptr(out))
 
     def run(self, buf: Buffers, tag, volume, B, D, H, W):
-        """volume [B,D,H,W,C] -> fp32 logits [B,D,H,W]."""
+        """volume [B,C/8,D,H,W,8] (channel-blocked) -> fp32 logits [B,D,H,W]."""
         if D % 8 or H % 8 or W % 8:
             raise RuntimeError(f"CostRegNet needs D, H, W divisible by 8 (got {D}x{H}x{W}); the reference fails the "
                                "same way at its skip additions (models/module.py:310-312)")
@@ -176,7 +182,7 @@ class Regulariser:
         self.tag = tag
         b = self.cw.layers["conv0"].cout
         D2, H2, W2, D4, H4, W4, D8, H8, W8 = D // 2, H // 2, W // 2, D // 4, H // 4, W // 4, D // 8, H // 8, W // 8
-        g = lambda n, s: buf.get(f"{tag}.{n}", s, st)
+        g = lambda n, s: buf.get(f"{tag}.{n}", (s[0], s[4] // 8) + tuple(s[1:4]) + (8,), st)   # [B, C/8, D, H, W, 8]
         c0 = g("c0", (B, D, H, W, b))
         c1 = g("c1", (B, D2, H2, W2, 2 * b))
         c2 = g("c2", (B, D2, H2, W2, 2 * b))
@@ -261,7 +267,7 @@ class CascadeEngine:
         vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
         kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]), VB, h, w,
               ptr(vis))
-        volume = buf.get(f"s{s}.volume", (B, D, h, w, C), self.storage)
+        volume = buf.get(f"s{s}.volume", (B, C // 8, D, h, w, 8), self.storage)
         kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P + C * D * P * e,
               "cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
               ptr(volume))

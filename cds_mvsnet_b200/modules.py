@@ -282,10 +282,10 @@ class CostRegNet(_CachedModule):
         dev = _dev(x)
         B, C, D, H, Wd = x.shape
         reg, buf = self._engine(dev)
-        # NCDHW -> NDHWC: D is folded into the image-batch axis of the 2-D converter per batch item
-        vol = torch.empty(B, D, H, Wd, C, dtype=self.storage, device=dev)
+        # NCDHW -> channel-blocked [B, C/8, D, H, W, 8]: every (b, c8) group is an 8-channel "image" of D*H rows
+        vol = torch.empty(B, C // 8, D, H, Wd, 8, dtype=self.storage, device=dev)
         xc = _f32c(x)
-        call("cds_nchw_to_nhwc", ptr(xc), B, C, D * H, Wd, _lib.dtype_code(self.storage), ptr(vol))
+        call("cds_nchw_to_nhwc", ptr(xc), B * (C // 8), 8, D * H, Wd, _lib.dtype_code(self.storage), ptr(vol))
         logits = reg.run(buf, "cr", vol, B, D, H, Wd)
         return logits.unsqueeze(1).clone()
 
@@ -344,7 +344,7 @@ class StageNet(_CachedModule):
         call("cds_costvol_entropy", ptr(ref_fea), ptr(src_fea), ptr(coef), ptr(samples), V, B, C, D, h, w, dt, ptr(entropy))
         vis = torch.empty(V, B, h, w, dtype=f32, device=dev)
         call("cds_visnet", ptr(entropy), ptr(ref_ncabs), ptr(vis_w[stage_idx]), V * B, h, w, ptr(vis))
-        volume = torch.empty(B, D, h, w, C, dtype=self.storage, device=dev)
+        volume = torch.empty(B, C // 8, D, h, w, 8, dtype=self.storage, device=dev)
         call("cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef), ptr(samples), ptr(vis), V, B, C, D, h, w, dt, ptr(volume))
         nc = torch.empty(B, 1, h, w, dtype=f32, device=dev)
         call("cds_nc_mean", ptr(ref_ncsq), ptr(src_ncsq), V, B * h * w, ptr(nc))

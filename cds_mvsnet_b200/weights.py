@@ -106,6 +106,32 @@ def pack_conv3d(sd, prefix, transposed, device) -> Conv3dWeights:
     return Conv3dWeights(ci, co, w.reshape(27, ci, co).to(**f32).contiguous(), shift.to(**f32).contiguous())
 
 
+def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
+    """fp16 B-operand image for csrc/conv3d_tc.cu: [mma][k-chunk 2][Npad/8][8 n][8 k] (K-major, no swizzle).
+
+    K order = 8-channel slabs.  Cin == 8: [tap0, zero pad], [tap1, tap2], ..., [tap25, tap26];
+    Cin > 8: slabs tap-major / channel-chunk minor, consecutive pairs."""
+    ci, co = l.cin, l.cout
+    c8 = ci // 8
+    npad = max(16, co)
+    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout]
+    if c8 == 1:
+        slabs = [(0, 0), None] + [(t, 0) for t in range(1, 27)]
+    else:
+        slabs = [(t, c) for t in range(27) for c in range(c8)]
+    assert len(slabs) % 2 == 0
+    img = torch.zeros(len(slabs) // 2, 2, npad // 8, 8, 8, dtype=torch.float64)
+    for s, sl in enumerate(slabs):
+        if sl is None:
+            continue
+        t, c = sl
+        blk = w[t, c * 8:(c + 1) * 8, :]                            # [8 k, Cout]
+        full = torch.zeros(8, npad, dtype=torch.float64)
+        full[:, :co] = blk
+        img[s // 2, s % 2] = full.t().reshape(npad // 8, 8, 8)      # [n-group, n row, k]
+    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+
+
 @dataclass
 class CostRegWeights:
     layers: dict          # name -> Conv3dWeights
@@ -115,6 +141,8 @@ class CostRegWeights:
 def pack_costreg(sd, prefix, device) -> CostRegWeights:
     layers = {n: pack_conv3d(sd, f"{prefix}.{n}", False, device) for n in COSTREG_CONVS}
     layers.update({n: pack_conv3d(sd, f"{prefix}.{n}", True, device) for n in COSTREG_DECONVS})
+    for n in ("conv0", "conv2", "conv4"):
+        layers[n].extra["tc"] = pack_conv3d_tc(layers[n])
     p = sd[prefix + ".prob.weight"].double()                        # [1,8,3,3,3]
     prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(dtype=torch.float32, device=device).contiguous()
     return CostRegWeights(layers, prob)

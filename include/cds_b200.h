@@ -13,7 +13,9 @@
  *     allocated or freed inside, inputs are never written
  *   - work is enqueued on `stream` and is CUDA-graph capturable (no host sync inside)
  *   - thread-safe / re-entrant: no mutable global state
- *   - activation tensors are channels-last ([n,H,W,C] / [B,D,H,W,C]) in the storage type `dtype`
+ *   - 2-D activation tensors are channels-last [n,H,W,C]; 3-D ones are channel-BLOCKED channels-last
+ *     [B,C/8,D,H,W,8] (plain NDHWC when C = 8) so an 8-channel slab of a voxel row is contiguous -- the unit
+ *     the TMA/tcgen05 kernels consume; all in the storage type `dtype`
  *     (CDS_F16: fp16 storage with fp32 accumulation -- the production setting; CDS_F32: fp32
  *     storage for tight parity checks); per-pixel maps, hypotheses and outputs are fp32
  */
@@ -78,7 +80,7 @@ int cds_depth_hypotheses(const float* depth_values, int Dtot, const float* prev_
 int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* coef, const float* depth, int V, int B,
                         int C, int D, int h, int w, int dtype, float* entropy, cudaStream_t stream);
 /* volume[b,d,y,x,:] = sum_v vis_v * ref_v (.) warp_{v,d} / (sum_v vis_v + 1e-6), vis [V,B,h,w]
- * (models/model.py:57-59,74); volume [B,D,h,w,C] channels-last. */
+ * (models/model.py:57-59,74); volume [B,C/8,D,h,w,8] channel-blocked. */
 int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float* coef, const float* depth,
                           const float* vis, int V, int B, int C, int D, int h, int w, int dtype, void* volume,
                           cudaStream_t stream);
@@ -95,13 +97,21 @@ int cds_visnet(const float* entropy, const float* curv, const float* wpack, int 
 
 /* ---- A4: 3-D regulariser blocks --------------------------------------------------------------- */
 /* Conv3d block (models/module.py:80-122): k3 p1, stride 1|2, BN folded into wgt [27][Cin][Cout] fp32
- * (tap = (kd*3+kh)*3+kw) and bias [Cout], optional ReLU.  in [B,D,H,W,Cin] -> out [B,ceil(D/s),..,Cout]. */
+ * (tap = (kd*3+kh)*3+kw) and bias [Cout], optional ReLU.  in [B,Cin/8,D,H,W,8] -> out [B,Cout/8,ceil(D/s),..,8]. */
 int cds_conv3d_k3(const void* in, const float* wgt, const float* bias, int B, int Cin, int Cout, int D, int H, int W,
                   int stride, int relu, int dtype, void* out, cudaStream_t stream);
 /* Deconv3d block (models/module.py:125-166): ConvTranspose3d k3 s2 p1 op1 + BN + ReLU, then `+ skip`
- * (models/module.py:310-312; skip may be NULL).  wgt [27][Cin][Cout]; out/skip [B,2D,2H,2W,Cout]. */
+ * (models/module.py:310-312; skip may be NULL).  wgt [27][Cin][Cout]; out/skip [B,Cout/8,2D,2H,2W,8]. */
 int cds_deconv3d_k3s2(const void* in, const float* wgt, const float* bias, const void* skip, int B, int Cin, int Cout,
                       int D, int H, int W, int dtype, void* out, cudaStream_t stream);
+/* Tensor-core (tcgen05 + TMEM) form of the stride-1 Conv3d block, fp16 storage only.  Same semantics as
+ * cds_conv3d_k3; wgt_packed is the fp16 operand image built by the host (cds_conv3d_k3_tc_weight_halfs()
+ * halfs, layout [mma][k-chunk 2][Npad/8][8 n][8 k], see csrc/conv3d_tc.cu).  cds_conv3d_k3_tc_supported()
+ * tells whether a layer shape is covered (stride 1, W >= 128, channel pairs of the regulariser). */
+int cds_conv3d_k3_tc_supported(int Cin, int Cout, int D, int H, int W, int stride);
+int cds_conv3d_k3_tc_weight_halfs(int Cin, int Cout);
+int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H,
+                     int W, int relu, void* out, cudaStream_t stream);
 /* prob head: plain Conv3d(8,1,3,p=1,bias=False) (models/module.py:303) -> fp32 logits [B,D,H,W]. */
 int cds_prob_conv(const void* in, const float* wgt, int B, int Cin, int D, int H, int W, int dtype, float* logits,
                   cudaStream_t stream);

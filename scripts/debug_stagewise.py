@@ -59,5 +59,5 @@ for st in range(3):
     print(f"stage{st+1}: samples {rel(buf[f's{st}.samples'], it['depth_samples']):.2e}")
     for v in range(V):
         print(f"   view{v}: entropy {rel(buf[f's{st}.entropy'][v], it['entropy'][v][:, 0]):.2e} vis {rel(buf[f's{st}.vis'][v], it['vis'][v][:, 0]):.2e}")
-    print(f"   volume {rel(buf[f's{st}.volume'].permute(0, 4, 1, 2, 3), it['volume']):.2e} logits {rel(buf[f's{st}.cr.logits'], it['logits']):.2e} "
+    print(f"   volume {rel(buf[f's{st}.volume'].permute(0, 1, 5, 2, 3, 4).reshape(it['volume'].shape), it['volume']):.2e} logits {rel(buf[f's{st}.cr.logits'], it['logits']):.2e} "
           f"depth {rel(out[f'stage{st+1}']['depth'], ref[f'stage{st+1}']['depth']):.2e} conf {(out[f'stage{st+1}']['photometric_confidence'].cpu() - ref[f'stage{st+1}']['photometric_confidence']).abs().mean():.2e}")

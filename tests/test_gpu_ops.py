@@ -28,6 +28,17 @@ def close(a, b, atol, rtol=1e-5):
     torch.testing.assert_close(a.float().cpu(), b.float().cpu(), atol=atol, rtol=rtol)
 
 
+def to_blocked(x):
+    """NCDHW -> the library's channel-blocked 3-D layout [B, C/8, D, H, W, 8]."""
+    B, C, D, H, Wd = x.shape
+    return x.reshape(B, C // 8, 8, D, H, Wd).permute(0, 1, 3, 4, 5, 2).contiguous()
+
+
+def from_blocked(x):
+    B, C8, D, H, Wd, _ = x.shape
+    return x.permute(0, 1, 5, 2, 3, 4).reshape(B, C8 * 8, D, H, Wd)
+
+
 # ---------------------------------------------------------------------------------------- A1
 def test_homo_warp_golden(golden):
     g = golden("warp")
@@ -218,12 +229,12 @@ def test_conv3d_block_vs_torch(cin, cout, stride):
     w = torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5
     b = torch.randn(cout)
     ref = torch.relu(torch.nn.functional.conv3d(x, w, b, stride=stride, padding=1))
-    xc = cu(x.permute(0, 2, 3, 4, 1).contiguous())
+    xc = cu(to_blocked(x))
     wc = cu(w.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous())
-    out = torch.empty(*ref.permute(0, 2, 3, 4, 1).shape, device=DEV)
+    out = torch.empty_like(cu(to_blocked(ref)))
     bc = cu(b)
     call("cds_conv3d_k3", ptr(xc), ptr(wc), ptr(bc), 2, cin, cout, 5, 9, 11, stride, 1, _lib.CDS_F32, ptr(out))
-    close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, 1e-4)
+    close(from_blocked(out), ref, 2e-5, 1e-4)
 
 
 @pytest.mark.parametrize("cin,cout", [(16, 8), (32, 16), (64, 32)])
@@ -234,13 +245,13 @@ def test_deconv3d_block_vs_torch(cin, cout):
     b = torch.randn(cout)
     skip = torch.randn(2, cout, 6, 10, 14)
     ref = skip + torch.relu(torch.nn.functional.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1))
-    xc = cu(x.permute(0, 2, 3, 4, 1).contiguous())
+    xc = cu(to_blocked(x))
     wc = cu(w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout).contiguous())
-    sc = cu(skip.permute(0, 2, 3, 4, 1).contiguous())
+    sc = cu(to_blocked(skip))
     out = torch.empty_like(sc)
     bc = cu(b)
     call("cds_deconv3d_k3s2", ptr(xc), ptr(wc), ptr(bc), ptr(sc), 2, cin, cout, 3, 5, 7, _lib.CDS_F32, ptr(out))
-    close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, 1e-4)
+    close(from_blocked(out), ref, 2e-5, 1e-4)
 
 
 # ---------------------------------------------------------------------------------------- A2
@@ -277,12 +288,48 @@ def test_costvol_vs_oracle(C_, storage, tol):
     dt = _lib.dtype_code(storage)
     call("cds_costvol_entropy", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), V, B, C_, D, h, w, dt, ptr(ent_out))
     close(ent_out, torch.stack(ents), 2e-4, 1e-4)
-    vol_out = torch.empty(B, D, h, w, C_, device=DEV, dtype=storage)
+    vol_out = torch.empty(B, C_ // 8, D, h, w, 8, device=DEV, dtype=storage)
     call("cds_costvol_aggregate", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), ptr(visc), V, B, C_, D, h, w, dt, ptr(vol_out))
-    assert O.rel_l1(vol_out.float().cpu().permute(0, 4, 1, 2, 3), vol) < tol
+    assert O.rel_l1(from_blocked(vol_out.float().cpu()), vol) < tol
 
 
 def test_costvol_rejects_too_many_views():
     z = torch.zeros(16, device=DEV)
     with pytest.raises(RuntimeError, match="V="):
         call("cds_costvol_entropy", ptr(z), ptr(z), ptr(z), ptr(z), 9, 1, 8, 4, 8, 8, 1, ptr(z))
+
+
+# ---------------------------------------------------------------------------------------- A4 on tensor cores
+@pytest.mark.parametrize("cin,cout", [(8, 8), (16, 8), (32, 8), (16, 16), (32, 32)])
+@pytest.mark.parametrize("shape", [(3, 5, 133), (2, 9, 256), (1, 4, 128)])
+def test_conv3d_tcgen05_vs_torch(cin, cout, shape):
+    """tcgen05 implicit-GEMM Conv3d block against the published operator on fp16-rounded operands
+    (fp32 accumulation on both sides, so only summation order differs)."""
+    D, H, Wd = shape
+    torch.manual_seed(cin * 100 + cout + Wd)
+    x = torch.randn(2, cin, D, H, Wd).half().float()
+    w = (torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5).half().float()
+    b = torch.randn(cout)
+    ref = torch.relu(torch.nn.functional.conv3d(x, w, b, stride=1, padding=1))
+    lw = W.Conv3dWeights(cin, cout, w.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous(), b)
+    packed = cu(W.pack_conv3d_tc(lw))
+    lib = _lib.LIB.load()
+    assert lib.cds_conv3d_k3_tc_supported(cin, cout, D, H, Wd, 1) == 1
+    assert packed.numel() == lib.cds_conv3d_k3_tc_weight_halfs(cin, cout)
+    xc = cu(to_blocked(x)).half()
+    bc = cu(b)
+    out = torch.empty(2, cout // 8, D, H, Wd, 8, device=DEV, dtype=torch.float16)
+    call("cds_conv3d_k3_tc", ptr(xc), ptr(packed), ptr(bc), 2, cin, cout, D, H, Wd, 1, ptr(out))
+    torch.cuda.synchronize()
+    got = from_blocked(out.float().cpu())
+    # output is rounded to fp16: half an ulp at |y| <= 8 is 4e-3
+    close(got, ref, 6e-3, 2e-3)
+
+
+def test_conv3d_tcgen05_unsupported_shapes():
+    lib = _lib.LIB.load()
+    assert lib.cds_conv3d_k3_tc_supported(8, 8, 8, 8, 100, 1) == 0      # W < 128: direct kernel instead
+    assert lib.cds_conv3d_k3_tc_supported(8, 16, 8, 8, 256, 2) == 0     # stride 2
+    z = torch.zeros(64, device=DEV, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        call("cds_conv3d_k3_tc", ptr(z), ptr(z), ptr(z), 1, 8, 8, 4, 4, 64, 1, ptr(z))
