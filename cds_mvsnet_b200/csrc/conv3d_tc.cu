@@ -15,6 +15,8 @@
 // Reference semantics: models/module.py:80-122 (Conv3d block), wired at :305-309.
 // Weights: fp16, pre-laid-out by the host (weights.py: pack_conv3d_tc) in exactly the smem image order:
 //   [mma j][k-chunk 2][n-group NPAD/8][8 rows n][8 halfs k]   (K-major, no swizzle; LBO = NPAD*16, SBO = 128).
+// For Cout = 8 the 8 padding columns of N = 16 carry the fp16 rounding residual of the weights (summed in the
+// epilogue), so those layers see effectively fp32-accurate weights at no extra tensor-core cost.
 #include "cds_common.cuh"
 #include "tc_common.cuh"
 #include "tma_host.h"
@@ -143,6 +145,13 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
         for (int c8 = 0; c8 < COUT / 8; ++c8) {
             float v[8];
             tc::tmem_ld8(taddr + c8 * 8, v);   // warp-collective: every lane executes it
+            if (COUT == 8) {
+                // N was padded 8 -> 16: columns 8..15 hold the product with the weights' fp16 rounding residual
+                float lo[8];
+                tc::tmem_ld8(taddr + 8, lo);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += lo[i];
+            }
             if (y < p.H && r < TXO) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

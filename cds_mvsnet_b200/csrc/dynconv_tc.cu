@@ -1,0 +1,380 @@
+// DynamicConv (A6) on the tensor cores: tcgen05.mma + TMEM + TMA, warp specialised.
+//
+// Reference: models/dynamic_conv.py:97-122.  One launch evaluates every kernel-size branch of a layer for a
+// batch of images as tap GEMMs without im2col (see tc_common.cuh):
+//   M = 128 consecutive pixels of an image row (a "row unit"; 128 - 2*halo of them are valid outputs),
+//   N = Cout feature channels + 3 curvature channels (a,b,c) of ONE branch (+ 3 columns carrying the fp16
+//       rounding residual of the curvature weights: the gate softmax(g/T) amplifies curvature error 100x), padded to 16,
+//   K = k*k taps x Cin (one 8-channel slab per tap and channel chunk; two slabs per K=16 MMA).
+// A CTA owns TY row units.  Warp roles (192 threads):
+//   warp 0      TMA producer: one cp.async.bulk.tensor for the haloed [TY+2h][128] pixel window (2 KB rows,
+//               zero fill outside the image = conv padding) + one bulk copy of the packed fp16 weights
+//   all warps   optional in-place InstanceNorm + LeakyReLU of the window (the PRODUCER layer's norm, applied
+//               by the consumer so it never costs a pass over HBM), then fence.proxy.async
+//   warp 1      MMA issuer: per row unit, all branches into one of two TMEM accumulator stages
+//   warps 2..5  epilogue: tcgen05.ld the unit's accumulators, curvature -> gate softmax -> blend the branches,
+//               write fp16 [n,H,W,8] + curvature maps, accumulate InstanceNorm statistics for the next layer
+// The MMA of unit u+1 overlaps the epilogue of unit u (tmem_full / tmem_empty mbarriers).
+//
+// Activations: channels-last fp16 with C = 8 (16 B per pixel), i.e. the full-resolution layers conv00 (image
+// padded to 8 channels), conv01 and out3 -- 60 % of the feature extractor's FLOPs.
+// Packed weights (host: weights.py pack_dynamic_conv_tc): per branch, per MMA j: [k-chunk 2][16/8][8 n][8 k] fp16.
+#include <algorithm>
+
+#include "cds_common.cuh"
+#include "tc_common.cuh"
+#include "tma_host.h"
+
+namespace {
+
+constexpr int TX = 128;
+constexpr int ROW_BYTES = TX * 16;
+constexpr int NPAD = 16;      // Cout (8) + 3 curvature channels, padded
+constexpr int COUT = 8;
+constexpr float kInEps = 1e-5f;
+
+template <int K0_, int K1_, int K2_>
+struct Cfg {
+    static constexpr int NK = K2_ > 0 ? 3 : 2;
+    static constexpr int K0 = K0_, K1 = K1_, K2 = K2_;
+    static constexpr int KMAX = K2_ > K1_ ? (K2_ > K0_ ? K2_ : K0_) : (K1_ > K0_ ? K1_ : K0_);
+    static constexpr int HALO = (KMAX - 1) / 2;
+    static constexpr int TXO = TX - 2 * HALO;    // valid outputs per row unit
+    __host__ __device__ static constexpr int ksize(int b) { return b == 0 ? K0_ : (b == 1 ? K1_ : K2_); }
+    __host__ __device__ static constexpr int nmma(int b) { return (ksize(b) * ksize(b) + 1) / 2; }
+    __host__ __device__ static constexpr int mma_base(int b) { return b == 0 ? 0 : (b == 1 ? nmma(0) : nmma(0) + nmma(1)); }
+    static constexpr int NMMA = nmma(0) + nmma(1) + (K2_ > 0 ? nmma(2) : 0);
+};
+
+// byte offset of tap t of a k x k branch inside the window, relative to the row unit's first row
+template <int HALO>
+__host__ __device__ constexpr uint32_t tap_off(int k, int t) {
+    return (uint32_t)((t / k + HALO - (k - 1) / 2) * ROW_BYTES + (t % k + HALO - (k - 1) / 2) * 16);
+}
+// low word of the A descriptor of MMA j of a k x k branch, minus the unit base: (start>>4) | (LBO>>4)<<16.
+// Slab order: [tap0, zero-weight pad], [tap1, tap2], ... (k*k is odd); LBO = distance to the second slab.
+template <int HALO>
+__host__ __device__ constexpr uint32_t a_desc_lo(int k, int j) {
+    uint32_t off0 = j == 0 ? tap_off<HALO>(k, 0) : tap_off<HALO>(k, 2 * j - 1);
+    uint32_t lbo = j == 0 ? 16u : tap_off<HALO>(k, 2 * j) - off0;
+    return (off0 >> 4) | ((lbo >> 4) << 16);
+}
+
+struct DynTcParams {
+    const int* img_index;     // item n reads image img_index[n] of the tensor map (NULL: n)
+    const double* in_stats;   // [n][8][2] (sum, sumsq) of the input, or NULL: input used as is
+    const float* epipole;     // [n][2]
+    const __half* wgt;        // packed fp16 B image
+    const float* bias;        // [NK][8] or NULL
+    const float* gate;        // W1f [4][NK], b1 [4], W2 [NK][4]
+    __half* out_raw;          // [n][H][W][8]
+    double* out_stats;        // [n][8][2] or NULL
+    float* norm_curv;         // [n][H][W] or NULL
+    float* nc_sq;             // [n][H][W] or NULL
+    float* nc_abs;            // [n][H][W] or NULL
+    int in_act, nc_mode, H, W;
+    float epi_scale, inv_temperature;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+template <class C, int B>
+__device__ __forceinline__ void issue_branch(uint32_t a_base, uint32_t b_base, uint32_t acc_col) {
+    constexpr uint32_t idesc = tc::instr_desc_f16(128, NPAD);
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t b_lo_const = ((uint32_t)(NPAD * 16) >> 4) << 16;
+    constexpr int k = C::ksize(B);
+#pragma unroll
+    for (int j = 0; j < C::nmma(B); ++j) {
+        const uint32_t a_lo = a_base + a_desc_lo<C::HALO>(k, j);
+        const uint32_t b_lo = b_base + ((((uint32_t)(C::mma_base(B) + j) * (2 * NPAD * 16)) >> 4) | b_lo_const);
+        tc::mma_f16(acc_col + B * NPAD, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, j > 0);
+    }
+}
+
+template <class C, int TY>
+__global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+    constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO;
+    constexpr int ROWS = TY + 2 * HALO;
+    constexpr uint32_t A_BYTES = ROWS * ROW_BYTES;
+    constexpr uint32_t B_BYTES = C::NMMA * 2 * NPAD * 16;
+    constexpr uint32_t STAGE_COLS = NK * NPAD;                      // 32 or 48 accumulator columns per row unit
+    constexpr uint32_t TMEM_COLS = 2 * STAGE_COLS <= 64 ? 64 : 128;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + A_BYTES;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES);
+    uint64_t* bar_full = bar_load + 1;    // [2]
+    uint64_t* bar_empty = bar_load + 3;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
+    float* s_norm = reinterpret_cast<float*>(bar_load + 6);   // [8][2] mean, rstd
+    float* s_red = s_norm + 16;                               // [4 warps][8][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.z;
+    const int x0 = min((int)blockIdx.x * TXO, p.W - TXO);   // last tile overlaps its neighbour (W >= TXO)
+    const int y0 = blockIdx.y * TY;
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x == 32) {
+        tc::mbar_init(bar_load, 1);
+        tc::mbar_init(bar_full, 1);
+        tc::mbar_init(bar_full + 1, 1);
+        tc::mbar_init(bar_empty, 4);
+        tc::mbar_init(bar_empty + 1, 4);
+        tc::mbar_fence_init();
+        tc::tma_prefetch_desc(&tmap);
+    }
+    if (p.in_stats && threadIdx.x >= 64 && threadIdx.x < 72) {
+        int c = threadIdx.x - 64;
+        double cnt = (double)p.H * p.W;
+        double s = p.in_stats[((size_t)n * 8 + c) * 2], ss = p.in_stats[((size_t)n * 8 + c) * 2 + 1];
+        double m = s / cnt, var = ss / cnt - m * m;
+        if (var < 0.0) var = 0.0;
+        s_norm[2 * c] = (float)m;
+        s_norm[2 * c + 1] = (float)(1.0 / sqrt(var + (double)kInEps));
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- producer: the haloed pixel window and the weights ---------------------------------------------------
+    if (threadIdx.x == 0) {
+        const int img = p.img_index ? __ldg(p.img_index + n) : n;
+        tc::mbar_expect_tx(bar_load, A_BYTES + B_BYTES);
+        tc::tma_load_4d(sA_u, &tmap, bar_load, 2 * (x0 - HALO), y0 - HALO, img, 0);
+        tc::bulk_copy_g2s(sB_u, p.wgt, B_BYTES, bar_load);
+    }
+    tc::mbar_wait(bar_load, 0);
+
+    // ---- the producer layer's InstanceNorm + activation, applied in place (zero padding stays zero) ---------
+    if (p.in_stats) {
+        for (int i = threadIdx.x; i < ROWS * TX; i += 192) {
+            int px = i % TX, ry = i / TX;
+            int gx = x0 - HALO + px, gy = y0 - HALO + ry;
+            if (gx < 0 || gx >= p.W || gy < 0 || gy >= p.H) continue;
+            uint4* q = reinterpret_cast<uint4*>(sA + (size_t)i * 16);
+            uint4 raw = *q;
+            __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]);
+                f.x = (f.x - s_norm[4 * j]) * s_norm[4 * j + 1];
+                f.y = (f.y - s_norm[4 * j + 2]) * s_norm[4 * j + 3];
+                if (p.in_act == 1) { f.x = f.x > 0.f ? f.x : 0.1f * f.x; f.y = f.y > 0.f ? f.y : 0.1f * f.y; }
+                h[j] = __floats2half2_rn(f.x, f.y);
+            }
+            *q = raw;
+        }
+        tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's operand reads
+        __syncthreads();
+    }
+
+    if (warp == 1) {
+        // ---- MMA issuer ------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int u = 0; u < TY; ++u) {
+                const int s = u & 1;
+                tc::mbar_wait(bar_empty + s, ((u >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+                tc::tc_fence_after();
+                const uint32_t a_base = (sA_u + (uint32_t)u * ROW_BYTES) >> 4;
+                const uint32_t acc = tmem + (uint32_t)s * STAGE_COLS;
+                issue_branch<C, 0>(a_base, sB_u >> 4, acc);
+                issue_branch<C, 1>(a_base, sB_u >> 4, acc);
+                if constexpr (NK == 3) issue_branch<C, 2>(a_base, sB_u >> 4, acc);
+                tc::mma_commit(bar_full + s);
+            }
+        }
+    } else if (warp >= 2) {
+        // ---- epilogue: gate + blend, one pixel per thread ---------------------------------------------------------
+        const int lg = warp & 3;                 // TMEM lane group this warp may read
+        const int r = lg * 32 + lane;            // MMA row = pixel x0 + r (valid while r < TXO)
+        const int gx = x0 + r;
+        const float ex = __ldg(p.epipole + 2 * n) * p.epi_scale, ey = __ldg(p.epipole + 2 * n + 1) * p.epi_scale;
+        float g_w1[4][NK], g_b1[4], g_w2[NK][4], bias[NK][COUT];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            g_b1[j] = __ldg(p.gate + 4 * NK + j);
+#pragma unroll
+            for (int b = 0; b < NK; ++b) { g_w1[j][b] = __ldg(p.gate + j * NK + b); g_w2[b][j] = __ldg(p.gate + 4 * NK + 4 + b * 4 + j); }
+        }
+#pragma unroll
+        for (int b = 0; b < NK; ++b)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) bias[b][c] = p.bias ? __ldg(p.bias + b * COUT + c) : 0.f;
+        float st_sum[COUT], st_sq[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+
+#pragma unroll 1
+        for (int u = 0; u < TY; ++u) {
+            const int s = u & 1;
+            tc::mbar_wait(bar_full + s, (u >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
+            float y[NK][COUT], abc[NK][8];
+#pragma unroll
+            for (int b = 0; b < NK; ++b) {
+                tc::tmem_ld8(taddr + b * NPAD, y[b]);
+                tc::tmem_ld8(taddr + b * NPAD + 8, abc[b]);
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + s);   // accumulators are in registers: the stage may be refilled
+
+            const int gy = y0 + u;
+            // tiles overlap at the right image edge (x0 is clamped): every pixel is owned by exactly one tile,
+            // which matters for the read-modify-write curvature accumulators and the statistics
+            const bool valid = r < TXO && gy < p.H && gx >= (int)blockIdx.x * TXO;
+            float uu = (float)gx - ex, vv = (float)gy - ey;
+            float rr = sqrtf(uu * uu + vv * vv) + 1e-6f;
+            uu /= rr;
+            vv /= rr;
+            float curv[NK];
+#pragma unroll
+            for (int b = 0; b < NK; ++b) {
+                // columns 8..10 = (a,b,c) from the fp16-rounded weights, 11..13 = from their rounding residuals
+                float ca = abc[b][0] + abc[b][3], cb = abc[b][1] + abc[b][4], cc = abc[b][2] + abc[b][5];
+                curv[b] = (ca * (uu * uu) + cb * (2.f * uu * vv)) + cc * (vv * vv);
+            }
+            float hdn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float t = g_b1[j];
+#pragma unroll
+                for (int b = 0; b < NK; ++b) t += g_w1[j][b] * curv[b];
+                hdn[j] = fmaxf(t, 0.f);
+            }
+            float lg_[NK], mx = -INFINITY;
+#pragma unroll
+            for (int b = 0; b < NK; ++b) {
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t += g_w2[b][j] * hdn[j];
+                lg_[b] = t * p.inv_temperature;
+                mx = fmaxf(mx, lg_[b]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int b = 0; b < NK; ++b) { lg_[b] = expf(lg_[b] - mx); den += lg_[b]; }
+            float out[COUT], nc = 0.f;
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) out[c] = 0.f;
+#pragma unroll
+            for (int b = 0; b < NK; ++b) {
+                float wgt = lg_[b] / den;
+                nc += curv[b] * wgt;
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) out[c] += wgt * (y[b][c] + bias[b][c]);
+            }
+            if (valid) {
+                size_t m = ((size_t)n * p.H + gy) * p.W + gx;
+                Vec8<__half>::store(p.out_raw + m * COUT, out);
+                if (p.norm_curv) p.norm_curv[m] = nc;
+                if (p.nc_sq) {
+                    if (p.nc_mode == 0) p.nc_sq[m] = nc * nc;
+                    else if (p.nc_mode == 1) p.nc_sq[m] = p.nc_sq[m] + nc * nc;
+                    else p.nc_sq[m] = (p.nc_sq[m] + nc * nc) / 3.f;
+                }
+                if (p.nc_abs) p.nc_abs[m] = fabsf(nc);
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) { st_sum[c] += out[c]; st_sq[c] += out[c] * out[c]; }
+            }
+        }
+        if (p.out_stats) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                float a = warp_sum(st_sum[c]), q = warp_sum(st_sq[c]);
+                if (lane == 0) { s_red[(lg * COUT + c) * 2] = a; s_red[(lg * COUT + c) * 2 + 1] = q; }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (p.out_stats && threadIdx.x < COUT * 2) {
+        double t = 0.0;
+        for (int w = 0; w < 4; ++w) t += (double)s_red[w * COUT * 2 + threadIdx.x];
+        atomicAdd(p.out_stats + (size_t)n * COUT * 2 + threadIdx.x, t);
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// fp32 planar images [n,3,H,W] -> fp16 [n,H,W,8] (channels 3..7 zero): the operand layout of the first layer
+__global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long HW, __half* __restrict__ out) {
+    const int n = blockIdx.y;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+        float v[8] = {__ldg(img + ((size_t)n * 3 + 0) * HW + i), __ldg(img + ((size_t)n * 3 + 1) * HW + i),
+                      __ldg(img + ((size_t)n * 3 + 2) * HW + i), 0.f, 0.f, 0.f, 0.f, 0.f};
+        Vec8<__half>::store(out + ((size_t)n * HW + i) * 8, v);
+    }
+}
+
+template <class C, int TY>
+int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::NMMA * 2 * NPAD * 16 + 8 * 6 + 16 * 4 + 64 * 4 + 16;
+    auto kern = dynconv_tc_kernel<C, TY>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cds_set_error("cds_dynamic_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    CUtensorMap tmap;
+    const uint64_t dims[4] = {2 * (uint64_t)p.W, (uint64_t)p.H, (uint64_t)n_images, 1};
+    const uint64_t strides[4] = {0, (uint64_t)p.W * 16, (uint64_t)p.H * p.W * 16, (uint64_t)n_images * p.H * p.W * 16};
+    const uint32_t box[4] = {2 * TX, (uint32_t)(TY + 2 * C::HALO), 1, 1};
+    if (!tma::make_u64(&tmap, x, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
+    dim3 grid(cds_div_up(p.W, C::TXO), cds_div_up(p.H, TY), n);
+    kern<<<grid, 192, smem, st>>>(tmap, p);
+    return cds_check_launch("cds_dynamic_conv_tc");
+}
+
+}  // namespace
+
+extern "C" {
+
+int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStream_t stream) {
+    CDS_REQUIRE(img && out && n > 0 && n <= 65535 && H > 0 && W > 0, CDS_EARG, "cds_image_to_nhwc8: bad arguments");
+    long long HW = (long long)H * W;
+    dim3 grid((unsigned)std::min<long long>(148 * 8, (HW + 255) / 256), n);
+    image_to_nhwc8_kernel<<<grid, 256, 0, stream>>>(img, HW, (__half*)out);
+    return cds_check_launch("cds_image_to_nhwc8");
+}
+
+// which (kernel sizes) the tensor-core DynamicConv covers: 8 -> 8 channels, W >= 128
+int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* ks) {
+    if (Cin != 8 || Cout != 8 || W < TX || H < 1 || !ks) return 0;
+    if (num_kernels == 3 && ks[0] == 3 && ks[1] == 7 && ks[2] == 11) return 1;
+    if (num_kernels == 3 && ks[0] == 3 && ks[1] == 5 && ks[2] == 7) return 1;
+    if (num_kernels == 2 && ks[0] == 1 && ks[1] == 3) return 1;
+    return 0;
+}
+
+int cds_dynamic_conv_tc_weight_halfs(int num_kernels, const int* ks) {
+    int n = 0;
+    for (int i = 0; i < num_kernels; ++i) n += (ks[i] * ks[i] + 1) / 2;
+    return n * 2 * NPAD * 8;
+}
+
+int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
+                        const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
+                        int n, int H, int W, int num_kernels, const int* kernel_sizes, float temperature, void* out_raw,
+                        double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream) {
+    CDS_REQUIRE(x && epipole && wgt_packed && gate && out_raw && kernel_sizes, CDS_EARG, "cds_dynamic_conv_tc: null pointer");
+    CDS_REQUIRE(n > 0 && n <= 65535 && n_images > 0, CDS_ESHAPE, "cds_dynamic_conv_tc: bad batch");
+    CDS_REQUIRE(temperature > 0.f, CDS_EARG, "cds_dynamic_conv_tc: temperature must be positive");
+    CDS_REQUIRE(cds_dynamic_conv_tc_supported(8, 8, H, W, num_kernels, kernel_sizes), CDS_EUNSUPPORTED,
+                "cds_dynamic_conv_tc: unsupported layer (needs 8->8 channels, W >= 128, kernel sets (3,7,11) (3,5,7) (1,3))");
+    DynTcParams p{};
+    p.img_index = img_index; p.in_stats = in_stats; p.epipole = epipole; p.wgt = (const __half*)wgt_packed; p.bias = bias;
+    p.gate = gate; p.out_raw = (__half*)out_raw; p.out_stats = out_stats; p.norm_curv = norm_curv; p.nc_sq = nc_sq;
+    p.nc_abs = nc_abs; p.in_act = in_act; p.nc_mode = nc_mode; p.H = H; p.W = W; p.epi_scale = epi_scale;
+    p.inv_temperature = 1.f / temperature;
+    if (num_kernels == 3 && kernel_sizes[2] == 11) return launch_dyn_tc<Cfg<3, 7, 11>, 8>(x, n_images, p, n, stream);
+    if (num_kernels == 3) return launch_dyn_tc<Cfg<3, 5, 7>, 8>(x, n_images, p, n, stream);
+    return launch_dyn_tc<Cfg<1, 3, 0>, 8>(x, n_images, p, n, stream);
+}
+
+}  // extern "C"

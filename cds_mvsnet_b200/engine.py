@@ -10,6 +10,7 @@ items are exactly the ``ref_fea [V,B,...]`` the cost-volume kernels want and the
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -59,10 +60,12 @@ class FeatureExtractor:
 
     N_STATS = 13
 
-    def __init__(self, fw, storage=torch.float16):
+    def __init__(self, fw, storage=torch.float16, use_tc=True):
         self.fw = fw
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
+        self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0"   # tcgen05 DynamicConv where covered
+        self._buf = None
 
     def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
              nc_mode, nc_abs, norm_curv=None):
@@ -72,6 +75,19 @@ class FeatureExtractor:
         flops = 2.0 * sum(k * k for k in w.ksizes) * w.cin * (w.cout + 3) * px
         nbytes = px * (w.cin * (4 if in_mode == 1 else e) + w.cout * e + 8)
         _lib.set_tag("feat." + name, (flops, float(nbytes)))
+        ks = _ksizes(w.ksizes)
+        if (self.use_tc and w.tc is not None and self.storage == torch.float16
+                and _lib.LIB.load().cds_dynamic_conv_tc_supported(8, w.cout, H, W, len(w.ksizes), ks)):
+            n_images = n
+            if in_mode == 1:   # planar fp32 images -> fp16 [*,H,W,8] once per forward
+                n_images = x.shape[0]
+                img8 = self._buf.get("f.img8", (n_images, H, W, 8), torch.float16)
+                call("cds_image_to_nhwc8", ptr(x), n_images, H, W, ptr(img8))
+                x = img8
+            call("cds_dynamic_conv_tc", ptr(x), n_images, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
+                 ptr(w.tc), ptr(w.bias), ptr(w.gate), n, H, W, len(w.ksizes), ks, float(T), ptr(out), ptr(out_stats),
+                 ptr(norm_curv), ptr(nc_sq), nc_mode, ptr(nc_abs))
+            return
         call("cds_dynamic_conv", ptr(x), in_mode, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
              ptr(w.w_att), ptr(w.w_conv), ptr(w.bias), ptr(w.gate), n, w.cin, w.cout, H, W, len(w.ksizes),
              _ksizes(w.ksizes), float(T), self.dt, ptr(out), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode,
@@ -81,6 +97,8 @@ class FeatureExtractor:
         """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
         Returns {stage: (fea [n,h,w,C] storage dtype, nc_sq [n,h,w] fp32, nc_abs [n,h,w] fp32)}."""
         st, dt = self.storage, self.dt
+        self._buf = buf
+        imgs = imgs.reshape(-1, 3, H, W)
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         e = _esize(st)
         stats = buf.get("f.stats", (self.N_STATS, n, 32, 2), torch.float64)
@@ -152,7 +170,7 @@ class Regulariser:
         self.cw = cw
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
-        self.use_tc = use_tc   # tensor-core (tcgen05) kernels where a layer shape is covered
+        self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0"   # tcgen05 kernels where covered
         self.tag = "cr"
 
     def _conv(self, name, x, B, D, H, W, stride, out):

@@ -146,6 +146,7 @@ class DynamicConv(_CachedModule):
         self.thresh_scale = thresh_scale
         self.in_c, self.out_c = in_c, out_c
         self.storage = kwargs.pop("storage", DEFAULT_STORAGE)
+        self.use_tc = kwargs.pop("use_tc", True)
         self.att_convs = nn.ModuleList([nn.Conv2d(in_c, 3, k, padding=(k - 1) // 2, bias=False) for k in size_kernels])
         self.convs = nn.ModuleList([nn.Conv2d(in_c, out_c, k, padding=(k - 1) // 2, stride=stride, bias=bias)
                                     for k in size_kernels])
@@ -168,14 +169,28 @@ class DynamicConv(_CachedModule):
                                                                    self.size_kernels, dev))
         w = self._cache
         dt = _lib.dtype_code(self.storage)
-        if C == 3:
-            x, mode = _f32c(feature_vol), 1
-        else:
-            x, mode = _nhwc(feature_vol, self.storage), 0
         raw = torch.empty(B, H, Wd, self.out_c, dtype=self.storage, device=dev)
         nc = torch.empty(B, 1, H, Wd, dtype=torch.float32, device=dev)
         ks = (ctypes.c_int * len(w.ksizes))(*w.ksizes)
         epi = _f32c(epipole)
+        if (self.use_tc and self.storage == torch.float16 and self.in_c in (3, 8) and self.out_c == 8
+                and _lib.LIB.load().cds_dynamic_conv_tc_supported(8, 8, H, Wd, len(w.ksizes), ks)):
+            # tensor-core path (tcgen05): 8-channel fp16 pixels, image zero-padded from 3 channels
+            if w.tc is None:
+                w.tc = W.pack_dynamic_conv_tc(w)
+            if C == 3:
+                x8 = torch.empty(B, H, Wd, 8, dtype=torch.float16, device=dev)
+                xc = _f32c(feature_vol)
+                call("cds_image_to_nhwc8", ptr(xc), B, H, Wd, ptr(x8))
+            else:
+                x8 = _nhwc(feature_vol, torch.float16)
+            call("cds_dynamic_conv_tc", ptr(x8), B, None, None, ACT_NONE, ptr(epi), 1.0, ptr(w.tc), ptr(w.bias), ptr(w.gate),
+                 B, H, Wd, len(w.ksizes), ks, float(temperature), ptr(raw), None, ptr(nc), None, 0, None)
+            return _nchw(raw), nc
+        if C == 3:
+            x, mode = _f32c(feature_vol), 1
+        else:
+            x, mode = _nhwc(feature_vol, self.storage), 0
         call("cds_dynamic_conv", ptr(x), mode, None, None, ACT_NONE, ptr(epi), 1.0, ptr(w.w_att), ptr(w.w_conv),
              ptr(w.bias), ptr(w.gate), B, self.in_c, self.out_c, H, Wd, len(w.ksizes), ks, float(temperature), dt,
              ptr(raw), None, ptr(nc), None, 0, None)

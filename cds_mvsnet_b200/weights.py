@@ -45,6 +45,7 @@ class DynWeights:
     w_conv: torch.Tensor   # [sum k*k, Cin, Cout]
     bias: torch.Tensor | None  # [K, Cout]
     gate: torch.Tensor     # 4K + 4 + 4K floats
+    tc: torch.Tensor | None = None   # fp16 tensor-core operand image (8 -> 8 channel layers)
 
 
 def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
@@ -66,6 +67,36 @@ def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
     f32 = dict(dtype=torch.float32, device=device)
     return DynWeights(cin, cout, tuple(ksizes), torch.cat(att).to(**f32).contiguous(), torch.cat(conv).to(**f32).contiguous(),
                       torch.stack(bias).to(**f32).contiguous() if bias else None, gate.to(**f32).contiguous())
+
+
+def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
+    """fp16 B-operand image for csrc/dynconv_tc.cu (8 -> 8 channel layers; Cin 3 is zero-padded to 8).
+
+    Per branch, taps in (ky, kx) order as 8-channel slabs [tap0, zero pad, tap1, tap2, ...] (k*k is odd), two
+    slabs per MMA; per MMA [k-chunk 2][n-group 2][8 n][8 k] with n = 8 feature channels, (a, b, c) rounded to
+    fp16, then the rounding residuals of (a, b, c)."""
+    assert w.cout == 8 and w.cin in (3, 8)
+    att, conv = w.w_att.detach().double().cpu(), w.w_conv.detach().double().cpu()
+    imgs, t0 = [], 0
+    for k in w.ksizes:
+        ntap = k * k
+        slabs = [0, None] + list(range(1, ntap))
+        img = torch.zeros(len(slabs) // 2, 2, 2, 8, 8, dtype=torch.float64)
+        for s, t in enumerate(slabs):
+            if t is None:
+                continue
+            full = torch.zeros(8, 16, dtype=torch.float64)               # [k (cin), n]
+            full[:w.cin, :8] = conv[t0 + t]
+            # curvature weights as hi + lo fp16 pairs in the spare N columns: the gate is softmax(g / T) with
+            # T = 0.01, so the curvature channels are the precision-critical ones
+            a = att[t0 + t][:, :3]
+            hi = a.to(torch.float16).to(torch.float64)
+            full[:w.cin, 8:11] = hi
+            full[:w.cin, 11:14] = a - hi
+            img[s // 2, s % 2] = full.t().reshape(2, 8, 8)
+        imgs.append(img)
+        t0 += ntap
+    return torch.cat(imgs).to(dtype=torch.float16, device=w.w_conv.device).contiguous()
 
 
 def pack_conv2d(sd, key, device) -> torch.Tensor:
@@ -128,6 +159,10 @@ def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
         blk = w[t, c * 8:(c + 1) * 8, :]                            # [8 k, Cout]
         full = torch.zeros(8, npad, dtype=torch.float64)
         full[:, :co] = blk
+        if co == 8:   # N is padded to 16 anyway: the spare columns carry the fp16 rounding residual of the weights
+            hi = blk.to(torch.float16).to(torch.float64)
+            full[:, :8] = hi
+            full[:, 8:16] = blk - hi
         img[s // 2, s % 2] = full.t().reshape(npad // 8, 8, 8)      # [n-group, n row, k]
     return img.to(dtype=torch.float16, device=l.w.device).contiguous()
 
@@ -159,6 +194,8 @@ class FeatureWeights:
 
 def pack_feature(sd, device) -> FeatureWeights:
     dyn = {n: pack_dynamic_conv(sd, pre, ci, co, ks, device) for n, (ci, co, ks, pre) in DYN_LAYERS.items()}
+    for n in ("conv00", "conv01", "out3"):
+        dyn[n].tc = pack_dynamic_conv_tc(dyn[n])
     return FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
                           pack_conv2d(sd, "feature.downsample2.conv.weight", device),
                           pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16).contiguous(),

@@ -333,3 +333,27 @@ def test_conv3d_tcgen05_unsupported_shapes():
     z = torch.zeros(64, device=DEV, dtype=torch.float16)
     with pytest.raises(RuntimeError, match="unsupported"):
         call("cds_conv3d_k3_tc", ptr(z), ptr(z), ptr(z), 1, 8, 8, 4, 4, 64, 1, ptr(z))
+
+
+# ---------------------------------------------------------------------------------------- A6 on tensor cores
+@pytest.mark.parametrize("name", ["conv00", "conv01", "out3"])
+@pytest.mark.parametrize("hw", [(37, 200), (64, 128), (16, 333)])
+def test_dynamic_conv_tcgen05_vs_oracle(pretrained_sd, name, hw):
+    """tcgen05 DynamicConv (8 -> 8 channel layers) against the oracle and against the CUDA-core kernel."""
+    cin, cout, ks, pre = W.DYN_LAYERS[name]
+    torch.manual_seed(hash(name) % 1000 + hw[1])
+    x = (torch.rand(2, cin, *hw) if cin == 3 else torch.randn(2, cin, *hw)).half().float()
+    epi = torch.tensor([[hw[1] * 1.7, -hw[0] * 0.6], [-30.0, hw[0] / 2.0]])
+    sd = {k[len(pre) + 1:]: v for k, v in pretrained_sd.items() if k.startswith(pre + ".")}
+    ref_y, ref_nc = O.dynamic_conv(x, pretrained_sd, pre, ks, epi, T)
+    outs = {}
+    for use_tc in (True, False):
+        m = C.DynamicConv(cin, cout, size_kernels=ks, bias=name.startswith("out"), storage=torch.float16, use_tc=use_tc)
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()
+        y, nc = m(cu(x), epipole=cu(epi), temperature=T)
+        torch.cuda.synchronize()
+        outs[use_tc] = (y.cpu(), nc.cpu())
+        assert O.rel_l1(y.cpu(), ref_y) < 4e-3, (use_tc, O.rel_l1(y.cpu(), ref_y))
+        assert O.rel_l1(nc.cpu(), ref_nc) < 4e-3, (use_tc, O.rel_l1(nc.cpu(), ref_nc))
+    assert O.rel_l1(outs[True][0], outs[False][0]) < 4e-3
