@@ -96,19 +96,22 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
     }
     // ---- MMA issue, spread over the warps: lane 0 of warp w issues the MMAs of row units w, w+4, ... ------------
     // (the issue rate of ONE thread, ~50 cycles per descriptor+MMA, would otherwise bound an 8-cycle N=16 MMA)
-    if (lane == 0 && warp < TY) {
+    const uint32_t warp_u = tc::uniform((uint32_t)warp);
+    const uint32_t tmem_u = tc::uniform(tmem);
+    if (warp_u < (uint32_t)TY) {
         tc::mbar_wait(bar_load, 0);
         tc::tc_fence_after();
+        const bool elected = tc::elect_one();
         constexpr uint32_t idesc = tc::instr_desc_f16(128, NPAD);
         // Descriptors: hi word is constant (SBO = 128 B, version 1); lo word = (start >> 4) | (LBO >> 4) << 16.
         // The j loop is fully unrolled so every slab offset / LBO is a compile-time constant.
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
         constexpr uint32_t b_lo_const = ((uint32_t)(NPAD * 16) >> 4) << 16;
 #pragma unroll 1
-        for (int u = warp; u < TY; u += 4) {
-            const uint32_t a_base = (sA_u + (uint32_t)u * ROW_BYTES) >> 4;
+        for (uint32_t u = warp_u; u < (uint32_t)TY; u += 4) {
+            const uint32_t a_base = (sA_u + u * ROW_BYTES) >> 4;
             const uint32_t b_base = sB_u >> 4;
-            const uint32_t acc_col = tmem + (uint32_t)u * NPAD;
+            const uint32_t acc_col = tmem_u + u * NPAD;
 #pragma unroll
             for (int j = 0; j < NMMA; ++j) {
                 uint32_t off0, lbo;
@@ -125,10 +128,10 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
                 const uint32_t b_lo = b_base + (((uint32_t)j * (2 * NPAD * 16)) >> 4 | b_lo_const);
                 const uint64_t da = ((uint64_t)desc_hi << 32) | a_lo;
                 const uint64_t db = ((uint64_t)desc_hi << 32) | b_lo;
-                tc::mma_f16(acc_col, da, db, idesc, j > 0);
+                if (elected) tc::mma_f16(acc_col, da, db, idesc, j > 0);
             }
         }
-        tc::mma_commit(bar_mma);
+        if (elected) tc::mma_commit(bar_mma);
     }
     __syncwarp();
     tc::mbar_wait(bar_mma, 0);

@@ -3,9 +3,10 @@
 // Reference: models/dynamic_conv.py:97-122.  One launch evaluates every kernel-size branch of a layer for a
 // batch of images as tap GEMMs without im2col (see tc_common.cuh):
 //   M = 128 consecutive pixels of an image row (a "row unit"; 128 - 2*halo of them are valid outputs),
-//   N = Cout feature channels + 3 curvature channels (a,b,c) of ONE branch (+ 3 columns carrying the fp16
-//       rounding residual of the curvature weights: the gate softmax(g/T) amplifies curvature error 100x), padded to 16,
-//   K = k*k taps x Cin (one 8-channel slab per tap and channel chunk; two slabs per K=16 MMA).
+//   N = per branch 8 feature channels + 3 curvature channels (a,b,c) (+ 3 columns carrying the fp16 rounding
+//       residual of the curvature weights: the gate softmax(g/T) amplifies curvature error 100x), padded to 16;
+//       ALL branches side by side (N = 32 or 48), embedded in the kmax x kmax tap grid,
+//   K = kmax*kmax taps x 8 channels (one 8-channel slab per tap; two slabs per K=16 MMA).
 // A CTA owns TY row units.  Warp roles (192 threads):
 //   warp 0      TMA producer: one cp.async.bulk.tensor for the haloed [TY+2h][128] pixel window (2 KB rows,
 //               zero fill outside the image = conv padding) + one bulk copy of the packed fp16 weights
@@ -18,8 +19,11 @@
 //
 // Activations: channels-last fp16 with C = 8 (16 B per pixel), i.e. the full-resolution layers conv00 (image
 // padded to 8 channels), conv01 and out3 -- 60 % of the feature extractor's FLOPs.
-// Packed weights (host: weights.py pack_dynamic_conv_tc): per branch, per MMA j: [k-chunk 2][16/8][8 n][8 k] fp16.
+// Packed weights (host: weights.py pack_dynamic_conv_tc): first the MMAs of the inner KIN x KIN taps
+// ([k-chunk 2][NK*16/8][8 n][8 k] fp16 each, branch b in columns [16b, 16b+16), zero where its kernel has no such
+// tap), then the MMAs of the outer ring ([k-chunk 2][2][8 n][8 k], largest kernel only).
 #include <algorithm>
+#include <utility>
 
 #include "cds_common.cuh"
 #include "tc_common.cuh"
@@ -29,7 +33,8 @@ namespace {
 
 constexpr int TX = 128;
 constexpr int ROW_BYTES = TX * 16;
-constexpr int NPAD = 16;      // Cout (8) + 3 curvature channels, padded
+constexpr int NPAD = 16;      // per branch: Cout (8) + 3 curvature channels (+3 residual columns), padded
+constexpr int NPAD_ = NPAD;
 constexpr int COUT = 8;
 constexpr float kInEps = 1e-5f;
 
@@ -40,10 +45,26 @@ struct Cfg {
     static constexpr int KMAX = K2_ > K1_ ? (K2_ > K0_ ? K2_ : K0_) : (K1_ > K0_ ? K1_ : K0_);
     static constexpr int HALO = (KMAX - 1) / 2;
     static constexpr int TXO = TX - 2 * HALO;    // valid outputs per row unit
-    __host__ __device__ static constexpr int ksize(int b) { return b == 0 ? K0_ : (b == 1 ? K1_ : K2_); }
-    __host__ __device__ static constexpr int nmma(int b) { return (ksize(b) * ksize(b) + 1) / 2; }
-    __host__ __device__ static constexpr int mma_base(int b) { return b == 0 ? 0 : (b == 1 ? nmma(0) : nmma(0) + nmma(1)); }
-    static constexpr int NMMA = nmma(0) + nmma(1) + (K2_ > 0 ? nmma(2) : 0);
+    // Branches are embedded in the KMAX x KMAX tap grid.  The tensor core re-reads the 4 KB A operand from shared
+    // memory for every MMA (>= 32 cycles whatever N is), so one wide MMA per tap pair beats one narrow MMA per
+    // branch and tap.  Taps inside the second-largest kernel's support (KIN x KIN) feed ALL branches (N = NK*16,
+    // zero weights where a smaller kernel has no tap); the outer ring only exists for the largest kernel (N = 16).
+    static constexpr int KIN = NK == 3 ? (K1_ > K0_ ? K1_ : K0_) : K0_;
+    static constexpr int NALL = NK * NPAD_;
+    static constexpr int NIN = KIN * KIN, NRING = KMAX * KMAX - KIN * KIN;   // taps (NIN odd, NRING even)
+    static constexpr int MMA_IN = (NIN + 1) / 2, MMA_RING = NRING / 2;
+    static constexpr int NMMA = MMA_IN + MMA_RING;
+    static constexpr int B_BYTES = MMA_IN * 2 * NALL * 16 + MMA_RING * 2 * NPAD_ * 16;
+    // i-th tap (row-major order) of the outer ring, as an index into the KMAX x KMAX grid
+    __host__ __device__ static constexpr int ring_tap(int i) {
+        int lo = (KMAX - KIN) / 2, hi = lo + KIN, c = 0;
+        for (int t = 0; t < KMAX * KMAX; ++t) {
+            int y = t / KMAX, x = t % KMAX;
+            bool inner = y >= lo && y < hi && x >= lo && x < hi;
+            if (!inner) { if (c == i) return t; ++c; }
+        }
+        return 0;
+    }
 };
 
 // byte offset of tap t of a k x k branch inside the window, relative to the row unit's first row
@@ -80,27 +101,51 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-template <class C, int B>
-__device__ __forceinline__ void issue_branch(uint32_t a_base, uint32_t b_base, uint32_t acc_col) {
-    constexpr uint32_t idesc = tc::instr_desc_f16(128, NPAD);
+// ring MMA J as a template parameter: forces the tap-table lookups (constexpr loops) to compile-time constants
+template <class C, int J>
+__device__ __forceinline__ void issue_ring_one(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t idesc = tc::instr_desc_f16(128, NPAD);
     constexpr uint32_t b_lo_const = ((uint32_t)(NPAD * 16) >> 4) << 16;
-    constexpr int k = C::ksize(B);
+    constexpr uint32_t b_ring = (uint32_t)(C::MMA_IN * 2 * C::NALL * 16);
+    constexpr uint32_t off0 = tap_off<C::HALO>(C::KMAX, C::ring_tap(2 * J));
+    constexpr uint32_t off1 = tap_off<C::HALO>(C::KMAX, C::ring_tap(2 * J + 1));
+    constexpr uint32_t a_const = (off0 >> 4) | (((off1 - off0) >> 4) << 16);
+    constexpr uint32_t b_const = ((b_ring + (uint32_t)J * (2 * NPAD * 16)) >> 4) | b_lo_const;
+    if (elected)
+        tc::mma_f16(acc_col + (C::NK - 1) * NPAD, ((uint64_t)desc_hi << 32) | (a_base + a_const),
+                    ((uint64_t)desc_hi << 32) | (b_base + b_const), idesc, true);
+}
+template <class C, int... J>
+__device__ __forceinline__ void issue_ring(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected,
+                                           std::integer_sequence<int, J...>) {
+    (issue_ring_one<C, J>(a_base, b_base, acc_col, elected), ...);
+}
+
+template <class C>
+__device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    {   // inner KIN x KIN taps: every branch, N = NALL.  Slabs [tap0, zero pad], [tap1, tap2], ...
+        constexpr uint32_t idesc = tc::instr_desc_f16(128, C::NALL);
+        constexpr uint32_t b_lo_const = ((uint32_t)(C::NALL * 16) >> 4) << 16;
 #pragma unroll
-    for (int j = 0; j < C::nmma(B); ++j) {
-        const uint32_t a_lo = a_base + a_desc_lo<C::HALO>(k, j);
-        const uint32_t b_lo = b_base + ((((uint32_t)(C::mma_base(B) + j) * (2 * NPAD * 16)) >> 4) | b_lo_const);
-        tc::mma_f16(acc_col + B * NPAD, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, j > 0);
+        for (int j = 0; j < C::MMA_IN; ++j) {
+            const uint32_t a_lo = a_base + a_desc_lo<C::HALO>(C::KIN, j);
+            const uint32_t b_lo = b_base + ((((uint32_t)j * (2 * C::NALL * 16)) >> 4) | b_lo_const);
+            if (elected) tc::mma_f16(acc_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, j > 0);
+        }
     }
+    // outer ring: only the largest kernel has these taps, N = 16 into the last branch's columns
+    issue_ring<C>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_RING>{});
 }
 
 template <class C, int TY>
-__global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+__global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
     constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO;
     constexpr int ROWS = TY + 2 * HALO;
     constexpr uint32_t A_BYTES = ROWS * ROW_BYTES;
-    constexpr uint32_t B_BYTES = C::NMMA * 2 * NPAD * 16;
-    constexpr uint32_t STAGE_COLS = NK * NPAD;                      // 32 or 48 accumulator columns per row unit
+    constexpr uint32_t B_BYTES = C::B_BYTES;
+    constexpr uint32_t STAGE_COLS = C::NALL;                        // 32 or 48 accumulator columns per row unit
     constexpr uint32_t TMEM_COLS = 2 * STAGE_COLS <= 64 ? 64 : 128;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
@@ -111,6 +156,8 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
     float* s_norm = reinterpret_cast<float*>(bar_load + 6);   // [8][2] mean, rstd
     float* s_red = s_norm + 16;                               // [4 warps][8][2]
+    float* s_gate = s_red + 64;                               // W1f [4][NK], b1 [4], W2 [NK][4]  (<= 28 floats)
+    float* s_bias = s_gate + 28;                              // [NK][8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.z;
@@ -137,6 +184,8 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
         s_norm[2 * c] = (float)m;
         s_norm[2 * c + 1] = (float)(1.0 / sqrt(var + (double)kInEps));
     }
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + 8 * NK + 4) s_gate[threadIdx.x - 96] = __ldg(p.gate + threadIdx.x - 96);
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + NK * COUT) s_bias[threadIdx.x - 128] = p.bias ? __ldg(p.bias + threadIdx.x - 128) : 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -175,21 +224,20 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
     }
 
     if (warp == 1) {
-        // ---- MMA issuer ------------------------------------------------------------------------------------------
-        if (lane == 0) {
-            tc::tc_fence_after();
+        // ---- MMA issuer: the warp stays converged, one elected lane issues ------------------------------------------
+        tc::tc_fence_after();
+        const bool elected = tc::elect_one();
+        const uint32_t tmem_u = tc::uniform(tmem);
 #pragma unroll 1
-            for (int u = 0; u < TY; ++u) {
-                const int s = u & 1;
-                tc::mbar_wait(bar_empty + s, ((u >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
-                tc::tc_fence_after();
-                const uint32_t a_base = (sA_u + (uint32_t)u * ROW_BYTES) >> 4;
-                const uint32_t acc = tmem + (uint32_t)s * STAGE_COLS;
-                issue_branch<C, 0>(a_base, sB_u >> 4, acc);
-                issue_branch<C, 1>(a_base, sB_u >> 4, acc);
-                if constexpr (NK == 3) issue_branch<C, 2>(a_base, sB_u >> 4, acc);
-                tc::mma_commit(bar_full + s);
-            }
+        for (uint32_t u = 0; u < (uint32_t)TY; ++u) {
+            const uint32_t s = u & 1;
+            tc::mbar_wait(bar_empty + s, ((u >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+            tc::tc_fence_after();
+            const uint32_t a_base = (sA_u + u * ROW_BYTES) >> 4;
+            const uint32_t acc = tmem_u + s * STAGE_COLS;
+            issue_unit<C>(a_base, sB_u >> 4, acc, elected);
+            if (elected) tc::mma_commit(bar_full + s);
+            __syncwarp();
         }
     } else if (warp >= 2) {
         // ---- epilogue: gate + blend, one pixel per thread ---------------------------------------------------------
@@ -197,17 +245,6 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
         const int r = lg * 32 + lane;            // MMA row = pixel x0 + r (valid while r < TXO)
         const int gx = x0 + r;
         const float ex = __ldg(p.epipole + 2 * n) * p.epi_scale, ey = __ldg(p.epipole + 2 * n + 1) * p.epi_scale;
-        float g_w1[4][NK], g_b1[4], g_w2[NK][4], bias[NK][COUT];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            g_b1[j] = __ldg(p.gate + 4 * NK + j);
-#pragma unroll
-            for (int b = 0; b < NK; ++b) { g_w1[j][b] = __ldg(p.gate + j * NK + b); g_w2[b][j] = __ldg(p.gate + 4 * NK + 4 + b * 4 + j); }
-        }
-#pragma unroll
-        for (int b = 0; b < NK; ++b)
-#pragma unroll
-            for (int c = 0; c < COUT; ++c) bias[b][c] = p.bias ? __ldg(p.bias + b * COUT + c) : 0.f;
         float st_sum[COUT], st_sq[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
@@ -218,12 +255,13 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
             tc::mbar_wait(bar_full + s, (u >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
-            float y[NK][COUT], abc[NK][8];
+            uint32_t yr[NK][COUT], ar[NK][8];
 #pragma unroll
             for (int b = 0; b < NK; ++b) {
-                tc::tmem_ld8(taddr + b * NPAD, y[b]);
-                tc::tmem_ld8(taddr + b * NPAD + 8, abc[b]);
+                tc::tmem_ld8_nowait(taddr + b * NPAD, yr[b]);
+                tc::tmem_ld8_nowait(taddr + b * NPAD + 8, ar[b]);
             }
+            tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + s);   // accumulators are in registers: the stage may be refilled
@@ -233,22 +271,24 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
             // which matters for the read-modify-write curvature accumulators and the statistics
             const bool valid = r < TXO && gy < p.H && gx >= (int)blockIdx.x * TXO;
             float uu = (float)gx - ex, vv = (float)gy - ey;
-            float rr = sqrtf(uu * uu + vv * vv) + 1e-6f;
-            uu /= rr;
-            vv /= rr;
+            float rinv = __frcp_rn(sqrtf(uu * uu + vv * vv) + 1e-6f);
+            uu *= rinv;
+            vv *= rinv;
             float curv[NK];
 #pragma unroll
             for (int b = 0; b < NK; ++b) {
                 // columns 8..10 = (a,b,c) from the fp16-rounded weights, 11..13 = from their rounding residuals
-                float ca = abc[b][0] + abc[b][3], cb = abc[b][1] + abc[b][4], cc = abc[b][2] + abc[b][5];
+                float ca = __uint_as_float(ar[b][0]) + __uint_as_float(ar[b][3]);
+                float cb = __uint_as_float(ar[b][1]) + __uint_as_float(ar[b][4]);
+                float cc = __uint_as_float(ar[b][2]) + __uint_as_float(ar[b][5]);
                 curv[b] = (ca * (uu * uu) + cb * (2.f * uu * vv)) + cc * (vv * vv);
             }
             float hdn[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float t = g_b1[j];
+                float t = s_gate[4 * NK + j];
 #pragma unroll
-                for (int b = 0; b < NK; ++b) t += g_w1[j][b] * curv[b];
+                for (int b = 0; b < NK; ++b) t += s_gate[j * NK + b] * curv[b];
                 hdn[j] = fmaxf(t, 0.f);
             }
             float lg_[NK], mx = -INFINITY;
@@ -256,22 +296,23 @@ __global__ void __launch_bounds__(192) dynconv_tc_kernel(const __grid_constant__
             for (int b = 0; b < NK; ++b) {
                 float t = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) t += g_w2[b][j] * hdn[j];
+                for (int j = 0; j < 4; ++j) t += s_gate[4 * NK + 4 + b * 4 + j] * hdn[j];
                 lg_[b] = t * p.inv_temperature;
                 mx = fmaxf(mx, lg_[b]);
             }
             float den = 0.f;
 #pragma unroll
-            for (int b = 0; b < NK; ++b) { lg_[b] = expf(lg_[b] - mx); den += lg_[b]; }
+            for (int b = 0; b < NK; ++b) { lg_[b] = __expf(lg_[b] - mx); den += lg_[b]; }
+            const float dinv = __frcp_rn(den);
             float out[COUT], nc = 0.f;
 #pragma unroll
             for (int c = 0; c < COUT; ++c) out[c] = 0.f;
 #pragma unroll
             for (int b = 0; b < NK; ++b) {
-                float wgt = lg_[b] / den;
+                float wgt = lg_[b] * dinv;
                 nc += curv[b] * wgt;
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) out[c] += wgt * (y[b][c] + bias[b][c]);
+                for (int c = 0; c < COUT; ++c) out[c] += wgt * (__uint_as_float(yr[b][c]) + s_bias[b * COUT + c]);
             }
             if (valid) {
                 size_t m = ((size_t)n * p.H + gy) * p.W + gx;
@@ -317,7 +358,7 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long H
 
 template <class C, int TY>
 int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::NMMA * 2 * NPAD * 16 + 8 * 6 + 16 * 4 + 64 * 4 + 16;
+    constexpr size_t smem = (size_t)(TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 + (16 + 64 + 28 + 24) * 4 + 16;
     auto kern = dynconv_tc_kernel<C, TY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cds_set_error("cds_dynamic_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -353,9 +394,11 @@ int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kerne
 }
 
 int cds_dynamic_conv_tc_weight_halfs(int num_kernels, const int* ks) {
-    int n = 0;
-    for (int i = 0; i < num_kernels; ++i) n += (ks[i] * ks[i] + 1) / 2;
-    return n * 2 * NPAD * 8;
+    int kmax = 0, kin = 0;
+    for (int i = 0; i < num_kernels; ++i) kmax = ks[i] > kmax ? ks[i] : kmax;
+    for (int i = 0; i < num_kernels; ++i) if (ks[i] < kmax && ks[i] > kin) kin = ks[i];
+    int nin = (kin * kin + 1) / 2, nring = (kmax * kmax - kin * kin) / 2;
+    return (nin * 2 * (num_kernels * NPAD) + nring * 2 * NPAD) * 8;
 }
 
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,

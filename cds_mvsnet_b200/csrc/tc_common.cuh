@@ -99,6 +99,23 @@ __host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One elected lane of a converged warp (the issue loops run warp-convergent with warp-uniform operands so the
+// descriptors live in uniform registers; only the tcgen05 instruction itself is under the elect predicate --
+// computing operands inside a divergent `lane == 0` region costs an R2UR "waterfall" loop per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp-uniform copy of a value every lane holds (lets the compiler keep it in a uniform register)
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
     uint32_t acc = accumulate ? 1u : 0u;
@@ -127,5 +144,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// batched form: issue several loads, then ONE wait
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 }  // namespace tc

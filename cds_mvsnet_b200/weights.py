@@ -72,31 +72,46 @@ def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
 def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     """fp16 B-operand image for csrc/dynconv_tc.cu (8 -> 8 channel layers; Cin 3 is zero-padded to 8).
 
-    Per branch, taps in (ky, kx) order as 8-channel slabs [tap0, zero pad, tap1, tap2, ...] (k*k is odd), two
-    slabs per MMA; per MMA [k-chunk 2][n-group 2][8 n][8 k] with n = 8 feature channels, (a, b, c) rounded to
-    fp16, then the rounding residuals of (a, b, c)."""
+    Every branch is embedded in the kmax x kmax tap grid.  Inner taps (support of the second-largest kernel), in
+    (ky, kx) order as 8-channel slabs [tap0, zero pad, tap1, tap2, ...], two slabs per MMA, feed all branches:
+    per MMA [k-chunk 2][n-group 2K][8 n][8 k], branch b owning columns [16b, 16b+16) = 8 feature channels, (a, b, c)
+    rounded to fp16, the rounding residuals of (a, b, c).  The outer-ring taps follow, for the largest kernel only:
+    per MMA [k-chunk 2][n-group 2][8 n][8 k]."""
     assert w.cout == 8 and w.cin in (3, 8)
     att, conv = w.w_att.detach().double().cpu(), w.w_conv.detach().double().cpu()
-    imgs, t0 = [], 0
-    for k in w.ksizes:
-        ntap = k * k
-        slabs = [0, None] + list(range(1, ntap))
-        img = torch.zeros(len(slabs) // 2, 2, 2, 8, 8, dtype=torch.float64)
-        for s, t in enumerate(slabs):
-            if t is None:
-                continue
-            full = torch.zeros(8, 16, dtype=torch.float64)               # [k (cin), n]
-            full[:w.cin, :8] = conv[t0 + t]
-            # curvature weights as hi + lo fp16 pairs in the spare N columns: the gate is softmax(g / T) with
-            # T = 0.01, so the curvature channels are the precision-critical ones
-            a = att[t0 + t][:, :3]
-            hi = a.to(torch.float16).to(torch.float64)
-            full[:w.cin, 8:11] = hi
-            full[:w.cin, 11:14] = a - hi
-            img[s // 2, s % 2] = full.t().reshape(2, 8, 8)
-        imgs.append(img)
-        t0 += ntap
-    return torch.cat(imgs).to(dtype=torch.float16, device=w.w_conv.device).contiguous()
+    K, kmax = len(w.ksizes), max(w.ksizes)
+    ntap = kmax * kmax
+    full = torch.zeros(ntap, 8, 16 * K, dtype=torch.float64)           # [tap, k (cin), n]
+    t0 = 0
+    for b, k in enumerate(w.ksizes):
+        o = (kmax - k) // 2
+        for ky in range(k):
+            for kx in range(k):
+                t = (ky + o) * kmax + (kx + o)
+                src = t0 + ky * k + kx
+                full[t, :w.cin, 16 * b:16 * b + 8] = conv[src]
+                a = att[src][:, :3]
+                hi = a.to(torch.float16).to(torch.float64)
+                full[t, :w.cin, 16 * b + 8:16 * b + 11] = hi
+                full[t, :w.cin, 16 * b + 11:16 * b + 14] = a - hi
+        t0 += k * k
+    # inner taps (support of the second-largest kernel): all branches; outer ring: the largest kernel only
+    kin = max(k for k in w.ksizes if k < kmax)
+    lo, hi = (kmax - kin) // 2, (kmax - kin) // 2 + kin
+    inner = [t for t in range(ntap) if lo <= t // kmax < hi and lo <= t % kmax < hi]
+    ring = [t for t in range(ntap) if not (lo <= t // kmax < hi and lo <= t % kmax < hi)]
+    slabs = [inner[0], None] + inner[1:]
+    img_in = torch.zeros(len(slabs) // 2, 2, 2 * K, 8, 8, dtype=torch.float64)
+    for s, t in enumerate(slabs):
+        if t is not None:
+            img_in[s // 2, s % 2] = full[t].t().reshape(2 * K, 8, 8)
+    assert len(ring) % 2 == 0
+    img_ring = torch.zeros(len(ring) // 2, 2, 2, 8, 8, dtype=torch.float64)
+    for s, t in enumerate(ring):
+        assert full[t, :, :16 * (K - 1)].abs().max() == 0     # only the largest kernel reaches the ring
+        img_ring[s // 2, s % 2] = full[t, :, 16 * (K - 1):].t().reshape(2, 8, 8)
+    out = torch.cat((img_in.reshape(-1), img_ring.reshape(-1)))
+    return out.to(dtype=torch.float16, device=w.w_conv.device).contiguous()
 
 
 def pack_conv2d(sd, key, device) -> torch.Tensor:
