@@ -278,10 +278,9 @@ def main():
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
+    from cds_mvsnet_b200 import parallel
+    ms_total = parallel.max_over_ranks(ms_total, dev)   # the slowest rank's interval
+    ms_e2e = parallel.max_over_ranks(ms_e2e, dev)
 
     if rank != 0:
         if world > 1:
