@@ -17,8 +17,9 @@
 //               write fp16 [n,H,W,8] + curvature maps, accumulate InstanceNorm statistics for the next layer
 // The MMA of unit u+1 overlaps the epilogue of unit u (tmem_full / tmem_empty mbarriers).
 //
-// Activations: channels-last fp16 with C = 8 (16 B per pixel), i.e. the full-resolution layers conv00 (image
-// padded to 8 channels), conv01 and out3 -- 60 % of the feature extractor's FLOPs.
+// Activations: channels-last fp16 [n,H,W,C], C in {8,16,32} (conv00's image is padded to 8 channels).  For C = 8 a
+// pixel row is one contiguous 2 KB TMA row; for C > 8 each 8-channel chunk is fetched by its own TMA box
+// (16-byte inner extent) so that shared memory still holds one slab per chunk.
 // Packed weights (host: weights.py pack_dynamic_conv_tc): first the MMAs of the inner KIN x KIN taps
 // ([k-chunk 2][NK*16/8][8 n][8 k] fp16 each, branch b in columns [16b, 16b+16), zero where its kernel has no such
 // tap), then the MMAs of the outer ring ([k-chunk 2][2][8 n][8 k], largest kernel only).
@@ -33,28 +34,31 @@ namespace {
 
 constexpr int TX = 128;
 constexpr int ROW_BYTES = TX * 16;
-constexpr int NPAD = 16;      // per branch: Cout (8) + 3 curvature channels (+3 residual columns), padded
-constexpr int NPAD_ = NPAD;
-constexpr int COUT = 8;
 constexpr float kInEps = 1e-5f;
 
-template <int K0_, int K1_, int K2_>
+template <int K0_, int K1_, int K2_, int CIN_, int COUT_>
 struct Cfg {
     static constexpr int NK = K2_ > 0 ? 3 : 2;
+    static constexpr int CIN = CIN_, COUT = COUT_, C8 = CIN_ / 8;
     static constexpr int K0 = K0_, K1 = K1_, K2 = K2_;
     static constexpr int KMAX = K2_ > K1_ ? (K2_ > K0_ ? K2_ : K0_) : (K1_ > K0_ ? K1_ : K0_);
     static constexpr int HALO = (KMAX - 1) / 2;
     static constexpr int TXO = TX - 2 * HALO;    // valid outputs per row unit
+    // per branch: COUT feature columns, (a,b,c) from fp16-rounded curvature weights, (a,b,c) from their residuals
+    static constexpr int NPAD = (COUT_ + 6 + 15) / 16 * 16;
     // Branches are embedded in the KMAX x KMAX tap grid.  The tensor core re-reads the 4 KB A operand from shared
     // memory for every MMA (>= 32 cycles whatever N is), so one wide MMA per tap pair beats one narrow MMA per
-    // branch and tap.  Taps inside the second-largest kernel's support (KIN x KIN) feed ALL branches (N = NK*16,
-    // zero weights where a smaller kernel has no tap); the outer ring only exists for the largest kernel (N = 16).
+    // branch and tap.  Taps inside the second-largest kernel's support (KIN x KIN) feed ALL branches (N = NK*NPAD,
+    // zero weights where a smaller kernel has no tap); the outer ring only exists for the largest kernel (N = NPAD).
     static constexpr int KIN = NK == 3 ? (K1_ > K0_ ? K1_ : K0_) : K0_;
-    static constexpr int NALL = NK * NPAD_;
+    static constexpr int NALL = NK * NPAD;
     static constexpr int NIN = KIN * KIN, NRING = KMAX * KMAX - KIN * KIN;   // taps (NIN odd, NRING even)
-    static constexpr int MMA_IN = (NIN + 1) / 2, MMA_RING = NRING / 2;
+    // K = 16 per MMA = two 8-channel slabs: for C8 = 1 two consecutive taps (first inner MMA = [tap0, zero pad]),
+    // for C8 > 1 two channel chunks of the same tap
+    static constexpr int MMA_IN = C8 == 1 ? (NIN + 1) / 2 : NIN * C8 / 2;
+    static constexpr int MMA_RING = C8 == 1 ? NRING / 2 : NRING * C8 / 2;
     static constexpr int NMMA = MMA_IN + MMA_RING;
-    static constexpr int B_BYTES = MMA_IN * 2 * NALL * 16 + MMA_RING * 2 * NPAD_ * 16;
+    static constexpr int B_BYTES = MMA_IN * 2 * NALL * 16 + MMA_RING * 2 * NPAD * 16;
     // i-th tap (row-major order) of the outer ring, as an index into the KMAX x KMAX grid
     __host__ __device__ static constexpr int ring_tap(int i) {
         int lo = (KMAX - KIN) / 2, hi = lo + KIN, c = 0;
@@ -72,24 +76,15 @@ template <int HALO>
 __host__ __device__ constexpr uint32_t tap_off(int k, int t) {
     return (uint32_t)((t / k + HALO - (k - 1) / 2) * ROW_BYTES + (t % k + HALO - (k - 1) / 2) * 16);
 }
-// low word of the A descriptor of MMA j of a k x k branch, minus the unit base: (start>>4) | (LBO>>4)<<16.
-// Slab order: [tap0, zero-weight pad], [tap1, tap2], ... (k*k is odd); LBO = distance to the second slab.
-template <int HALO>
-__host__ __device__ constexpr uint32_t a_desc_lo(int k, int j) {
-    uint32_t off0 = j == 0 ? tap_off<HALO>(k, 0) : tap_off<HALO>(k, 2 * j - 1);
-    uint32_t lbo = j == 0 ? 16u : tap_off<HALO>(k, 2 * j) - off0;
-    return (off0 >> 4) | ((lbo >> 4) << 16);
-}
-
 struct DynTcParams {
     const int* img_index;     // item n reads image img_index[n] of the tensor map (NULL: n)
-    const double* in_stats;   // [n][8][2] (sum, sumsq) of the input, or NULL: input used as is
+    const double* in_stats;   // [n][CIN][2] (sum, sumsq) of the input, or NULL: input used as is
     const float* epipole;     // [n][2]
     const __half* wgt;        // packed fp16 B image
-    const float* bias;        // [NK][8] or NULL
+    const float* bias;        // [NK][COUT] or NULL
     const float* gate;        // W1f [4][NK], b1 [4], W2 [NK][4]
-    __half* out_raw;          // [n][H][W][8]
-    double* out_stats;        // [n][8][2] or NULL
+    __half* out_raw;          // [n][H][W][COUT]
+    double* out_stats;        // [n][COUT][2] or NULL
     float* norm_curv;         // [n][H][W] or NULL
     float* nc_sq;             // [n][H][W] or NULL
     float* nc_abs;            // [n][H][W] or NULL
@@ -101,52 +96,49 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-// ring MMA J as a template parameter: forces the tap-table lookups (constexpr loops) to compile-time constants
-template <class C, int J>
-__device__ __forceinline__ void issue_ring_one(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
+// MMA J of a tap group as a template parameter: forces every table lookup to a compile-time constant.
+// RING = false: inner KIN x KIN taps, all branches (N = NALL); RING = true: outer ring, largest kernel only.
+template <class C, int CHUNK, bool RING, int J>
+__device__ __forceinline__ void issue_one(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    constexpr uint32_t idesc = tc::instr_desc_f16(128, NPAD);
-    constexpr uint32_t b_lo_const = ((uint32_t)(NPAD * 16) >> 4) << 16;
-    constexpr uint32_t b_ring = (uint32_t)(C::MMA_IN * 2 * C::NALL * 16);
-    constexpr uint32_t off0 = tap_off<C::HALO>(C::KMAX, C::ring_tap(2 * J));
-    constexpr uint32_t off1 = tap_off<C::HALO>(C::KMAX, C::ring_tap(2 * J + 1));
-    constexpr uint32_t a_const = (off0 >> 4) | (((off1 - off0) >> 4) << 16);
-    constexpr uint32_t b_const = ((b_ring + (uint32_t)J * (2 * NPAD * 16)) >> 4) | b_lo_const;
+    constexpr int N = RING ? C::NPAD : C::NALL;
+    constexpr uint32_t idesc = tc::instr_desc_f16(128, N);
+    constexpr uint32_t b_lo_const = ((uint32_t)(N * 16) >> 4) << 16;            // LBO of B: between its two k-chunks
+    constexpr uint32_t b_off = (RING ? (uint32_t)(C::MMA_IN * 2 * C::NALL * 16) : 0u) + (uint32_t)J * (2 * N * 16);
+    constexpr int k = RING ? C::KMAX : C::KIN;
+    constexpr uint32_t off0 = C::C8 == 1
+        ? (RING ? tap_off<C::HALO>(k, C::ring_tap(2 * J)) : (J == 0 ? tap_off<C::HALO>(k, 0) : tap_off<C::HALO>(k, 2 * J - 1)))
+        : (uint32_t)((2 * J) % C::C8) * CHUNK + tap_off<C::HALO>(k, RING ? C::ring_tap((2 * J) / C::C8) : (2 * J) / C::C8);
+    constexpr uint32_t lbo = C::C8 == 1
+        ? (RING ? tap_off<C::HALO>(k, C::ring_tap(2 * J + 1)) - off0 : (J == 0 ? 16u : tap_off<C::HALO>(k, 2 * J) - off0))
+        : (uint32_t)CHUNK;
+    constexpr uint32_t a_const = (off0 >> 4) | ((lbo >> 4) << 16);
+    constexpr uint32_t b_const = (b_off >> 4) | b_lo_const;
+    constexpr bool first = !RING && J == 0;
     if (elected)
-        tc::mma_f16(acc_col + (C::NK - 1) * NPAD, ((uint64_t)desc_hi << 32) | (a_base + a_const),
-                    ((uint64_t)desc_hi << 32) | (b_base + b_const), idesc, true);
+        tc::mma_f16(acc_col + (RING ? (C::NK - 1) * C::NPAD : 0), ((uint64_t)desc_hi << 32) | (a_base + a_const),
+                    ((uint64_t)desc_hi << 32) | (b_base + b_const), idesc, !first);
 }
-template <class C, int... J>
-__device__ __forceinline__ void issue_ring(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected,
-                                           std::integer_sequence<int, J...>) {
-    (issue_ring_one<C, J>(a_base, b_base, acc_col, elected), ...);
+template <class C, int CHUNK, bool RING, int... J>
+__device__ __forceinline__ void issue_group(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected,
+                                            std::integer_sequence<int, J...>) {
+    (issue_one<C, CHUNK, RING, J>(a_base, b_base, acc_col, elected), ...);
 }
-
-template <class C>
+template <class C, int CHUNK>
 __device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
-    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    {   // inner KIN x KIN taps: every branch, N = NALL.  Slabs [tap0, zero pad], [tap1, tap2], ...
-        constexpr uint32_t idesc = tc::instr_desc_f16(128, C::NALL);
-        constexpr uint32_t b_lo_const = ((uint32_t)(C::NALL * 16) >> 4) << 16;
-#pragma unroll
-        for (int j = 0; j < C::MMA_IN; ++j) {
-            const uint32_t a_lo = a_base + a_desc_lo<C::HALO>(C::KIN, j);
-            const uint32_t b_lo = b_base + ((((uint32_t)j * (2 * C::NALL * 16)) >> 4) | b_lo_const);
-            if (elected) tc::mma_f16(acc_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, j > 0);
-        }
-    }
-    // outer ring: only the largest kernel has these taps, N = 16 into the last branch's columns
-    issue_ring<C>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_RING>{});
+    issue_group<C, CHUNK, false>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_IN>{});
+    issue_group<C, CHUNK, true>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_RING>{});
 }
 
 template <class C, int TY>
-__global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
-    constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO;
+__global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+    constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO, C8 = C::C8, CIN = C::CIN, COUT = C::COUT, NPAD = C::NPAD;
     constexpr int ROWS = TY + 2 * HALO;
-    constexpr uint32_t A_BYTES = ROWS * ROW_BYTES;
+    constexpr uint32_t CHUNK = ROWS * ROW_BYTES;                    // one 8-channel slab of the window
+    constexpr uint32_t A_BYTES = C8 * CHUNK;
     constexpr uint32_t B_BYTES = C::B_BYTES;
-    constexpr uint32_t STAGE_COLS = C::NALL;                        // 32 or 48 accumulator columns per row unit
-    constexpr uint32_t TMEM_COLS = 2 * STAGE_COLS <= 64 ? 64 : 128;
+    constexpr uint32_t STAGE_COLS = C::NALL;                        // accumulator columns per row unit
+    constexpr uint32_t TMEM_COLS = 2 * STAGE_COLS <= 64 ? 64 : (2 * STAGE_COLS <= 128 ? 128 : 256);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + A_BYTES;
@@ -154,14 +146,14 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
     uint64_t* bar_full = bar_load + 1;    // [2]
     uint64_t* bar_empty = bar_load + 3;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
-    float* s_norm = reinterpret_cast<float*>(bar_load + 6);   // [8][2] mean, rstd
-    float* s_red = s_norm + 16;                               // [4 warps][8][2]
-    float* s_gate = s_red + 64;                               // W1f [4][NK], b1 [4], W2 [NK][4]  (<= 28 floats)
-    float* s_bias = s_gate + 28;                              // [NK][8]
+    float* s_norm = reinterpret_cast<float*>(bar_load + 6);   // [CIN][2] mean, rstd
+    float* s_red = s_norm + 2 * CIN;                          // [4 warps][COUT][2]
+    float* s_gate = s_red + 4 * COUT * 2;                     // W1f [4][NK], b1 [4], W2 [NK][4]  (<= 28 floats)
+    float* s_bias = s_gate + 28;                              // [NK][COUT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.z;
-    const int x0 = min((int)blockIdx.x * TXO, p.W - TXO);   // last tile overlaps its neighbour (W >= TXO)
+    const int x0 = min((int)blockIdx.x * TXO, p.W - TXO);   // last tile overlaps its neighbour (W >= TX)
     const int y0 = blockIdx.y * TY;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
 
@@ -175,10 +167,10 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
         tc::mbar_fence_init();
         tc::tma_prefetch_desc(&tmap);
     }
-    if (p.in_stats && threadIdx.x >= 64 && threadIdx.x < 72) {
+    if (p.in_stats && threadIdx.x >= 64 && threadIdx.x < 64 + CIN) {
         int c = threadIdx.x - 64;
         double cnt = (double)p.H * p.W;
-        double s = p.in_stats[((size_t)n * 8 + c) * 2], ss = p.in_stats[((size_t)n * 8 + c) * 2 + 1];
+        double s = p.in_stats[((size_t)n * CIN + c) * 2], ss = p.in_stats[((size_t)n * CIN + c) * 2 + 1];
         double m = s / cnt, var = ss / cnt - m * m;
         if (var < 0.0) var = 0.0;
         s_norm[2 * c] = (float)m;
@@ -186,34 +178,41 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + 8 * NK + 4) s_gate[threadIdx.x - 96] = __ldg(p.gate + threadIdx.x - 96);
     if (threadIdx.x >= 128 && threadIdx.x < 128 + NK * COUT) s_bias[threadIdx.x - 128] = p.bias ? __ldg(p.bias + threadIdx.x - 128) : 0.f;
+    for (int i = threadIdx.x; i < 4 * COUT * 2; i += 192) s_red[i] = 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // ---- producer: the haloed pixel window and the weights ---------------------------------------------------
+    // ---- producer: the haloed pixel window (one TMA per 8-channel chunk) and the weights ---------------------
     if (threadIdx.x == 0) {
         const int img = p.img_index ? __ldg(p.img_index + n) : n;
         tc::mbar_expect_tx(bar_load, A_BYTES + B_BYTES);
-        tc::tma_load_4d(sA_u, &tmap, bar_load, 2 * (x0 - HALO), y0 - HALO, img, 0);
+        if (C8 == 1) {
+            tc::tma_load_4d(sA_u, &tmap, bar_load, 2 * (x0 - HALO), y0 - HALO, img, 0);
+        } else {
+#pragma unroll
+            for (int c8 = 0; c8 < C8; ++c8) tc::tma_load_5d(sA_u + c8 * CHUNK, &tmap, bar_load, 0, c8, x0 - HALO, y0 - HALO, img);
+        }
         tc::bulk_copy_g2s(sB_u, p.wgt, B_BYTES, bar_load);
     }
     tc::mbar_wait(bar_load, 0);
 
     // ---- the producer layer's InstanceNorm + activation, applied in place (zero padding stays zero) ---------
     if (p.in_stats) {
-        for (int i = threadIdx.x; i < ROWS * TX; i += 192) {
-            int px = i % TX, ry = i / TX;
+        for (int i = threadIdx.x; i < C8 * ROWS * TX; i += 192) {
+            int px = i % TX, ry = (i / TX) % ROWS, c8 = i / (TX * ROWS);
             int gx = x0 - HALO + px, gy = y0 - HALO + ry;
             if (gx < 0 || gx >= p.W || gy < 0 || gy >= p.H) continue;
             uint4* q = reinterpret_cast<uint4*>(sA + (size_t)i * 16);
             uint4 raw = *q;
             __half2* h = reinterpret_cast<__half2*>(&raw);
+            const float* nm = s_norm + c8 * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float2 f = __half22float2(h[j]);
-                f.x = (f.x - s_norm[4 * j]) * s_norm[4 * j + 1];
-                f.y = (f.y - s_norm[4 * j + 2]) * s_norm[4 * j + 3];
+                f.x = (f.x - nm[4 * j]) * nm[4 * j + 1];
+                f.y = (f.y - nm[4 * j + 2]) * nm[4 * j + 3];
                 if (p.in_act == 1) { f.x = f.x > 0.f ? f.x : 0.1f * f.x; f.y = f.y > 0.f ? f.y : 0.1f * f.y; }
                 h[j] = __floats2half2_rn(f.x, f.y);
             }
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
             tc::tc_fence_after();
             const uint32_t a_base = (sA_u + u * ROW_BYTES) >> 4;
             const uint32_t acc = tmem_u + s * STAGE_COLS;
-            issue_unit<C>(a_base, sB_u >> 4, acc, elected);
+            issue_unit<C, (int)CHUNK>(a_base, sB_u >> 4, acc, elected);
             if (elected) tc::mma_commit(bar_full + s);
             __syncwarp();
         }
@@ -245,9 +244,10 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
         const int r = lg * 32 + lane;            // MMA row = pixel x0 + r (valid while r < TXO)
         const int gx = x0 + r;
         const float ex = __ldg(p.epipole + 2 * n) * p.epi_scale, ey = __ldg(p.epipole + 2 * n + 1) * p.epi_scale;
-        float st_sum[COUT], st_sq[COUT];
+        constexpr bool REG_STATS = COUT <= 16;   // per-thread statistics accumulators only while they fit in registers
+        float st_sum[REG_STATS ? COUT : 1], st_sq[REG_STATS ? COUT : 1];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+        for (int c = 0; c < (REG_STATS ? COUT : 1); ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
 
 #pragma unroll 1
         for (int u = 0; u < TY; ++u) {
@@ -255,16 +255,11 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
             tc::mbar_wait(bar_full + s, (u >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
-            uint32_t yr[NK][COUT], ar[NK][8];
+            // 1. curvature columns of every branch -> gate weights
+            uint32_t ar[NK][8];
 #pragma unroll
-            for (int b = 0; b < NK; ++b) {
-                tc::tmem_ld8_nowait(taddr + b * NPAD, yr[b]);
-                tc::tmem_ld8_nowait(taddr + b * NPAD + 8, ar[b]);
-            }
+            for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + b * NPAD + COUT, ar[b]);
             tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + s);   // accumulators are in registers: the stage may be refilled
 
             const int gy = y0 + u;
             // tiles overlap at the right image edge (x0 is clamped): every pixel is owned by exactly one tile,
@@ -277,7 +272,7 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
             float curv[NK];
 #pragma unroll
             for (int b = 0; b < NK; ++b) {
-                // columns 8..10 = (a,b,c) from the fp16-rounded weights, 11..13 = from their rounding residuals
+                // (a,b,c) from the fp16-rounded weights + from their rounding residuals
                 float ca = __uint_as_float(ar[b][0]) + __uint_as_float(ar[b][3]);
                 float cb = __uint_as_float(ar[b][1]) + __uint_as_float(ar[b][4]);
                 float cc = __uint_as_float(ar[b][2]) + __uint_as_float(ar[b][5]);
@@ -291,32 +286,58 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
                 for (int b = 0; b < NK; ++b) t += s_gate[j * NK + b] * curv[b];
                 hdn[j] = fmaxf(t, 0.f);
             }
-            float lg_[NK], mx = -INFINITY;
+            float wgt[NK], mx = -INFINITY;
 #pragma unroll
             for (int b = 0; b < NK; ++b) {
                 float t = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) t += s_gate[4 * NK + 4 + b * 4 + j] * hdn[j];
-                lg_[b] = t * p.inv_temperature;
-                mx = fmaxf(mx, lg_[b]);
+                wgt[b] = t * p.inv_temperature;
+                mx = fmaxf(mx, wgt[b]);
             }
-            float den = 0.f;
+            float den = 0.f, nc = 0.f;
 #pragma unroll
-            for (int b = 0; b < NK; ++b) { lg_[b] = __expf(lg_[b] - mx); den += lg_[b]; }
+            for (int b = 0; b < NK; ++b) { wgt[b] = __expf(wgt[b] - mx); den += wgt[b]; }
             const float dinv = __frcp_rn(den);
-            float out[COUT], nc = 0.f;
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) out[c] = 0.f;
+            for (int b = 0; b < NK; ++b) { wgt[b] *= dinv; nc += curv[b] * wgt[b]; }
+
+            // 2. feature columns, 8 channels at a time: blend the branches, store, statistics
+            const size_t m = ((size_t)n * p.H + gy) * p.W + gx;
 #pragma unroll
-            for (int b = 0; b < NK; ++b) {
-                float wgt = lg_[b] * dinv;
-                nc += curv[b] * wgt;
+            for (int c8 = 0; c8 < COUT / 8; ++c8) {
+                uint32_t yr[NK][8];
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) out[c] += wgt * (__uint_as_float(yr[b][c]) + s_bias[b * COUT + c]);
+                for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + b * NPAD + c8 * 8, yr[b]);
+                tc::tmem_ld_wait();
+                float out[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) out[c] = 0.f;
+#pragma unroll
+                for (int b = 0; b < NK; ++b)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) out[c] += wgt[b] * (__uint_as_float(yr[b][c]) + s_bias[b * COUT + c8 * 8 + c]);
+                if (valid) Vec8<__half>::store(p.out_raw + m * COUT + c8 * 8, out);
+                if (p.out_stats) {
+                    if constexpr (REG_STATS) {
+                        if (valid) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) { st_sum[c8 * 8 + c] += out[c]; st_sq[c8 * 8 + c] += out[c] * out[c]; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float a = warp_sum(valid ? out[c] : 0.f), q = warp_sum(valid ? out[c] * out[c] : 0.f);
+                            if (lane == 0) { s_red[(lg * COUT + c8 * 8 + c) * 2] += a; s_red[(lg * COUT + c8 * 8 + c) * 2 + 1] += q; }
+                        }
+                    }
+                }
             }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + s);   // every accumulator column has been read: the stage may be refilled
+
             if (valid) {
-                size_t m = ((size_t)n * p.H + gy) * p.W + gx;
-                Vec8<__half>::store(p.out_raw + m * COUT, out);
                 if (p.norm_curv) p.norm_curv[m] = nc;
                 if (p.nc_sq) {
                     if (p.nc_mode == 0) p.nc_sq[m] = nc * nc;
@@ -324,15 +345,15 @@ __global__ void __launch_bounds__(192, 3) dynconv_tc_kernel(const __grid_constan
                     else p.nc_sq[m] = (p.nc_sq[m] + nc * nc) / 3.f;
                 }
                 if (p.nc_abs) p.nc_abs[m] = fabsf(nc);
-#pragma unroll
-                for (int c = 0; c < COUT; ++c) { st_sum[c] += out[c]; st_sq[c] += out[c] * out[c]; }
             }
         }
-        if (p.out_stats) {
+        if constexpr (REG_STATS) {
+            if (p.out_stats) {
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) {
-                float a = warp_sum(st_sum[c]), q = warp_sum(st_sq[c]);
-                if (lane == 0) { s_red[(lg * COUT + c) * 2] = a; s_red[(lg * COUT + c) * 2 + 1] = q; }
+                for (int c = 0; c < COUT; ++c) {
+                    float a = warp_sum(st_sum[c]), q = warp_sum(st_sq[c]);
+                    if (lane == 0) { s_red[(lg * COUT + c) * 2] = a; s_red[(lg * COUT + c) * 2 + 1] = q; }
+                }
             }
         }
     }
@@ -358,18 +379,42 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long H
 
 template <class C, int TY>
 int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 + (16 + 64 + 28 + 24) * 4 + 16;
+    constexpr size_t smem = (size_t)C::C8 * (TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 +
+                            (2 * C::CIN + 8 * C::COUT + 28 + C::NK * C::COUT) * 4 + 16;
+    static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
     auto kern = dynconv_tc_kernel<C, TY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cds_set_error("cds_dynamic_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     CUtensorMap tmap;
-    const uint64_t dims[4] = {2 * (uint64_t)p.W, (uint64_t)p.H, (uint64_t)n_images, 1};
-    const uint64_t strides[4] = {0, (uint64_t)p.W * 16, (uint64_t)p.H * p.W * 16, (uint64_t)n_images * p.H * p.W * 16};
-    const uint32_t box[4] = {2 * TX, (uint32_t)(TY + 2 * C::HALO), 1, 1};
-    if (!tma::make_u64(&tmap, x, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
+    const uint64_t H = p.H, W = p.W, NI = n_images;
+    bool ok;
+    if (C::C8 == 1) {   // 16-byte pixels: 8-byte elements so that a box row is 2 KB (128 pixels)
+        const uint64_t dims[4] = {2 * W, H, NI, 1};
+        const uint64_t strides[4] = {0, W * 16, H * W * 16, NI * H * W * 16};
+        const uint32_t box[4] = {2 * TX, (uint32_t)(TY + 2 * C::HALO), 1, 1};
+        ok = tma::make_u64(&tmap, x, 4, dims, strides, box);
+    } else {            // (8 ch, chunk, W, H, image): one box per 8-channel chunk lands as a slab
+        const uint64_t dims[5] = {8, (uint64_t)C::C8, W, H, NI};
+        const uint64_t strides[5] = {0, 16, (uint64_t)C::CIN * 2, W * C::CIN * 2, H * W * C::CIN * 2};
+        const uint32_t box[5] = {8, 1, TX, (uint32_t)(TY + 2 * C::HALO), 1};
+        ok = tma::make_f16(&tmap, x, 5, dims, strides, box);
+    }
+    if (!ok) return CDS_EUNSUPPORTED;
     dim3 grid(cds_div_up(p.W, C::TXO), cds_div_up(p.H, TY), n);
     kern<<<grid, 192, smem, st>>>(tmap, p);
     return cds_check_launch("cds_dynamic_conv_tc");
+}
+
+// the layer shapes of the feature extractor (models/module.py:211-234); 0 = not covered
+int layer_id(int Cin, int Cout, int nk, const int* ks) {
+    if (!ks) return 0;
+    if (Cin == 8 && Cout == 8 && nk == 3 && ks[0] == 3 && ks[1] == 7 && ks[2] == 11) return 1;   // conv00 (image padded)
+    if (Cin == 8 && Cout == 8 && nk == 3 && ks[0] == 3 && ks[1] == 5 && ks[2] == 7) return 2;    // conv01
+    if (Cin == 8 && Cout == 8 && nk == 2 && ks[0] == 1 && ks[1] == 3) return 3;                  // out3
+    if (Cin == 16 && Cout == 16 && nk == 2 && ks[0] == 3 && ks[1] == 5) return 4;                // conv10, conv11
+    if (Cin == 16 && Cout == 16 && nk == 2 && ks[0] == 1 && ks[1] == 3) return 5;                // out2
+    if (Cin == 32 && Cout == 32 && nk == 2 && ks[0] == 1 && ks[1] == 3) return 6;                // conv20, conv21, out1
+    return 0;
 }
 
 }  // namespace
@@ -384,40 +429,45 @@ int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStr
     return cds_check_launch("cds_image_to_nhwc8");
 }
 
-// which (kernel sizes) the tensor-core DynamicConv covers: 8 -> 8 channels, W >= 128
+// 1 when the tensor-core DynamicConv covers this layer (the feature extractor's shapes, W >= 128)
 int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* ks) {
-    if (Cin != 8 || Cout != 8 || W < TX || H < 1 || !ks) return 0;
-    if (num_kernels == 3 && ks[0] == 3 && ks[1] == 7 && ks[2] == 11) return 1;
-    if (num_kernels == 3 && ks[0] == 3 && ks[1] == 5 && ks[2] == 7) return 1;
-    if (num_kernels == 2 && ks[0] == 1 && ks[1] == 3) return 1;
-    return 0;
+    if (W < TX || H < 1) return 0;
+    return layer_id(Cin, Cout, num_kernels, ks) != 0;
 }
 
-int cds_dynamic_conv_tc_weight_halfs(int num_kernels, const int* ks) {
-    int kmax = 0, kin = 0;
+int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks) {
+    int kmax = 0, kin = 0, c8 = Cin / 8, npad = (Cout + 6 + 15) / 16 * 16;
     for (int i = 0; i < num_kernels; ++i) kmax = ks[i] > kmax ? ks[i] : kmax;
     for (int i = 0; i < num_kernels; ++i) if (ks[i] < kmax && ks[i] > kin) kin = ks[i];
-    int nin = (kin * kin + 1) / 2, nring = (kmax * kmax - kin * kin) / 2;
-    return (nin * 2 * (num_kernels * NPAD) + nring * 2 * NPAD) * 8;
+    int nin = kin * kin, nring = kmax * kmax - nin;
+    int mma_in = c8 == 1 ? (nin + 1) / 2 : nin * c8 / 2, mma_ring = c8 == 1 ? nring / 2 : nring * c8 / 2;
+    return (mma_in * 2 * (num_kernels * npad) + mma_ring * 2 * npad) * 8;
 }
 
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
                         const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
-                        int n, int H, int W, int num_kernels, const int* kernel_sizes, float temperature, void* out_raw,
-                        double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream) {
+                        int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
+                        void* out_raw, double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs,
+                        cudaStream_t stream) {
     CDS_REQUIRE(x && epipole && wgt_packed && gate && out_raw && kernel_sizes, CDS_EARG, "cds_dynamic_conv_tc: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && n_images > 0, CDS_ESHAPE, "cds_dynamic_conv_tc: bad batch");
     CDS_REQUIRE(temperature > 0.f, CDS_EARG, "cds_dynamic_conv_tc: temperature must be positive");
-    CDS_REQUIRE(cds_dynamic_conv_tc_supported(8, 8, H, W, num_kernels, kernel_sizes), CDS_EUNSUPPORTED,
-                "cds_dynamic_conv_tc: unsupported layer (needs 8->8 channels, W >= 128, kernel sets (3,7,11) (3,5,7) (1,3))");
+    CDS_REQUIRE(cds_dynamic_conv_tc_supported(Cin, Cout, H, W, num_kernels, kernel_sizes), CDS_EUNSUPPORTED,
+                "cds_dynamic_conv_tc: unsupported layer (Cin=%d Cout=%d W=%d): needs W >= 128 and a feature-extractor layer shape",
+                Cin, Cout, W);
     DynTcParams p{};
     p.img_index = img_index; p.in_stats = in_stats; p.epipole = epipole; p.wgt = (const __half*)wgt_packed; p.bias = bias;
     p.gate = gate; p.out_raw = (__half*)out_raw; p.out_stats = out_stats; p.norm_curv = norm_curv; p.nc_sq = nc_sq;
     p.nc_abs = nc_abs; p.in_act = in_act; p.nc_mode = nc_mode; p.H = H; p.W = W; p.epi_scale = epi_scale;
     p.inv_temperature = 1.f / temperature;
-    if (num_kernels == 3 && kernel_sizes[2] == 11) return launch_dyn_tc<Cfg<3, 7, 11>, 8>(x, n_images, p, n, stream);
-    if (num_kernels == 3) return launch_dyn_tc<Cfg<3, 5, 7>, 8>(x, n_images, p, n, stream);
-    return launch_dyn_tc<Cfg<1, 3, 0>, 8>(x, n_images, p, n, stream);
+    switch (layer_id(Cin, Cout, num_kernels, kernel_sizes)) {
+        case 1: return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8>(x, n_images, p, n, stream);
+        case 2: return launch_dyn_tc<Cfg<3, 5, 7, 8, 8>, 8>(x, n_images, p, n, stream);
+        case 3: return launch_dyn_tc<Cfg<1, 3, 0, 8, 8>, 8>(x, n_images, p, n, stream);
+        case 4: return launch_dyn_tc<Cfg<3, 5, 0, 16, 16>, 8>(x, n_images, p, n, stream);
+        case 5: return launch_dyn_tc<Cfg<1, 3, 0, 16, 16>, 8>(x, n_images, p, n, stream);
+        default: return launch_dyn_tc<Cfg<1, 3, 0, 32, 32>, 8>(x, n_images, p, n, stream);
+    }
 }
 
 }  // extern "C"

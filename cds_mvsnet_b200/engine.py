@@ -77,7 +77,7 @@ class FeatureExtractor:
         _lib.set_tag("feat." + name, (flops, float(nbytes)))
         ks = _ksizes(w.ksizes)
         if (self.use_tc and w.tc is not None and self.storage == torch.float16
-                and _lib.LIB.load().cds_dynamic_conv_tc_supported(8, w.cout, H, W, len(w.ksizes), ks)):
+                and _lib.LIB.load().cds_dynamic_conv_tc_supported(max(8, w.cin), w.cout, H, W, len(w.ksizes), ks)):
             n_images = n
             if in_mode == 1:   # planar fp32 images -> fp16 [*,H,W,8] once per forward
                 n_images = x.shape[0]
@@ -85,7 +85,8 @@ class FeatureExtractor:
                 call("cds_image_to_nhwc8", ptr(x), n_images, H, W, ptr(img8))
                 x = img8
             call("cds_dynamic_conv_tc", ptr(x), n_images, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
-                 ptr(w.tc), ptr(w.bias), ptr(w.gate), n, H, W, len(w.ksizes), ks, float(T), ptr(out), ptr(out_stats),
+                 ptr(w.tc), ptr(w.bias), ptr(w.gate), n, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T), ptr(out),
+                 ptr(out_stats),
                  ptr(norm_curv), ptr(nc_sq), nc_mode, ptr(nc_abs))
             return
         call("cds_dynamic_conv", ptr(x), in_mode, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),

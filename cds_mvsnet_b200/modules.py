@@ -173,9 +173,10 @@ class DynamicConv(_CachedModule):
         nc = torch.empty(B, 1, H, Wd, dtype=torch.float32, device=dev)
         ks = (ctypes.c_int * len(w.ksizes))(*w.ksizes)
         epi = _f32c(epipole)
-        if (self.use_tc and self.storage == torch.float16 and self.in_c in (3, 8) and self.out_c == 8
-                and _lib.LIB.load().cds_dynamic_conv_tc_supported(8, 8, H, Wd, len(w.ksizes), ks)):
-            # tensor-core path (tcgen05): 8-channel fp16 pixels, image zero-padded from 3 channels
+        cin_tc = max(8, self.in_c)
+        if (self.use_tc and self.storage == torch.float16
+                and _lib.LIB.load().cds_dynamic_conv_tc_supported(cin_tc, self.out_c, H, Wd, len(w.ksizes), ks)):
+            # tensor-core path (tcgen05): fp16 channels-last pixels, image zero-padded from 3 to 8 channels
             if w.tc is None:
                 w.tc = W.pack_dynamic_conv_tc(w)
             if C == 3:
@@ -185,7 +186,7 @@ class DynamicConv(_CachedModule):
             else:
                 x8 = _nhwc(feature_vol, torch.float16)
             call("cds_dynamic_conv_tc", ptr(x8), B, None, None, ACT_NONE, ptr(epi), 1.0, ptr(w.tc), ptr(w.bias), ptr(w.gate),
-                 B, H, Wd, len(w.ksizes), ks, float(temperature), ptr(raw), None, ptr(nc), None, 0, None)
+                 B, cin_tc, self.out_c, H, Wd, len(w.ksizes), ks, float(temperature), ptr(raw), None, ptr(nc), None, 0, None)
             return _nchw(raw), nc
         if C == 3:
             x, mode = _f32c(feature_vol), 1

@@ -70,18 +70,21 @@ def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
 
 
 def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
-    """fp16 B-operand image for csrc/dynconv_tc.cu (8 -> 8 channel layers; Cin 3 is zero-padded to 8).
+    """fp16 B-operand image for csrc/dynconv_tc.cu (Cin 3 is zero-padded to 8).
 
-    Every branch is embedded in the kmax x kmax tap grid.  Inner taps (support of the second-largest kernel), in
-    (ky, kx) order as 8-channel slabs [tap0, zero pad, tap1, tap2, ...], two slabs per MMA, feed all branches:
-    per MMA [k-chunk 2][n-group 2K][8 n][8 k], branch b owning columns [16b, 16b+16) = 8 feature channels, (a, b, c)
-    rounded to fp16, the rounding residuals of (a, b, c).  The outer-ring taps follow, for the largest kernel only:
-    per MMA [k-chunk 2][n-group 2][8 n][8 k]."""
-    assert w.cout == 8 and w.cin in (3, 8)
+    Every branch is embedded in the kmax x kmax tap grid.  Branch b owns N columns [b*NPAD, (b+1)*NPAD) with
+    NPAD = roundup16(Cout + 6): Cout feature channels, (a, b, c) rounded to fp16, the rounding residuals of (a, b, c).
+    K = 16 per MMA = two 8-channel slabs: for Cin <= 8 two consecutive taps ([tap0, zero pad], [tap1, tap2], ...), for
+    Cin > 8 two channel chunks of one tap.  First the MMAs of the inner taps (support of the second-largest kernel;
+    all branches, N = K*NPAD), then those of the outer ring (largest kernel only, N = NPAD); per MMA
+    [k-chunk 2][N/8][8 n][8 k]."""
+    cin, cout = w.cin, w.cout
+    c8 = max(1, cin // 8)
     att, conv = w.w_att.detach().double().cpu(), w.w_conv.detach().double().cpu()
     K, kmax = len(w.ksizes), max(w.ksizes)
+    npad = (cout + 6 + 15) // 16 * 16
     ntap = kmax * kmax
-    full = torch.zeros(ntap, 8, 16 * K, dtype=torch.float64)           # [tap, k (cin), n]
+    full = torch.zeros(ntap, c8 * 8, npad * K, dtype=torch.float64)           # [tap, k (cin), n]
     t0 = 0
     for b, k in enumerate(w.ksizes):
         o = (kmax - k) // 2
@@ -89,28 +92,35 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
             for kx in range(k):
                 t = (ky + o) * kmax + (kx + o)
                 src = t0 + ky * k + kx
-                full[t, :w.cin, 16 * b:16 * b + 8] = conv[src]
+                full[t, :cin, npad * b:npad * b + cout] = conv[src]
                 a = att[src][:, :3]
                 hi = a.to(torch.float16).to(torch.float64)
-                full[t, :w.cin, 16 * b + 8:16 * b + 11] = hi
-                full[t, :w.cin, 16 * b + 11:16 * b + 14] = a - hi
+                full[t, :cin, npad * b + cout:npad * b + cout + 3] = hi
+                full[t, :cin, npad * b + cout + 3:npad * b + cout + 6] = a - hi
         t0 += k * k
-    # inner taps (support of the second-largest kernel): all branches; outer ring: the largest kernel only
     kin = max(k for k in w.ksizes if k < kmax)
-    lo, hi = (kmax - kin) // 2, (kmax - kin) // 2 + kin
-    inner = [t for t in range(ntap) if lo <= t // kmax < hi and lo <= t % kmax < hi]
-    ring = [t for t in range(ntap) if not (lo <= t // kmax < hi and lo <= t % kmax < hi)]
-    slabs = [inner[0], None] + inner[1:]
-    img_in = torch.zeros(len(slabs) // 2, 2, 2 * K, 8, 8, dtype=torch.float64)
-    for s, t in enumerate(slabs):
-        if t is not None:
-            img_in[s // 2, s % 2] = full[t].t().reshape(2 * K, 8, 8)
-    assert len(ring) % 2 == 0
-    img_ring = torch.zeros(len(ring) // 2, 2, 2, 8, 8, dtype=torch.float64)
-    for s, t in enumerate(ring):
-        assert full[t, :, :16 * (K - 1)].abs().max() == 0     # only the largest kernel reaches the ring
-        img_ring[s // 2, s % 2] = full[t, :, 16 * (K - 1):].t().reshape(2, 8, 8)
-    out = torch.cat((img_in.reshape(-1), img_ring.reshape(-1)))
+    lo, hi_ = (kmax - kin) // 2, (kmax - kin) // 2 + kin
+    inside = lambda t: lo <= t // kmax < hi_ and lo <= t % kmax < hi_
+    inner = [t for t in range(ntap) if inside(t)]
+    ring = [t for t in range(ntap) if not inside(t)]
+
+    def slabs_of(taps, pad_first):
+        if c8 == 1:
+            return ([(taps[0], 0), None] + [(t, 0) for t in taps[1:]]) if pad_first else [(t, 0) for t in taps]
+        return [(t, c) for t in taps for c in range(c8)]
+
+    def image(slabs, col0, ncol):
+        assert len(slabs) % 2 == 0
+        img = torch.zeros(len(slabs) // 2, 2, ncol // 8, 8, 8, dtype=torch.float64)
+        for s, sl in enumerate(slabs):
+            if sl is not None:
+                t, c = sl
+                img[s // 2, s % 2] = full[t, c * 8:(c + 1) * 8, col0:col0 + ncol].t().reshape(ncol // 8, 8, 8)
+        return img.reshape(-1)
+
+    for t in ring:
+        assert full[t, :, :npad * (K - 1)].abs().max() == 0     # only the largest kernel reaches the ring
+    out = torch.cat((image(slabs_of(inner, True), 0, npad * K), image(slabs_of(ring, False), npad * (K - 1), npad)))
     return out.to(dtype=torch.float16, device=w.w_conv.device).contiguous()
 
 
@@ -209,7 +219,7 @@ class FeatureWeights:
 
 def pack_feature(sd, device) -> FeatureWeights:
     dyn = {n: pack_dynamic_conv(sd, pre, ci, co, ks, device) for n, (ci, co, ks, pre) in DYN_LAYERS.items()}
-    for n in ("conv00", "conv01", "out3"):
+    for n in dyn:
         dyn[n].tc = pack_dynamic_conv_tc(dyn[n])
     return FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
                           pack_conv2d(sd, "feature.downsample2.conv.weight", device),

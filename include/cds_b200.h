@@ -141,18 +141,19 @@ int cds_dynamic_conv(const void* x, int in_mode, const int* img_index, const dou
                      const float* gate, int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes,
                      float temperature, int dtype, void* out_raw, double* out_stats, float* norm_curv, float* nc_sq,
                      int nc_mode, float* nc_abs, cudaStream_t stream);
-/* Tensor-core (tcgen05 + TMEM + TMA) DynamicConv for the 8 -> 8 channel full-resolution layers (conv00 with the
- * image padded to 8 channels by cds_image_to_nhwc8, conv01, out3), fp16 storage.  Same semantics and outputs as
- * cds_dynamic_conv.  x: [n_images,H,W,8] fp16; item i reads image img_index[i] (NULL: i); wgt_packed: fp16 operand
- * image from the host (cds_dynamic_conv_tc_weight_halfs() halfs: per branch, per MMA [2][2][8 n][8 k] with
- * n = 8 feature + 3 curvature channels, see csrc/dynconv_tc.cu).  kernel_sizes is a HOST array. */
+/* Tensor-core (tcgen05 + TMEM + TMA) DynamicConv for the feature extractor's layer shapes (8->8 with kernels
+ * (3,7,11) [conv00, image padded to 8 channels by cds_image_to_nhwc8], (3,5,7), (1,3); 16->16 with (3,5), (1,3);
+ * 32->32 with (1,3)), fp16 storage, W >= 128.  Same semantics and outputs as cds_dynamic_conv.
+ * x: [n_images,H,W,Cin] fp16; item i reads image img_index[i] (NULL: i); wgt_packed: fp16 operand image from the host
+ * (cds_dynamic_conv_tc_weight_halfs() halfs, layout in csrc/dynconv_tc.cu).  kernel_sizes is a HOST array. */
 int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStream_t stream);
 int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes);
-int cds_dynamic_conv_tc_weight_halfs(int num_kernels, const int* kernel_sizes);
+int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
                         const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
-                        int n, int H, int W, int num_kernels, const int* kernel_sizes, float temperature, void* out_raw,
-                        double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream);
+                        int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
+                        void* out_raw, double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs,
+                        cudaStream_t stream);
 /* FeatureNet.downsample1/2 (models/module.py:214,218): 3x3 stride 2 pad 1, wgt [9][Cin][Cout]. */
 int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
                      int W, int dtype, void* out, double* out_stats, cudaStream_t stream);

@@ -336,10 +336,10 @@ def test_conv3d_tcgen05_unsupported_shapes():
 
 
 # ---------------------------------------------------------------------------------------- A6 on tensor cores
-@pytest.mark.parametrize("name", ["conv00", "conv01", "out3"])
+@pytest.mark.parametrize("name", ["conv00", "conv01", "out3", "conv10", "out2", "conv20", "out1"])
 @pytest.mark.parametrize("hw", [(37, 200), (64, 128), (16, 333)])
 def test_dynamic_conv_tcgen05_vs_oracle(pretrained_sd, name, hw):
-    """tcgen05 DynamicConv (8 -> 8 channel layers) against the oracle and against the CUDA-core kernel."""
+    """tcgen05 DynamicConv (every layer shape of the feature extractor) against the oracle and the CUDA-core kernel."""
     cin, cout, ks, pre = W.DYN_LAYERS[name]
     torch.manual_seed(hash(name) % 1000 + hw[1])
     x = (torch.rand(2, cin, *hw) if cin == 3 else torch.randn(2, cin, *hw)).half().float()
