@@ -49,6 +49,7 @@ struct ConvTcParams {
     const __half* wgt;   // packed fp16 image, NMMA * 2 * NPAD * 8 halfs
     const float* bias;   // [COUT]
     __half* out;         // [COUT/8, D, H, W, 8]  (one batch item)
+    float* logits;       // prob-head mode (COUT == 1): fp32 [D, H, W], no bias / ReLU
     int D, H, W, relu;
 };
 
@@ -144,24 +145,32 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
     for (int u = 0; u < TY; ++u) {
         const int y = y0 + u;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)u * NPAD;
-#pragma unroll
-        for (int c8 = 0; c8 < COUT / 8; ++c8) {
+        if constexpr (COUT == 1) {
+            // prob head (models/module.py:303): column 0 = product with the fp16-rounded weights, column 1 = with
+            // their rounding residual; plain sum, fp32 logits in [D,H,W] order
             float v[8];
-            tc::tmem_ld8(taddr + c8 * 8, v);   // warp-collective: every lane executes it
-            if (COUT == 8) {
-                // N was padded 8 -> 16: columns 8..15 hold the product with the weights' fp16 rounding residual
-                float lo[8];
-                tc::tmem_ld8(taddr + 8, lo);
+            tc::tmem_ld8(taddr, v);
+            if (y < p.H && r < TXO) p.logits[((size_t)d * p.H + y) * p.W + x0 + r] = v[0] + v[1];
+        } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += lo[i];
-            }
-            if (y < p.H && r < TXO) {
+            for (int c8 = 0; c8 < COUT / 8; ++c8) {
+                float v[8];
+                tc::tmem_ld8(taddr + c8 * 8, v);   // warp-collective: every lane executes it
+                if (COUT == 8) {
+                    // N was padded 8 -> 16: columns 8..15 hold the product with the weights' fp16 rounding residual
+                    float lo[8];
+                    tc::tmem_ld8(taddr + 8, lo);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float t = v[i] + __ldg(p.bias + c8 * 8 + i);
-                    v[i] = p.relu ? fmaxf(t, 0.f) : t;
+                    for (int i = 0; i < 8; ++i) v[i] += lo[i];
                 }
-                Vec8<__half>::store(p.out + ((size_t)c8 * M + ((size_t)d * p.H + y) * p.W + x0 + r) * 8, v);
+                if (y < p.H && r < TXO) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float t = v[i] + __ldg(p.bias + c8 * 8 + i);
+                        v[i] = p.relu ? fmaxf(t, 0.f) : t;
+                    }
+                    Vec8<__half>::store(p.out + ((size_t)c8 * M + ((size_t)d * p.H + y) * p.W + x0 + r) * 8, v);
+                }
             }
         }
     }
@@ -187,7 +196,8 @@ int launch_tc(const void* in, const void* wgt, const float* bias, int B, int D, 
         const uint32_t box[4] = {2 * TX, TY + 2, 3, 1};
         if (!tma::make_u64(&tmap, base, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
         ConvTcParams p;
-        p.out = (__half*)out + (size_t)b * D * H * W * COUT;
+        p.out = COUT == 1 ? nullptr : (__half*)out + (size_t)b * D * H * W * COUT;
+        p.logits = COUT == 1 ? (float*)out + (size_t)b * D * H * W : nullptr;
         p.wgt = (const __half*)wgt;
         p.bias = bias;
         p.D = D; p.H = H; p.W = W; p.relu = relu;
@@ -203,7 +213,7 @@ extern "C" {
 // 1 when the tensor-core kernel covers this layer shape (otherwise use cds_conv3d_k3)
 int cds_conv3d_k3_tc_supported(int Cin, int Cout, int D, int H, int W, int stride) {
     if (stride != 1 || W < TX || D < 1 || H < 1 || D > 65535) return 0;
-    return (Cin == 8 && Cout == 8) || (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 8) || (Cin == 16 && Cout == 16) ||
+    return (Cin == 8 && Cout == 1) || (Cin == 8 && Cout == 8) || (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 8) || (Cin == 16 && Cout == 16) ||
            (Cin == 32 && Cout == 32);
 }
 
@@ -216,7 +226,11 @@ int cds_conv3d_k3_tc_weight_halfs(int Cin, int Cout) {
 
 int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H,
                      int W, int relu, void* out, cudaStream_t stream) {
-    CDS_REQUIRE(in && wgt_packed && bias && out, CDS_EARG, "cds_conv3d_k3_tc: null pointer");
+    CDS_REQUIRE(in && wgt_packed && out && (bias || Cout == 1), CDS_EARG, "cds_conv3d_k3_tc: null pointer");
+    if (Cin == 8 && Cout == 1) {   // prob head: fp32 logits [B,D,H,W]
+        CDS_REQUIRE(cds_conv3d_k3_tc_supported(8, 1, D, H, W, 1), CDS_EUNSUPPORTED, "cds_conv3d_k3_tc: prob head needs W >= 128");
+        return launch_tc<8, 1, 16, 4>(in, wgt_packed, bias, B, D, H, W, 0, out, stream);
+    }
     CDS_REQUIRE(cds_conv3d_k3_tc_supported(Cin, Cout, D, H, W, 1), CDS_EUNSUPPORTED,
                 "cds_conv3d_k3_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs W >= 128)", Cin, Cout, D, H, W);
     if (Cin == 8 && Cout == 8) return launch_tc<8, 8, 16, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);

@@ -224,8 +224,13 @@ class Regulariser:
         self._deconv("conv9", u7, c2, B, D4, H4, W4, u9)
         self._deconv("conv11", u9, c0, B, D2, H2, W2, u11)
         m = B * D * H * W
-        kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_prob_conv", ptr(u11), ptr(self.cw.prob), B, b, D, H,
-              W, self.dt, ptr(logits))
+        if (self.use_tc and st == torch.float16 and self.cw.prob_tc is not None
+                and _lib.LIB.load().cds_conv3d_k3_tc_supported(b, 1, D, H, W, 1)):
+            kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_conv3d_k3_tc", ptr(u11), ptr(self.cw.prob_tc), None,
+                  B, b, 1, D, H, W, 0, ptr(logits))
+        else:
+            kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_prob_conv", ptr(u11), ptr(self.cw.prob), B, b, D,
+                  H, W, self.dt, ptr(logits))
         return logits
 
 

@@ -184,10 +184,10 @@ def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
         blk = w[t, c * 8:(c + 1) * 8, :]                            # [8 k, Cout]
         full = torch.zeros(8, npad, dtype=torch.float64)
         full[:, :co] = blk
-        if co == 8:   # N is padded to 16 anyway: the spare columns carry the fp16 rounding residual of the weights
+        if co in (1, 8):   # N is padded to 16 anyway: the spare columns carry the fp16 rounding residual of the weights
             hi = blk.to(torch.float16).to(torch.float64)
-            full[:, :8] = hi
-            full[:, 8:16] = blk - hi
+            full[:, :co] = hi
+            full[:, co:2 * co] = blk - hi
         img[s // 2, s % 2] = full.t().reshape(npad // 8, 8, 8)      # [n-group, n row, k]
     return img.to(dtype=torch.float16, device=l.w.device).contiguous()
 
@@ -196,6 +196,7 @@ def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
 class CostRegWeights:
     layers: dict          # name -> Conv3dWeights
     prob: torch.Tensor    # [27, 8]
+    prob_tc: torch.Tensor | None = None
 
 
 def pack_costreg(sd, prefix, device) -> CostRegWeights:
@@ -205,7 +206,10 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
         layers[n].extra["tc"] = pack_conv3d_tc(layers[n])
     p = sd[prefix + ".prob.weight"].double()                        # [1,8,3,3,3]
     prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(dtype=torch.float32, device=device).contiguous()
-    return CostRegWeights(layers, prob)
+    cw = CostRegWeights(layers, prob)
+    if p.shape[1] == 8:   # tensor-core image of the prob head (8 -> 1)
+        cw.prob_tc = pack_conv3d_tc(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), torch.zeros(1, device=device)))
+    return cw
 
 
 @dataclass

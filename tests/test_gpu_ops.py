@@ -357,3 +357,18 @@ def test_dynamic_conv_tcgen05_vs_oracle(pretrained_sd, name, hw):
         assert O.rel_l1(y.cpu(), ref_y) < 4e-3, (use_tc, O.rel_l1(y.cpu(), ref_y))
         assert O.rel_l1(nc.cpu(), ref_nc) < 4e-3, (use_tc, O.rel_l1(nc.cpu(), ref_nc))
     assert O.rel_l1(outs[True][0], outs[False][0]) < 4e-3
+
+
+def test_prob_head_tcgen05_vs_torch():
+    """8 -> 1 prob conv on the tensor cores (hi + residual fp16 weights) against the published operator."""
+    torch.manual_seed(11)
+    D, H, Wd = 8, 10, 200
+    x = torch.randn(2, 8, D, H, Wd).half().float()
+    w = torch.randn(1, 8, 3, 3, 3) / 14.7
+    ref = torch.nn.functional.conv3d(x, w, padding=1)[:, 0]
+    lw = W.Conv3dWeights(8, 1, w.permute(2, 3, 4, 1, 0).reshape(27, 8, 1).contiguous(), torch.zeros(1))
+    packed = cu(W.pack_conv3d_tc(lw))
+    xc = cu(to_blocked(x)).half()
+    out = torch.empty(2, D, H, Wd, device=DEV)
+    call("cds_conv3d_k3_tc", ptr(xc), ptr(packed), None, 2, 8, 1, D, H, Wd, 0, ptr(out))
+    close(out, ref, 2e-4, 1e-4)
