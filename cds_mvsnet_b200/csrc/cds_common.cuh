@@ -104,6 +104,15 @@ __device__ __forceinline__ void project(const WarpCoef& k, float rx, float ry, f
     u = px / pz;
     v = py / pz;
 }
+// same projection with one correctly-rounded reciprocal instead of two divisions (fused cost-volume kernels:
+// the difference is <= 1 ulp of the coordinate, ~1e-4 px at w = 1600)
+__device__ __forceinline__ void project_fast(const WarpCoef& k, float rx, float ry, float rz, float depth, float& u, float& v) {
+    float px = rx * depth + k.t[0];
+    float py = ry * depth + k.t[1];
+    float inv = __frcp_rn(rz * depth + k.t[2] + 1e-6f);
+    u = px * inv;
+    v = py * inv;
+}
 
 // Bilinear footprint at pixel coords (u,v) with zero padding (grid_sample bilinear/zeros/
 // align_corners=True after the reference's normalisation, warping.py:95-101).

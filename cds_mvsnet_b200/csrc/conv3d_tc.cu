@@ -229,11 +229,11 @@ int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, 
     CDS_REQUIRE(in && wgt_packed && out && (bias || Cout == 1), CDS_EARG, "cds_conv3d_k3_tc: null pointer");
     if (Cin == 8 && Cout == 1) {   // prob head: fp32 logits [B,D,H,W]
         CDS_REQUIRE(cds_conv3d_k3_tc_supported(8, 1, D, H, W, 1), CDS_EUNSUPPORTED, "cds_conv3d_k3_tc: prob head needs W >= 128");
-        return launch_tc<8, 1, 16, 4>(in, wgt_packed, bias, B, D, H, W, 0, out, stream);
+        return launch_tc<8, 1, 16, 8>(in, wgt_packed, bias, B, D, H, W, 0, out, stream);
     }
     CDS_REQUIRE(cds_conv3d_k3_tc_supported(Cin, Cout, D, H, W, 1), CDS_EUNSUPPORTED,
                 "cds_conv3d_k3_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs W >= 128)", Cin, Cout, D, H, W);
-    if (Cin == 8 && Cout == 8) return launch_tc<8, 8, 16, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
+    if (Cin == 8 && Cout == 8) return launch_tc<8, 8, 16, 8>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 16 && Cout == 8) return launch_tc<16, 8, 16, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 32 && Cout == 8) return launch_tc<32, 8, 16, 2>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 16 && Cout == 16) return launch_tc<16, 16, 16, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);

@@ -32,7 +32,7 @@ __device__ __forceinline__ void gather8(const T* __restrict__ fea, int w, int h,
 // pass 1: entropy[v, b, y, x] = H(softmax_d(sum_c ref[c] * warp_d[c]))
 // ---------------------------------------------------------------------------------------------
 template <typename T, int C>
-__global__ void __launch_bounds__(256) entropy_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
+__global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                       const float* __restrict__ coef, const float* __restrict__ depth,
                                                       int V, int B, int D, int h, int w, float* __restrict__ entropy) {
     constexpr int LPP = C / 8;  // lanes per pixel
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) entropy_kernel(const T* __restrict__ ref_
     for (int d = 0; d < D; ++d) {
         float dep = __ldg(dp + (size_t)d * P);
         float u, vv;
-        project(k, rx, ry, rz, dep, u, vv);
+        project_fast(k, rx, ry, rz, dep, u, vv);
         Taps t = make_taps(u, vv, w, h);
         float wv[8];
         gather8<T>(sf, w, h, C, t, wv);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) entropy_kernel(const T* __restrict__ ref_
 // pass 2: volume[b, d, y, x, :] = sum_v vis_v * ref_v (.) warp_{v,d} / (sum_v vis_v + 1e-6)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int C>
-__global__ void __launch_bounds__(256) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
+__global__ void __launch_bounds__(256, 4) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                         const float* __restrict__ coef, const float* __restrict__ depth,
                                                         const float* __restrict__ vis, int V, int B, int D, int h, int w,
                                                         T* __restrict__ volume) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const T* __restrict__ re
                 WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
                 float rx, ry, rz, u, vv;
                 pixel_ray(k, (float)x, (float)y, rx, ry, rz);
-                project(k, rx, ry, rz, dep, u, vv);
+                project_fast(k, rx, ry, rz, dep, u, vv);
                 Taps t = make_taps(u, vv, w, h);
                 float wv[8], ref[8];
                 gather8<T>(src_fea + ((size_t)v * B + b) * P * C + chunk * 8, w, h, C, t, wv);
