@@ -179,6 +179,156 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
     if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ConvTranspose3d k3 s2 p1 op1 + BN + ReLU, then + skip (models/module.py:125-166, 310-312) on the tensor cores.
+// out[2i - 1 + k] += in[i] * w[k] per axis: output parity 0 takes tap k=1 from input i, parity 1 takes k=2 from i and
+// k=0 from i+1.  So with M = 128 consecutive INPUT voxels as the GEMM rows, the A operands are the 8 neighbour
+// offsets (sd,sh,sw) in {0,1}^3 of the same haloed window, and the 8 output parity classes sit side by side in N
+// (N = 8*Cout, zero weight blocks where a parity does not use an offset): 8 * Cin/16 MMAs per row unit.
+// The epilogue scatters each row's 8 parity results to the 2x2x2 output cell (bias, ReLU, + skip).
+// Weights: [mma (offset s, chunk pair q)][k-chunk 2][N/8][8 n][8 k], n = parity*Cout + co.
+// ---------------------------------------------------------------------------------------------------------------
+struct DeconvTcParams {
+    const __half* wgt;
+    const float* bias;    // [COUT]
+    const __half* skip;   // [COUT/8, 2D, 2H, 2W, 8] or null (one batch item)
+    __half* out;          // [COUT/8, 2D, 2H, 2W, 8]
+    int D, H, W;          // INPUT extent
+};
+
+template <int CIN, int COUT, int TY>
+__global__ void __launch_bounds__(128) deconv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcParams p) {
+    constexpr int C8 = CIN / 8, NMMA = 8 * C8 / 2, N = 8 * COUT;
+    constexpr int TXI = TX - 1;                                       // input voxels per row unit that own outputs
+    constexpr uint32_t CHUNK = 2 * (TY + 1) * ROW_BYTES;              // one 8-channel slab: [2 d][TY+1 h][128 w]
+    constexpr uint32_t A_BYTES = C8 * CHUNK;
+    constexpr uint32_t B_BYTES = NMMA * 2 * N * 16;
+    constexpr uint32_t TMEM_COLS = TY * N <= 64 ? 64 : (TY * N <= 128 ? 128 : (TY * N <= 256 ? 256 : 512));
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + A_BYTES;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES);
+    uint64_t* bar_mma = bar_load + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = min((int)blockIdx.x * TXI, p.W - TXI);
+    const int y0 = blockIdx.y * TY;
+    const int d = blockIdx.z;
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x == 32) {
+        tc::mbar_init(bar_load, 1);
+        tc::mbar_init(bar_mma, TY < 4 ? TY : 4);
+        tc::mbar_fence_init();
+        tc::tma_prefetch_desc(&tmap);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(bar_load, A_BYTES + B_BYTES);
+#pragma unroll
+        for (int c8 = 0; c8 < C8; ++c8) tc::tma_load_4d(sA_u + c8 * CHUNK, &tmap, bar_load, 2 * x0, y0, d, c8);
+        tc::bulk_copy_g2s(sB_u, p.wgt, B_BYTES, bar_load);
+    }
+    const uint32_t warp_u = tc::uniform((uint32_t)warp);
+    const uint32_t tmem_u = tc::uniform(tmem);
+    if (warp_u < (uint32_t)TY) {
+        tc::mbar_wait(bar_load, 0);
+        tc::tc_fence_after();
+        const bool elected = tc::elect_one();
+        constexpr uint32_t idesc = tc::instr_desc_f16(128, N);
+        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        constexpr uint32_t b_lo_const = ((uint32_t)(N * 16) >> 4) << 16;
+#pragma unroll 1
+        for (uint32_t u = warp_u; u < (uint32_t)TY; u += 4) {
+            const uint32_t a_base = (sA_u + u * ROW_BYTES) >> 4;
+            const uint32_t b_base = sB_u >> 4;
+            const uint32_t acc_col = tmem_u + u * N;
+#pragma unroll
+            for (int j = 0; j < NMMA; ++j) {
+                const int s = j / (C8 / 2), q = j % (C8 / 2);   // neighbour offset (sd,sh,sw), channel-chunk pair
+                const int sd = s >> 2, sh = (s >> 1) & 1, sw = s & 1;
+                const uint32_t off0 = (uint32_t)(2 * q) * CHUNK + (uint32_t)((sd * (TY + 1) + sh) * ROW_BYTES + sw * 16);
+                const uint32_t a_lo = a_base + ((off0 >> 4) | ((CHUNK >> 4) << 16));
+                const uint32_t b_lo = b_base + (((uint32_t)j * (2 * N * 16)) >> 4 | b_lo_const);
+                if (elected) tc::mma_f16(acc_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, j > 0);
+            }
+        }
+        if (elected) tc::mma_commit(bar_mma);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar_mma, 0);
+    tc::tc_fence_after();
+
+    // ---- epilogue: row r = input voxel x0 + r owns the 2x2x2 output cell at (2d, 2y, 2x) -------------------------
+    const int r = warp * 32 + lane;
+    const int xi = x0 + r;
+    const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+    const size_t Mo = (size_t)Do * Ho * Wo;
+    const bool own = r < TXI && xi >= (int)blockIdx.x * TXI;   // tiles overlap at the right edge: one owner per voxel
+#pragma unroll 1
+    for (int u = 0; u < TY; ++u) {
+        const int yi = y0 + u;
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)u * N;
+#pragma unroll
+        for (int par = 0; par < 8; ++par) {
+            const int pd = par >> 2, ph = (par >> 1) & 1, pw = par & 1;
+#pragma unroll
+            for (int c8 = 0; c8 < COUT / 8; ++c8) {
+                float v[8];
+                tc::tmem_ld8(taddr + par * COUT + c8 * 8, v);
+                if (own && yi < p.H) {
+                    const size_t o = ((size_t)c8 * Mo + ((size_t)(2 * d + pd) * Ho + 2 * yi + ph) * Wo + 2 * xi + pw) * 8;
+                    float sk[8];
+                    if (p.skip) Vec8<__half>::load(p.skip + o, sk);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float t = fmaxf(v[i] + __ldg(p.bias + c8 * 8 + i), 0.f);
+                        v[i] = p.skip ? sk[i] + t : t;
+                    }
+                    Vec8<__half>::store(p.out + o, v);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int CIN, int COUT, int TY>
+int launch_deconv_tc(const void* in, const void* wgt, const float* bias, const void* skip, int B, int D, int H, int W, void* out,
+                     cudaStream_t st) {
+    constexpr int C8 = CIN / 8;
+    constexpr size_t smem = (size_t)C8 * 2 * (TY + 1) * ROW_BYTES + (size_t)(8 * C8 / 2) * 2 * (8 * COUT) * 16 + 32;
+    static_assert(smem <= 227 * 1024, "deconv tile does not fit in shared memory");
+    auto kern = deconv3d_tc_kernel<CIN, COUT, TY>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cds_set_error("cds_deconv3d_k3s2_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    dim3 grid(cds_div_up(W, TX - 1), cds_div_up(H, TY), D);
+    for (int b = 0; b < B; ++b) {
+        const __half* base = (const __half*)in + (size_t)b * D * H * W * CIN;
+        CUtensorMap tmap;
+        const uint64_t dims[4] = {2 * (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)C8};
+        const uint64_t strides[4] = {0, (uint64_t)W * 16, (uint64_t)H * W * 16, (uint64_t)D * H * W * 16};
+        const uint32_t box[4] = {2 * TX, TY + 1, 2, 1};
+        if (!tma::make_u64(&tmap, base, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
+        DeconvTcParams p;
+        p.wgt = (const __half*)wgt;
+        p.bias = bias;
+        p.skip = skip ? (const __half*)skip + (size_t)b * 8 * D * H * W * COUT : nullptr;
+        p.out = (__half*)out + (size_t)b * 8 * D * H * W * COUT;
+        p.D = D; p.H = H; p.W = W;
+        kern<<<grid, 128, smem, st>>>(tmap, p);
+    }
+    return cds_check_launch("cds_deconv3d_k3s2_tc");
+}
+
 template <int CIN, int COUT, int NPAD, int TY>
 int launch_tc(const void* in, const void* wgt, const float* bias, int B, int D, int H, int W, int relu, void* out,
               cudaStream_t st) {
@@ -238,6 +388,23 @@ int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, 
     if (Cin == 32 && Cout == 8) return launch_tc<32, 8, 16, 2>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 16 && Cout == 16) return launch_tc<16, 16, 16, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     return launch_tc<32, 32, 32, 2>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
+}
+
+// ---- transposed convolution on the tensor cores (input extent D,H,W; output 2D,2H,2W) ---------------------------------
+int cds_deconv3d_k3s2_tc_supported(int Cin, int Cout, int D, int H, int W) {
+    if (W < TX || D < 1 || H < 1 || D > 65535) return 0;
+    return (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 16);   // 64 -> 32: the weight image (256 KB) exceeds smem
+}
+
+int cds_deconv3d_k3s2_tc_weight_halfs(int Cin, int Cout) { return (8 * (Cin / 8) / 2) * 2 * (8 * Cout) * 8; }
+
+int cds_deconv3d_k3s2_tc(const void* in, const void* wgt_packed, const float* bias, const void* skip, int B, int Cin, int Cout,
+                         int D, int H, int W, void* out, cudaStream_t stream) {
+    CDS_REQUIRE(in && wgt_packed && bias && out, CDS_EARG, "cds_deconv3d_k3s2_tc: null pointer");
+    CDS_REQUIRE(cds_deconv3d_k3s2_tc_supported(Cin, Cout, D, H, W), CDS_EUNSUPPORTED,
+                "cds_deconv3d_k3s2_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs input W >= 128)", Cin, Cout, D, H, W);
+    if (Cin == 16) return launch_deconv_tc<16, 8, 4>(in, wgt_packed, bias, skip, B, D, H, W, out, stream);
+    return launch_deconv_tc<32, 16, 2>(in, wgt_packed, bias, skip, B, D, H, W, out, stream);
 }
 
 }  // extern "C"

@@ -190,6 +190,10 @@ class Regulariser:
         e = _esize(self.storage)
         m_in = B * D * H * W
         _lib.set_tag(f"{self.tag}.{name}", (2.0 * 27 * l.cin * l.cout * m_in, float((l.cin * m_in + 2 * l.cout * 8 * m_in) * e)))
+        if (self.use_tc and self.storage == torch.float16 and "tc" in l.extra
+                and _lib.LIB.load().cds_deconv3d_k3s2_tc_supported(l.cin, l.cout, D, H, W)):
+            call("cds_deconv3d_k3s2_tc", ptr(x), ptr(l.extra["tc"]), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, ptr(out))
+            return
         call("cds_deconv3d_k3s2", ptr(x), ptr(l.w), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, self.dt, ptr(out))
 
     def run(self, buf: Buffers, tag, volume, B, D, H, W):

@@ -192,6 +192,39 @@ def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
     return img.to(dtype=torch.float16, device=l.w.device).contiguous()
 
 
+def pack_deconv3d_tc(l: Conv3dWeights) -> torch.Tensor:
+    """fp16 B-operand image for the transposed-conv kernel in csrc/conv3d_tc.cu.
+
+    MMA j = (neighbour offset s = (sd,sh,sw) in {0,1}^3, channel-chunk pair q); N = 8*Cout, column n = parity*Cout + co
+    with parity = (pd,ph,pw).  Per axis: parity 0 uses tap k=1 from offset 0 only; parity 1 uses k=2 from offset 0 and
+    k=0 from offset 1 (out[2i-1+k] += in[i] w[k]).  Layout [mma][k-chunk 2][N/8][8 n][8 k]."""
+    ci, co = l.cin, l.cout
+    c8, N = ci // 8, 8 * l.cout
+    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout] folded
+
+    def tap(par, off):
+        if par == 0:
+            return 1 if off == 0 else None
+        return 2 if off == 0 else 0
+
+    img = torch.zeros(8 * c8 // 2, 2, N // 8, 8, 8, dtype=torch.float64)
+    for s in range(8):
+        sd, sh, sw = s >> 2, (s >> 1) & 1, s & 1
+        blockw = torch.zeros(ci, N, dtype=torch.float64)            # [k (cin), n]
+        for par in range(8):
+            pd, ph, pw = par >> 2, (par >> 1) & 1, par & 1
+            kd, kh, kw = tap(pd, sd), tap(ph, sh), tap(pw, sw)
+            if kd is None or kh is None or kw is None:
+                continue
+            blockw[:, par * co:(par + 1) * co] = w[(kd * 3 + kh) * 3 + kw]
+        for q in range(c8 // 2):
+            j = s * (c8 // 2) + q
+            for kc in range(2):
+                c = 2 * q + kc
+                img[j, kc] = blockw[c * 8:(c + 1) * 8].t().reshape(N // 8, 8, 8)
+    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+
+
 @dataclass
 class CostRegWeights:
     layers: dict          # name -> Conv3dWeights
@@ -204,6 +237,8 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
     layers.update({n: pack_conv3d(sd, f"{prefix}.{n}", True, device) for n in COSTREG_DECONVS})
     for n in ("conv0", "conv2", "conv4"):
         layers[n].extra["tc"] = pack_conv3d_tc(layers[n])
+    for n in ("conv9", "conv11"):
+        layers[n].extra["tc"] = pack_deconv3d_tc(layers[n])
     p = sd[prefix + ".prob.weight"].double()                        # [1,8,3,3,3]
     prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(dtype=torch.float32, device=device).contiguous()
     cw = CostRegWeights(layers, prob)

@@ -112,6 +112,12 @@ int cds_conv3d_k3_tc_supported(int Cin, int Cout, int D, int H, int W, int strid
 int cds_conv3d_k3_tc_weight_halfs(int Cin, int Cout);
 int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H,
                      int W, int relu, void* out, cudaStream_t stream);
+/* Tensor-core form of the Deconv3d block (same semantics as cds_deconv3d_k3s2, fp16 storage, input W >= 128).
+ * wgt_packed: fp16 operand image (cds_deconv3d_k3s2_tc_weight_halfs() halfs, layout in csrc/conv3d_tc.cu). */
+int cds_deconv3d_k3s2_tc_supported(int Cin, int Cout, int D, int H, int W);
+int cds_deconv3d_k3s2_tc_weight_halfs(int Cin, int Cout);
+int cds_deconv3d_k3s2_tc(const void* in, const void* wgt_packed, const float* bias, const void* skip, int B, int Cin, int Cout,
+                         int D, int H, int W, void* out, cudaStream_t stream);
 /* prob head: plain Conv3d(8,1,3,p=1,bias=False) (models/module.py:303) -> fp32 logits [B,D,H,W]. */
 int cds_prob_conv(const void* in, const float* wgt, int B, int Cin, int D, int H, int W, int dtype, float* logits,
                   cudaStream_t stream);

@@ -372,3 +372,26 @@ def test_prob_head_tcgen05_vs_torch():
     out = torch.empty(2, D, H, Wd, device=DEV)
     call("cds_conv3d_k3_tc", ptr(xc), ptr(packed), None, 2, 8, 1, D, H, Wd, 0, ptr(out))
     close(out, ref, 2e-4, 1e-4)
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 8), (32, 16)])
+@pytest.mark.parametrize("shape", [(3, 5, 133), (2, 4, 256), (1, 2, 128)])
+def test_deconv3d_tcgen05_vs_torch(cin, cout, shape):
+    """tcgen05 transposed conv (8 output parity classes side by side in N) against the published operator."""
+    D, H, Wd = shape
+    torch.manual_seed(cin + Wd)
+    x = torch.randn(2, cin, D, H, Wd).half().float()
+    w = (torch.randn(cin, cout, 3, 3, 3) / (8 * cin) ** 0.5).half().float()
+    b = torch.randn(cout)
+    skip = torch.randn(2, cout, 2 * D, 2 * H, 2 * Wd).half().float()
+    ref = skip + torch.relu(torch.nn.functional.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1))
+    lw = W.Conv3dWeights(cin, cout, w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout).contiguous(), b)
+    packed = cu(W.pack_deconv3d_tc(lw))
+    lib = _lib.LIB.load()
+    assert lib.cds_deconv3d_k3s2_tc_supported(cin, cout, D, H, Wd) == 1
+    assert packed.numel() == lib.cds_deconv3d_k3s2_tc_weight_halfs(cin, cout)
+    xc, sc, bc = cu(to_blocked(x)).half(), cu(to_blocked(skip)).half(), cu(b)
+    out = torch.empty_like(sc)
+    call("cds_deconv3d_k3s2_tc", ptr(xc), ptr(packed), ptr(bc), ptr(sc), 2, cin, cout, D, H, Wd, ptr(out))
+    torch.cuda.synchronize()
+    close(from_blocked(out.float().cpu()), ref, 8e-3, 2e-3)
