@@ -251,6 +251,7 @@ class CascadeEngine:
         self.buf = Buffers(self.device)
         self.features = FeatureExtractor(weights.feature, storage)
         self.regs = [Regulariser(cw, storage) for cw in weights.costreg]
+        self.use_tc = os.environ.get("CDS_USE_TC", "1") != "0"
         self.launches = 0
 
     # -- pieces -------------------------------------------------------------------------------
@@ -293,8 +294,13 @@ class CascadeEngine:
         kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P, "cds_costvol_entropy",
               ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, self.dt, ptr(entropy))
         vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
-        kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]), VB, h, w,
-              ptr(vis))
+        if (self.use_tc and self.w.vis_tc and self.storage == torch.float16 and _lib.LIB.load().cds_visnet_tc_supported(h, w)):
+            wgt, fp = self.w.vis_tc[s]
+            kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet_tc", ptr(entropy), ptr(ncabs[:VB]), ptr(wgt), ptr(fp),
+                  VB, h, w, ptr(vis))
+        else:
+            kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]),
+                  VB, h, w, ptr(vis))
         volume = buf.get(f"s{s}.volume", (B, C // 8, D, h, w, 8), self.storage)
         kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P + C * D * P * e,
               "cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,

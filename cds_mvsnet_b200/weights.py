@@ -140,6 +140,41 @@ def pack_visnet(sd, prefix, device) -> torch.Tensor:
     return torch.cat(parts).to(dtype=torch.float32, device=device).contiguous()
 
 
+def pack_visnet_tc(sd, prefix, device):
+    """Operands for csrc/visnet_tc.cu: (fp16 image [L1 5 MMAs | L2 9 | L3 9] x [k-chunk 2][2][8 n][8 k], fp32 b1 b2 b3 w4 b4).
+
+    Layer 1 sees (entropy_hi, curv_hi, entropy_lo, curv_lo, 0, 0, 0, 0) per pixel, so its weights are duplicated for the
+    "lo" channels; its 9 taps are paired [tap0, zero pad], [tap1, tap2], ...  Layers 2/3: one MMA per tap, the two
+    k-chunks are the two 8-channel halves of the 16 input channels."""
+    ws, bs = [], []
+    for j in range(3):
+        scale, shift = _bn_fold(sd, f"{prefix}.{j}.bn")
+        ws.append((sd[f"{prefix}.{j}.conv.weight"].double() * scale.reshape(-1, 1, 1, 1)).cpu())   # [16, Cin, 3, 3]
+        bs.append(shift.cpu())
+    parts = []
+    slabs = [0, None] + list(range(1, 9))
+    img = torch.zeros(5, 2, 2, 8, 8, dtype=torch.float64)
+    for s, t in enumerate(slabs):
+        if t is None:
+            continue
+        full = torch.zeros(8, 16, dtype=torch.float64)                     # [k, n]
+        wt = ws[0][:, :, t // 3, t % 3]                                    # [16, 2]
+        full[0], full[1], full[2], full[3] = wt[:, 0], wt[:, 1], wt[:, 0], wt[:, 1]
+        img[s // 2, s % 2] = full.t().reshape(2, 8, 8)
+    parts.append(img.reshape(-1))
+    for j in (1, 2):
+        img = torch.zeros(9, 2, 2, 8, 8, dtype=torch.float64)
+        for t in range(9):
+            wt = ws[j][:, :, t // 3, t % 3]                                # [16 n, 16 cin]
+            for c in range(2):
+                img[t, c] = wt[:, c * 8:(c + 1) * 8].reshape(2, 8, 8)      # [n-group][n][k]
+        parts.append(img.reshape(-1))
+    wgt = torch.cat(parts).to(dtype=torch.float16, device=device).contiguous()
+    fp = torch.cat((bs[0], bs[1], bs[2], sd[f"{prefix}.3.weight"].double().reshape(-1).cpu(),
+                    sd[f"{prefix}.3.bias"].double().reshape(-1).cpu())).to(dtype=torch.float32, device=device).contiguous()
+    return wgt, fp
+
+
 @dataclass
 class Conv3dWeights:
     cin: int
@@ -271,6 +306,7 @@ class ModelWeights:
     feature: FeatureWeights
     vis: list
     costreg: list
+    vis_tc: list = field(default_factory=list)   # per stage (fp16 operand image, fp32 biases) for csrc/visnet_tc.cu
 
 
 def pack_model(sd, n_stages: int, device, share_cr: bool = False) -> ModelWeights:
@@ -280,4 +316,5 @@ def pack_model(sd, n_stages: int, device, share_cr: bool = False) -> ModelWeight
         cr = [pack_costreg(sd, "cost_regularization", device)] * n_stages
     else:
         cr = [pack_costreg(sd, f"cost_regularization.{s}", device) for s in range(n_stages)]
-    return ModelWeights(pack_feature(sd, device), vis, cr)
+    vis_tc = [pack_visnet_tc(sd, f"stage_net.vis.{s}", device) for s in range(n_stages)]
+    return ModelWeights(pack_feature(sd, device), vis, cr, vis_tc)

@@ -95,6 +95,13 @@ int cds_visnet_weight_floats(void);
 int cds_visnet(const float* entropy, const float* curv, const float* wpack, int n, int h, int w, float* vis,
                cudaStream_t stream);
 
+/* Tensor-core form (three tcgen05 tap-GEMM layers chained through shared memory), w >= 128.  wgt_packed: fp16 operand
+ * image (cds_visnet_tc_weight_halfs() halfs); fparams: b1[16] b2[16] b3[16] w4[16] b4[1] fp32 (BN folded). */
+int cds_visnet_tc_supported(int h, int w);
+int cds_visnet_tc_weight_halfs(void);
+int cds_visnet_tc(const float* entropy, const float* curv, const void* wgt_packed, const float* fparams, int n, int h, int w,
+                  float* vis, cudaStream_t stream);
+
 /* ---- A4: 3-D regulariser blocks --------------------------------------------------------------- */
 /* Conv3d block (models/module.py:80-122): k3 p1, stride 1|2, BN folded into wgt [27][Cin][Cout] fp32
  * (tap = (kd*3+kh)*3+kw) and bias [Cout], optional ReLU.  in [B,Cin/8,D,H,W,8] -> out [B,Cout/8,ceil(D/s),..,8]. */

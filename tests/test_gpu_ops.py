@@ -395,3 +395,21 @@ def test_deconv3d_tcgen05_vs_torch(cin, cout, shape):
     call("cds_deconv3d_k3s2_tc", ptr(xc), ptr(packed), ptr(bc), ptr(sc), 2, cin, cout, D, H, Wd, ptr(out))
     torch.cuda.synchronize()
     close(from_blocked(out.float().cpu()), ref, 8e-3, 2e-3)
+
+
+@pytest.mark.parametrize("st", [0, 1, 2])
+@pytest.mark.parametrize("hw", [(37, 200), (8, 128), (21, 300)])
+def test_visnet_tcgen05_vs_oracle(pretrained_sd, st, hw):
+    """tcgen05 visibility net (3 chained tap-GEMM layers) against the oracle."""
+    torch.manual_seed(st * 10 + hw[0])
+    x = torch.cat((3.5 * torch.rand(3, 1, *hw), 0.3 * torch.rand(3, 1, *hw)), 1)
+    ref = O.vis_net(x, pretrained_sd, f"stage_net.vis.{st}")
+    wgt, fp = W.pack_visnet_tc(pretrained_sd, f"stage_net.vis.{st}", DEV)
+    assert wgt.numel() == _lib.LIB.load().cds_visnet_tc_weight_halfs()
+    xc = cu(x)
+    ent, cur = xc[:, 0].contiguous(), xc[:, 1].contiguous()
+    out = torch.full((3, *hw), -1.0, device=DEV)
+    call("cds_visnet_tc", ptr(ent), ptr(cur), ptr(wgt), ptr(fp), 3, hw[0], hw[1], ptr(out))
+    torch.cuda.synchronize()
+    assert out.min() >= 0            # every pixel written exactly by its owner tile
+    close(out.unsqueeze(1), ref, 4e-3, 1e-3)
