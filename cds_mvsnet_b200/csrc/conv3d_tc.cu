@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = min((int)blockIdx.x * TXO, p.W - TXO);   // last tile overlaps its neighbour (W >= 128)
+    const int x0 = max(0, min((int)blockIdx.x * TXO, p.W - TXO));   // last tile overlaps its neighbour; W < TXO: one partial tile
     const int y0 = blockIdx.y * TY;
     const int d = blockIdx.z;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
             // their rounding residual; plain sum, fp32 logits in [D,H,W] order
             float v[8];
             tc::tmem_ld8(taddr, v);
-            if (y < p.H && r < TXO) p.logits[((size_t)d * p.H + y) * p.W + x0 + r] = v[0] + v[1];
+            if (y < p.H && r < TXO && x0 + r < p.W) p.logits[((size_t)d * p.H + y) * p.W + x0 + r] = v[0] + v[1];
         } else {
 #pragma unroll
             for (int c8 = 0; c8 < COUT / 8; ++c8) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(128) conv3d_tc_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] += lo[i];
                 }
-                if (y < p.H && r < TXO) {
+                if (y < p.H && r < TXO && x0 + r < p.W) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float t = v[i] + __ldg(p.bias + c8 * 8 + i);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) deconv3d_tc_kernel(const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = min((int)blockIdx.x * TXI, p.W - TXI);
+    const int x0 = max(0, min((int)blockIdx.x * TXI, p.W - TXI));
     const int y0 = blockIdx.y * TY;
     const int d = blockIdx.z;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128) deconv3d_tc_kernel(const __grid_constant_
     const int xi = x0 + r;
     const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
     const size_t Mo = (size_t)Do * Ho * Wo;
-    const bool own = r < TXI && xi >= (int)blockIdx.x * TXI;   // tiles overlap at the right edge: one owner per voxel
+    const bool own = r < TXI && xi < p.W && xi >= (int)blockIdx.x * TXI;   // tiles overlap at the right edge: one owner per voxel
 #pragma unroll 1
     for (int u = 0; u < TY; ++u) {
         const int yi = y0 + u;
@@ -362,7 +362,7 @@ extern "C" {
 
 // 1 when the tensor-core kernel covers this layer shape (otherwise use cds_conv3d_k3)
 int cds_conv3d_k3_tc_supported(int Cin, int Cout, int D, int H, int W, int stride) {
-    if (stride != 1 || W < TX || D < 1 || H < 1 || D > 65535) return 0;
+    if (stride != 1 || W < 8 || D < 1 || H < 1 || D > 65535) return 0;
     return (Cin == 8 && Cout == 1) || (Cin == 8 && Cout == 8) || (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 8) || (Cin == 16 && Cout == 16) ||
            (Cin == 32 && Cout == 32);
 }
@@ -378,11 +378,11 @@ int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, 
                      int W, int relu, void* out, cudaStream_t stream) {
     CDS_REQUIRE(in && wgt_packed && out && (bias || Cout == 1), CDS_EARG, "cds_conv3d_k3_tc: null pointer");
     if (Cin == 8 && Cout == 1) {   // prob head: fp32 logits [B,D,H,W]
-        CDS_REQUIRE(cds_conv3d_k3_tc_supported(8, 1, D, H, W, 1), CDS_EUNSUPPORTED, "cds_conv3d_k3_tc: prob head needs W >= 128");
+        CDS_REQUIRE(cds_conv3d_k3_tc_supported(8, 1, D, H, W, 1), CDS_EUNSUPPORTED, "cds_conv3d_k3_tc: prob head needs W >= 8");
         return launch_tc<8, 1, 16, 8>(in, wgt_packed, bias, B, D, H, W, 0, out, stream);
     }
     CDS_REQUIRE(cds_conv3d_k3_tc_supported(Cin, Cout, D, H, W, 1), CDS_EUNSUPPORTED,
-                "cds_conv3d_k3_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs W >= 128)", Cin, Cout, D, H, W);
+                "cds_conv3d_k3_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs W >= 8)", Cin, Cout, D, H, W);
     if (Cin == 8 && Cout == 8) return launch_tc<8, 8, 16, 8>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 16 && Cout == 8) return launch_tc<16, 8, 16, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 32 && Cout == 8) return launch_tc<32, 8, 16, 2>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
@@ -392,7 +392,7 @@ int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, 
 
 // ---- transposed convolution on the tensor cores (input extent D,H,W; output 2D,2H,2W) ---------------------------------
 int cds_deconv3d_k3s2_tc_supported(int Cin, int Cout, int D, int H, int W) {
-    if (W < TX || D < 1 || H < 1 || D > 65535) return 0;
+    if (W < 8 || D < 1 || H < 1 || D > 65535) return 0;
     return (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 16);   // 64 -> 32: the weight image (256 KB) exceeds smem
 }
 
@@ -402,7 +402,7 @@ int cds_deconv3d_k3s2_tc(const void* in, const void* wgt_packed, const float* bi
                          int D, int H, int W, void* out, cudaStream_t stream) {
     CDS_REQUIRE(in && wgt_packed && bias && out, CDS_EARG, "cds_deconv3d_k3s2_tc: null pointer");
     CDS_REQUIRE(cds_deconv3d_k3s2_tc_supported(Cin, Cout, D, H, W), CDS_EUNSUPPORTED,
-                "cds_deconv3d_k3s2_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs input W >= 128)", Cin, Cout, D, H, W);
+                "cds_deconv3d_k3s2_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d (needs input W >= 8)", Cin, Cout, D, H, W);
     if (Cin == 16) return launch_deconv_tc<16, 8, 4>(in, wgt_packed, bias, skip, B, D, H, W, out, stream);
     return launch_deconv_tc<32, 16, 2>(in, wgt_packed, bias, skip, B, D, H, W, out, stream);
 }

@@ -84,6 +84,8 @@ struct DynTcParams {
     const float* bias;        // [NK][COUT] or NULL
     const float* gate;        // W1f [4][NK], b1 [4], W2 [NK][4]
     __half* out_raw;          // [n][H][W][COUT]
+    __half* out_lo;           // optional: fp16 rounding residual of out_raw (split-precision storage), same shape
+    long long in_lo_images;   // SPLIT input: the residual plane is image index + in_lo_images of the same tensor map
     double* out_stats;        // [n][COUT][2] or NULL
     float* norm_curv;         // [n][H][W] or NULL
     float* nc_sq;             // [n][H][W] or NULL
@@ -98,7 +100,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // MMA J of a tap group as a template parameter: forces every table lookup to a compile-time constant.
 // RING = false: inner KIN x KIN taps, all branches (N = NALL); RING = true: outer ring, largest kernel only.
-template <class C, int CHUNK, bool RING, int J>
+template <class C, int CHUNK, bool RING, bool SPLIT, int J>
 __device__ __forceinline__ void issue_one(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
     constexpr int N = RING ? C::NPAD : C::NALL;
@@ -118,24 +120,34 @@ __device__ __forceinline__ void issue_one(uint32_t a_base, uint32_t b_base, uint
     if (elected)
         tc::mma_f16(acc_col + (RING ? (C::NK - 1) * C::NPAD : 0), ((uint64_t)desc_hi << 32) | (a_base + a_const),
                     ((uint64_t)desc_hi << 32) | (b_base + b_const), idesc, !first);
+    if constexpr (SPLIT) {
+        // split-precision input: the same weights applied to the residual slabs, C8 chunks further on
+        constexpr uint32_t lo_off = ((uint32_t)C::C8 * CHUNK) >> 4;
+        if (elected)
+            tc::mma_f16(acc_col + (RING ? (C::NK - 1) * C::NPAD : 0), ((uint64_t)desc_hi << 32) | (a_base + a_const + lo_off),
+                        ((uint64_t)desc_hi << 32) | (b_base + b_const), idesc, true);
+    }
 }
-template <class C, int CHUNK, bool RING, int... J>
+template <class C, int CHUNK, bool RING, bool SPLIT, int... J>
 __device__ __forceinline__ void issue_group(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected,
                                             std::integer_sequence<int, J...>) {
-    (issue_one<C, CHUNK, RING, J>(a_base, b_base, acc_col, elected), ...);
+    (issue_one<C, CHUNK, RING, SPLIT, J>(a_base, b_base, acc_col, elected), ...);
 }
-template <class C, int CHUNK>
+template <class C, int CHUNK, bool SPLIT>
 __device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uint32_t acc_col, bool elected) {
-    issue_group<C, CHUNK, false>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_IN>{});
-    issue_group<C, CHUNK, true>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_RING>{});
+    issue_group<C, CHUNK, false, SPLIT>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_IN>{});
+    issue_group<C, CHUNK, true, SPLIT>(a_base, b_base, acc_col, elected, std::make_integer_sequence<int, C::MMA_RING>{});
 }
 
-template <class C, int TY>
-__global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+// SPLIT: the input arrives as two fp16 planes (value + rounding residual, i.e. ~22-bit activations); both are normalised
+// together, re-split and fed to the tensor cores as twice as many K slabs (same weights).  Used for the layers the
+// depth output is most sensitive to (conv10, conv11).
+template <class C, int TY, bool SPLIT>
+__global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
     constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO, C8 = C::C8, CIN = C::CIN, COUT = C::COUT, NPAD = C::NPAD;
     constexpr int ROWS = TY + 2 * HALO;
     constexpr uint32_t CHUNK = ROWS * ROW_BYTES;                    // one 8-channel slab of the window
-    constexpr uint32_t A_BYTES = C8 * CHUNK;
+    constexpr uint32_t A_BYTES = (SPLIT ? 2 : 1) * C8 * CHUNK;
     constexpr uint32_t B_BYTES = C::B_BYTES;
     constexpr uint32_t STAGE_COLS = C::NALL;                        // accumulator columns per row unit
     constexpr uint32_t TMEM_COLS = 2 * STAGE_COLS <= 64 ? 64 : (2 * STAGE_COLS <= 128 ? 128 : 256);
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.z;
-    const int x0 = min((int)blockIdx.x * TXO, p.W - TXO);   // last tile overlaps its neighbour (W >= TX)
+    const int x0 = max(0, min((int)blockIdx.x * TXO, p.W - TXO));   // last tile overlaps its neighbour; W < TXO: one partial tile
     const int y0 = blockIdx.y * TY;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
 
@@ -193,6 +205,11 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
         } else {
 #pragma unroll
             for (int c8 = 0; c8 < C8; ++c8) tc::tma_load_5d(sA_u + c8 * CHUNK, &tmap, bar_load, 0, c8, x0 - HALO, y0 - HALO, img);
+            if constexpr (SPLIT) {
+#pragma unroll
+                for (int c8 = 0; c8 < C8; ++c8)
+                    tc::tma_load_5d(sA_u + (C8 + c8) * CHUNK, &tmap, bar_load, 0, c8, x0 - HALO, y0 - HALO, img + (int)p.in_lo_images);
+            }
         }
         tc::bulk_copy_g2s(sB_u, p.wgt, B_BYTES, bar_load);
     }
@@ -208,13 +225,30 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
             uint4 raw = *q;
             __half2* h = reinterpret_cast<__half2*>(&raw);
             const float* nm = s_norm + c8 * 16;
+            if constexpr (SPLIT) {
+                uint4* ql = reinterpret_cast<uint4*>(sA + (size_t)C8 * CHUNK + (size_t)i * 16);
+                uint4 rawl = *ql;
+                __half2* hl = reinterpret_cast<__half2*>(&rawl);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h[j]);
-                f.x = (f.x - nm[4 * j]) * nm[4 * j + 1];
-                f.y = (f.y - nm[4 * j + 2]) * nm[4 * j + 3];
-                if (p.in_act == 1) { f.x = f.x > 0.f ? f.x : 0.1f * f.x; f.y = f.y > 0.f ? f.y : 0.1f * f.y; }
-                h[j] = __floats2half2_rn(f.x, f.y);
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = __half22float2(h[j]), g = __half22float2(hl[j]);
+                    f.x = ((f.x + g.x) - nm[4 * j]) * nm[4 * j + 1];
+                    f.y = ((f.y + g.y) - nm[4 * j + 2]) * nm[4 * j + 3];
+                    if (p.in_act == 1) { f.x = f.x > 0.f ? f.x : 0.1f * f.x; f.y = f.y > 0.f ? f.y : 0.1f * f.y; }
+                    h[j] = __floats2half2_rn(f.x, f.y);
+                    float2 back = __half22float2(h[j]);
+                    hl[j] = __floats2half2_rn(f.x - back.x, f.y - back.y);
+                }
+                *ql = rawl;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = __half22float2(h[j]);
+                    f.x = (f.x - nm[4 * j]) * nm[4 * j + 1];
+                    f.y = (f.y - nm[4 * j + 2]) * nm[4 * j + 3];
+                    if (p.in_act == 1) { f.x = f.x > 0.f ? f.x : 0.1f * f.x; f.y = f.y > 0.f ? f.y : 0.1f * f.y; }
+                    h[j] = __floats2half2_rn(f.x, f.y);
+                }
             }
             *q = raw;
         }
@@ -234,7 +268,7 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
             tc::tc_fence_after();
             const uint32_t a_base = (sA_u + u * ROW_BYTES) >> 4;
             const uint32_t acc = tmem_u + s * STAGE_COLS;
-            issue_unit<C, (int)CHUNK>(a_base, sB_u >> 4, acc, elected);
+            issue_unit<C, (int)CHUNK, SPLIT>(a_base, sB_u >> 4, acc, elected);
             if (elected) tc::mma_commit(bar_full + s);
             __syncwarp();
         }
@@ -264,7 +298,7 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
             const int gy = y0 + u;
             // tiles overlap at the right image edge (x0 is clamped): every pixel is owned by exactly one tile,
             // which matters for the read-modify-write curvature accumulators and the statistics
-            const bool valid = r < TXO && gy < p.H && gx >= (int)blockIdx.x * TXO;
+            const bool valid = r < TXO && gy < p.H && gx < p.W && gx >= (int)blockIdx.x * TXO;
             float uu = (float)gx - ex, vv = (float)gy - ey;
             float rinv = __frcp_rn(sqrtf(uu * uu + vv * vv) + 1e-6f);
             uu *= rinv;
@@ -317,7 +351,15 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
                 for (int b = 0; b < NK; ++b)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) out[c] += wgt[b] * (__uint_as_float(yr[b][c]) + s_bias[b * COUT + c8 * 8 + c]);
-                if (valid) Vec8<__half>::store(p.out_raw + m * COUT + c8 * 8, out);
+                if (valid) {
+                    Vec8<__half>::store(p.out_raw + m * COUT + c8 * 8, out);
+                    if (p.out_lo) {   // split-precision storage: what fp16 rounding just dropped
+                        float res[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) res[c] = out[c] - __half2float(__float2half_rn(out[c]));
+                        Vec8<__half>::store(p.out_lo + m * COUT + c8 * 8, res);
+                    }
+                }
                 if (p.out_stats) {
                     if constexpr (REG_STATS) {
                         if (valid) {
@@ -367,22 +409,33 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? 3 : 2)) dynconv_tc_kerne
     if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// fp32 planar images [n,3,H,W] -> fp16 [n,H,W,8] (channels 3..7 zero): the operand layout of the first layer
+// fp32 planar images [n,3,H,W] -> fp16 [n,H,W,8] = (r, g, b, r_lo, g_lo, b_lo, 0, 0): each colour as an fp16 value plus the
+// fp16 rounding residual.  conv00's weights are duplicated for the residual channels (its 8-channel operand slab has
+// 5 spare channels anyway), so the tensor cores see the image to ~22 bits -- rounding the image itself to fp16 is the
+// largest single term of the fp16 error budget.
 __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long HW, __half* __restrict__ out) {
     const int n = blockIdx.y;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
-        float v[8] = {__ldg(img + ((size_t)n * 3 + 0) * HW + i), __ldg(img + ((size_t)n * 3 + 1) * HW + i),
-                      __ldg(img + ((size_t)n * 3 + 2) * HW + i), 0.f, 0.f, 0.f, 0.f, 0.f};
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float x = __ldg(img + ((size_t)n * 3 + c) * HW + i);
+            float hi = __half2float(__float2half_rn(x));
+            v[c] = hi;
+            v[3 + c] = x - hi;
+        }
+        v[6] = v[7] = 0.f;
         Vec8<__half>::store(out + ((size_t)n * HW + i) * 8, v);
     }
 }
 
-template <class C, int TY>
+template <class C, int TY, bool SPLIT = false>
 int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cudaStream_t st) {
-    constexpr size_t smem = (size_t)C::C8 * (TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 +
+    constexpr size_t smem = (size_t)(SPLIT ? 2 : 1) * C::C8 * (TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 +
                             (2 * C::CIN + 8 * C::COUT + 28 + C::NK * C::COUT) * 4 + 16;
     static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
-    auto kern = dynconv_tc_kernel<C, TY>;
+    static_assert(!SPLIT || C::C8 > 1, "split-precision input is implemented for the multi-chunk layers");
+    auto kern = dynconv_tc_kernel<C, TY, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cds_set_error("cds_dynamic_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     CUtensorMap tmap;
@@ -394,7 +447,7 @@ int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cuda
         const uint32_t box[4] = {2 * TX, (uint32_t)(TY + 2 * C::HALO), 1, 1};
         ok = tma::make_u64(&tmap, x, 4, dims, strides, box);
     } else {            // (8 ch, chunk, W, H, image): one box per 8-channel chunk lands as a slab
-        const uint64_t dims[5] = {8, (uint64_t)C::C8, W, H, NI};
+        const uint64_t dims[5] = {8, (uint64_t)C::C8, W, H, (SPLIT ? 2 : 1) * NI};   // SPLIT: residual plane follows
         const uint64_t strides[5] = {0, 16, (uint64_t)C::CIN * 2, W * C::CIN * 2, H * W * C::CIN * 2};
         const uint32_t box[5] = {8, 1, TX, (uint32_t)(TY + 2 * C::HALO), 1};
         ok = tma::make_f16(&tmap, x, 5, dims, strides, box);
@@ -431,7 +484,7 @@ int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStr
 
 // 1 when the tensor-core DynamicConv covers this layer (the feature extractor's shapes, W >= 128)
 int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* ks) {
-    if (W < TX || H < 1) return 0;
+    if (W < 8 || H < 1) return 0;
     return layer_id(Cin, Cout, num_kernels, ks) != 0;
 }
 
@@ -447,20 +500,28 @@ int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const i
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
                         const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
                         int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
-                        void* out_raw, double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs,
-                        cudaStream_t stream) {
+                        int split_in, void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq,
+                        int nc_mode, float* nc_abs, cudaStream_t stream) {
     CDS_REQUIRE(x && epipole && wgt_packed && gate && out_raw && kernel_sizes, CDS_EARG, "cds_dynamic_conv_tc: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && n_images > 0, CDS_ESHAPE, "cds_dynamic_conv_tc: bad batch");
     CDS_REQUIRE(temperature > 0.f, CDS_EARG, "cds_dynamic_conv_tc: temperature must be positive");
     CDS_REQUIRE(cds_dynamic_conv_tc_supported(Cin, Cout, H, W, num_kernels, kernel_sizes), CDS_EUNSUPPORTED,
-                "cds_dynamic_conv_tc: unsupported layer (Cin=%d Cout=%d W=%d): needs W >= 128 and a feature-extractor layer shape",
+                "cds_dynamic_conv_tc: unsupported layer (Cin=%d Cout=%d W=%d): needs a feature-extractor layer shape",
                 Cin, Cout, W);
     DynTcParams p{};
     p.img_index = img_index; p.in_stats = in_stats; p.epipole = epipole; p.wgt = (const __half*)wgt_packed; p.bias = bias;
     p.gate = gate; p.out_raw = (__half*)out_raw; p.out_stats = out_stats; p.norm_curv = norm_curv; p.nc_sq = nc_sq;
     p.nc_abs = nc_abs; p.in_act = in_act; p.nc_mode = nc_mode; p.H = H; p.W = W; p.epi_scale = epi_scale;
     p.inv_temperature = 1.f / temperature;
-    switch (layer_id(Cin, Cout, num_kernels, kernel_sizes)) {
+    p.out_lo = (__half*)out_lo;
+    p.in_lo_images = n_images;
+    const int lid = layer_id(Cin, Cout, num_kernels, kernel_sizes);
+    if (split_in) {
+        CDS_REQUIRE(lid == 4 && in_stats, CDS_EUNSUPPORTED,
+                    "cds_dynamic_conv_tc: split-precision input is implemented for the 16->16 (3,5) layers with input statistics");
+        return launch_dyn_tc<Cfg<3, 5, 0, 16, 16>, 4, true>(x, n_images, p, n, stream);
+    }
+    switch (lid) {
         case 1: return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8>(x, n_images, p, n, stream);
         case 2: return launch_dyn_tc<Cfg<3, 5, 7, 8, 8>, 8>(x, n_images, p, n, stream);
         case 3: return launch_dyn_tc<Cfg<1, 3, 0, 8, 8>, 8>(x, n_images, p, n, stream);

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) dynconv_kernel(DynParams p) {
 template <typename T, int CIN, int COUT>
 __global__ void __launch_bounds__(128) conv3x3s2_kernel(const T* __restrict__ in, const double* __restrict__ in_stats, int in_act,
                                                         const float* __restrict__ wgt /*[9][CIN][COUT]*/, int Hi, int Wi,
-                                                        T* __restrict__ out, double* __restrict__ out_stats) {
+                                                        T* __restrict__ out, T* __restrict__ out_lo, double* __restrict__ out_stats) {
     extern __shared__ __align__(16) float sm[];
     float* s_w = sm;                       // [9][CIN][COUT]
     float* s_norm = s_w + 9 * CIN * COUT;  // [CIN][2]
@@ -350,6 +350,12 @@ __global__ void __launch_bounds__(128) conv3x3s2_kernel(const T* __restrict__ in
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = acc[0][c8 * 8 + j];
             Vec8<T>::store(op + c8 * 8, y);
+            if (out_lo) {   // split-precision storage: the residual the storage type just dropped
+                float b[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = y[j] - to_f32<T>(from_f32<T>(y[j]));
+                Vec8<T>::store(out_lo + ((size_t)n * Ho * Wo + m) * COUT + c8 * 8, b);
+            }
         }
     }
     bool valid[1] = {live};
@@ -526,7 +532,7 @@ int cds_dynamic_conv(const void* x, int in_mode, const int* img_index, const dou
 }
 
 int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
-                     int W, int dtype, void* out, double* out_stats, cudaStream_t stream) {
+                     int W, int dtype, void* out, void* out_lo, double* out_stats, cudaStream_t stream) {
     CDS_REQUIRE(in && wgt && out, CDS_EARG, "cds_conv2d_3x3s2: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0, CDS_ESHAPE, "cds_conv2d_3x3s2: bad shape");
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
@@ -535,7 +541,7 @@ int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const f
     {                                                                                                                        \
         size_t smem = sizeof(float) * (9 * ci * co + ci * 2 + 4 * co * 2);                                                   \
         cudaFuncSetAttribute(conv3x3s2_kernel<T, ci, co>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        conv3x3s2_kernel<T, ci, co><<<grid, 128, smem, stream>>>((const T*)in, in_stats, in_act, wgt, H, W, (T*)out, out_stats); \
+        conv3x3s2_kernel<T, ci, co><<<grid, 128, smem, stream>>>((const T*)in, in_stats, in_act, wgt, H, W, (T*)out, (T*)out_lo, out_stats); \
         return cds_check_launch("cds_conv2d_3x3s2");                                                                        \
     }
     if (dtype == CDS_F16) {

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.z;
-    const int x0 = min((int)blockIdx.x * TXO, p.W - TXO);
+    const int x0 = max(0, min((int)blockIdx.x * TXO, p.W - TXO));
     const int y0 = blockIdx.y * TY;
     const int xs = x0 - 3;
     const size_t plane = (size_t)p.H * p.W;
@@ -233,14 +233,14 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
 
 extern "C" {
 
-int cds_visnet_tc_supported(int h, int w) { return h >= 1 && w >= TX; }
+int cds_visnet_tc_supported(int h, int w) { return h >= 1 && w >= 8; }
 int cds_visnet_tc_weight_halfs(void) { return (int)(W_BYTES / 2); }
 
 // wgt_packed: fp16 operand image (cds_visnet_tc_weight_halfs() halfs); fparams: b1[16] b2[16] b3[16] w4[16] b4[1] fp32
 int cds_visnet_tc(const float* entropy, const float* curv, const void* wgt_packed, const float* fparams, int n, int h, int w,
                   float* vis, cudaStream_t stream) {
     CDS_REQUIRE(entropy && curv && wgt_packed && fparams && vis, CDS_EARG, "cds_visnet_tc: null pointer");
-    CDS_REQUIRE(n > 0 && n <= 65535 && cds_visnet_tc_supported(h, w), CDS_EUNSUPPORTED, "cds_visnet_tc: needs w >= 128 (got %dx%d)", h, w);
+    CDS_REQUIRE(n > 0 && n <= 65535 && cds_visnet_tc_supported(h, w), CDS_EUNSUPPORTED, "cds_visnet_tc: needs w >= 8 (got %dx%d)", h, w);
     constexpr size_t smem = (size_t)X_BYTES + Y_BYTES + W_BYTES + 8 * 5 + 65 * 4 + 32;
     cudaError_t e = cudaFuncSetAttribute(visnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cds_set_error("cds_visnet_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -64,11 +64,14 @@ class FeatureExtractor:
         self.fw = fw
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
-        self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0"   # tcgen05 DynamicConv where covered
+        self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_DYN", "1") != "0"
+        # opt-in: hi/lo fp16 activation planes into conv10/conv11 (4x lower error in those layers at 2x their MMAs; the
+        # end-to-end gain on the worst-case input is within sample noise)
+        self.split_precision = os.environ.get("CDS_SPLIT", "0") == "1"
         self._buf = None
 
     def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
-             nc_mode, nc_abs, norm_curv=None):
+             nc_mode, nc_abs, norm_curv=None, split_in=False, out_lo=None):
         w = self.fw.dyn[name]
         e = _esize(self.storage)
         px = n * H * W
@@ -85,14 +88,20 @@ class FeatureExtractor:
                 call("cds_image_to_nhwc8", ptr(x), n_images, H, W, ptr(img8))
                 x = img8
             call("cds_dynamic_conv_tc", ptr(x), n_images, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
-                 ptr(w.tc), ptr(w.bias), ptr(w.gate), n, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T), ptr(out),
-                 ptr(out_stats),
+                 ptr(w.tc), ptr(w.bias), ptr(w.gate), n, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T),
+                 int(split_in), ptr(out), ptr(out_lo), ptr(out_stats),
                  ptr(norm_curv), ptr(nc_sq), nc_mode, ptr(nc_abs))
             return
+        assert not split_in and out_lo is None, "split-precision activations exist on the tensor-core path only"
         call("cds_dynamic_conv", ptr(x), in_mode, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
              ptr(w.w_att), ptr(w.w_conv), ptr(w.bias), ptr(w.gate), n, w.cin, w.cout, H, W, len(w.ksizes),
              _ksizes(w.ksizes), float(T), self.dt, ptr(out), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode,
              ptr(nc_abs))
+
+    def _split_ok(self, H2, W2):
+        w = self.fw.dyn["conv10"]
+        return bool(self.use_tc and self.split_precision and w.tc is not None and self.storage == torch.float16
+                    and _lib.LIB.load().cds_dynamic_conv_tc_supported(16, 16, H2, W2, 2, _ksizes(w.ksizes)))
 
     def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature):
         """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
@@ -115,8 +124,11 @@ class FeatureExtractor:
         f32 = torch.float32
         raw00 = buf.get("f.raw00", (n, H, W, 8), st)
         raw01 = buf.get("f.raw01", (n, H, W, 8), st)
-        rawd1 = buf.get("f.rawd1", (n, H2, W2, 16), st)
-        raw10 = buf.get("f.raw10", (n, H2, W2, 16), st)
+        # conv10 / conv11 are the layers the depth output is most sensitive to: on the tensor-core path
+        # their inputs are kept as two fp16 planes (value + rounding residual) and fed as twice as many K slabs
+        split = self._split_ok(H2, W2)
+        rawd1 = buf.get("f.rawd1", (2 if split else 1, n, H2, W2, 16), st)
+        raw10 = buf.get("f.raw10", (2 if split else 1, n, H2, W2, 16), st)
         raw11 = buf.get("f.raw11", (n, H2, W2, 16), st)
         rawd2 = buf.get("f.rawd2", (n, H4, W4, 32), st)
         raw20 = buf.get("f.raw20", (n, H4, W4, 32), st)
@@ -138,12 +150,16 @@ class FeatureExtractor:
         self._dyn("conv01", raw00, 0, None, sv(0, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, raw01, sv(1, 8), ncsq[2], 1, None)
         # 1/2 resolution
         kcall("feat.downsample1", 2.0 * 9 * 8 * 16 * n * H2 * W2, n * (H * W * 8 + H2 * W2 * 16) * e,
-              "cds_conv2d_3x3s2", ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.downsample1), n, 8, 16, H, W, dt, ptr(rawd1), ptr(sv(2, 16)))
-        self._dyn("conv10", rawd1, 0, None, sv(2, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw10, sv(3, 16), ncsq[1], 0, None)
-        self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11, sv(4, 16), ncsq[1], 1, None)
+              "cds_conv2d_3x3s2", ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.downsample1), n, 8, 16, H, W, dt, ptr(rawd1[0]),
+              ptr(rawd1[1]) if split else None, ptr(sv(2, 16)))
+        self._dyn("conv10", rawd1, 0, None, sv(2, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw10[0], sv(3, 16), ncsq[1], 0, None,
+                  split_in=split, out_lo=raw10[1] if split else None)
+        self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11, sv(4, 16), ncsq[1], 1, None,
+                  split_in=split)
         # 1/4 resolution
         kcall("feat.downsample2", 2.0 * 9 * 16 * 32 * n * H4 * W4, n * (H2 * W2 * 16 + H4 * W4 * 32) * e,
-              "cds_conv2d_3x3s2", ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.downsample2), n, 16, 32, H2, W2, dt, ptr(rawd2), ptr(sv(5, 32)))
+              "cds_conv2d_3x3s2", ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.downsample2), n, 16, 32, H2, W2, dt, ptr(rawd2), None,
+              ptr(sv(5, 32)))
         self._dyn("conv20", rawd2, 0, None, sv(5, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw20, sv(6, 32), ncsq[0], 0, None)
         self._dyn("conv21", raw20, 0, None, sv(6, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw21, sv(7, 32), ncsq[0], 1, None)
         # stage-1 output
@@ -171,7 +187,7 @@ class Regulariser:
         self.cw = cw
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
-        self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0"   # tcgen05 kernels where covered
+        self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV3D", "1") != "0"
         self.tag = "cr"
 
     def _conv(self, name, x, B, D, H, W, stride, out):
@@ -251,7 +267,7 @@ class CascadeEngine:
         self.buf = Buffers(self.device)
         self.features = FeatureExtractor(weights.feature, storage)
         self.regs = [Regulariser(cw, storage) for cw in weights.costreg]
-        self.use_tc = os.environ.get("CDS_USE_TC", "1") != "0"
+        self.use_tc = os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_VIS", "1") != "0"
         self.launches = 0
 
     # -- pieces -------------------------------------------------------------------------------

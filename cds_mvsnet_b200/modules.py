@@ -186,7 +186,8 @@ class DynamicConv(_CachedModule):
             else:
                 x8 = _nhwc(feature_vol, torch.float16)
             call("cds_dynamic_conv_tc", ptr(x8), B, None, None, ACT_NONE, ptr(epi), 1.0, ptr(w.tc), ptr(w.bias), ptr(w.gate),
-                 B, cin_tc, self.out_c, H, Wd, len(w.ksizes), ks, float(temperature), ptr(raw), None, ptr(nc), None, 0, None)
+                 B, cin_tc, self.out_c, H, Wd, len(w.ksizes), ks, float(temperature), 0, ptr(raw), None, None, ptr(nc), None, 0,
+                 None)
             return _nchw(raw), nc
         if C == 3:
             x, mode = _f32c(feature_vol), 1

@@ -98,6 +98,8 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
                 full[t, :cin, npad * b + cout:npad * b + cout + 3] = hi
                 full[t, :cin, npad * b + cout + 3:npad * b + cout + 6] = a - hi
         t0 += k * k
+    if cin == 3:   # image layer: channels 3..5 of the operand carry the image's fp16 rounding residual (cds_image_to_nhwc8)
+        full[:, 3:6, :] = full[:, 0:3, :]
     kin = max(k for k in w.ksizes if k < kmax)
     lo, hi_ = (kmax - kin) // 2, (kmax - kin) // 2 + kin
     inside = lambda t: lo <= t // kmax < hi_ and lo <= t % kmax < hi_

@@ -158,18 +158,21 @@ int cds_dynamic_conv(const void* x, int in_mode, const int* img_index, const dou
  * (3,7,11) [conv00, image padded to 8 channels by cds_image_to_nhwc8], (3,5,7), (1,3); 16->16 with (3,5), (1,3);
  * 32->32 with (1,3)), fp16 storage, W >= 128.  Same semantics and outputs as cds_dynamic_conv.
  * x: [n_images,H,W,Cin] fp16; item i reads image img_index[i] (NULL: i); wgt_packed: fp16 operand image from the host
- * (cds_dynamic_conv_tc_weight_halfs() halfs, layout in csrc/dynconv_tc.cu).  kernel_sizes is a HOST array. */
+ * (cds_dynamic_conv_tc_weight_halfs() halfs, layout in csrc/dynconv_tc.cu).  kernel_sizes is a HOST array.
+ * Split-precision activations (value + fp16 rounding residual as two fp16 planes, ~22 bits): split_in = 1 means x is
+ * [2,n_images,H,W,Cin] (residual plane second; 16->16 (3,5) layers only); out_lo, if non-NULL, receives the residual
+ * plane of out_raw.  cds_conv2d_3x3s2 has the same out_lo. */
 int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStream_t stream);
 int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
                         const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
                         int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
-                        void* out_raw, double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs,
-                        cudaStream_t stream);
+                        int split_in, void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq,
+                        int nc_mode, float* nc_abs, cudaStream_t stream);
 /* FeatureNet.downsample1/2 (models/module.py:214,218): 3x3 stride 2 pad 1, wgt [9][Cin][Cout]. */
 int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
-                     int W, int dtype, void* out, double* out_stats, cudaStream_t stream);
+                     int W, int dtype, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
 /* FeatureNet.inner1/2 (models/module.py:253-254,260-261): 1x1 conv over cat(nearest-up2(a), b);
  * a [n,H/2,W/2,Ca], b [n,H,W,Cb], wgt [Ca+Cb][Cout]. */
 int cds_conv2d_1x1_cat(const void* a, const double* a_stats, int a_act, const void* b, const double* b_stats, int b_act,

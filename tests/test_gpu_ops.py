@@ -301,7 +301,7 @@ def test_costvol_rejects_too_many_views():
 
 # ---------------------------------------------------------------------------------------- A4 on tensor cores
 @pytest.mark.parametrize("cin,cout", [(8, 8), (16, 8), (32, 8), (16, 16), (32, 32)])
-@pytest.mark.parametrize("shape", [(3, 5, 133), (2, 9, 256), (1, 4, 128)])
+@pytest.mark.parametrize("shape", [(3, 5, 133), (2, 9, 256), (1, 4, 128), (4, 6, 50), (2, 3, 100)])
 def test_conv3d_tcgen05_vs_torch(cin, cout, shape):
     """tcgen05 implicit-GEMM Conv3d block against the published operator on fp16-rounded operands
     (fp32 accumulation on both sides, so only summation order differs)."""
@@ -328,16 +328,16 @@ def test_conv3d_tcgen05_vs_torch(cin, cout, shape):
 
 def test_conv3d_tcgen05_unsupported_shapes():
     lib = _lib.LIB.load()
-    assert lib.cds_conv3d_k3_tc_supported(8, 8, 8, 8, 100, 1) == 0      # W < 128: direct kernel instead
-    assert lib.cds_conv3d_k3_tc_supported(8, 16, 8, 8, 256, 2) == 0     # stride 2
+    assert lib.cds_conv3d_k3_tc_supported(8, 8, 8, 8, 4, 1) == 0        # too narrow
+    assert lib.cds_conv3d_k3_tc_supported(8, 16, 8, 8, 256, 2) == 0     # stride 2: CUDA-core kernel
     z = torch.zeros(64, device=DEV, dtype=torch.float16)
     with pytest.raises(RuntimeError, match="unsupported"):
-        call("cds_conv3d_k3_tc", ptr(z), ptr(z), ptr(z), 1, 8, 8, 4, 4, 64, 1, ptr(z))
+        call("cds_conv3d_k3_tc", ptr(z), ptr(z), ptr(z), 1, 8, 24, 4, 4, 64, 1, ptr(z))
 
 
 # ---------------------------------------------------------------------------------------- A6 on tensor cores
 @pytest.mark.parametrize("name", ["conv00", "conv01", "out3", "conv10", "out2", "conv20", "out1"])
-@pytest.mark.parametrize("hw", [(37, 200), (64, 128), (16, 333)])
+@pytest.mark.parametrize("hw", [(37, 200), (64, 128), (16, 333), (24, 40), (30, 100)])
 def test_dynamic_conv_tcgen05_vs_oracle(pretrained_sd, name, hw):
     """tcgen05 DynamicConv (every layer shape of the feature extractor) against the oracle and the CUDA-core kernel."""
     cin, cout, ks, pre = W.DYN_LAYERS[name]
@@ -375,7 +375,7 @@ def test_prob_head_tcgen05_vs_torch():
 
 
 @pytest.mark.parametrize("cin,cout", [(16, 8), (32, 16)])
-@pytest.mark.parametrize("shape", [(3, 5, 133), (2, 4, 256), (1, 2, 128)])
+@pytest.mark.parametrize("shape", [(3, 5, 133), (2, 4, 256), (1, 2, 128), (3, 4, 25), (2, 2, 100)])
 def test_deconv3d_tcgen05_vs_torch(cin, cout, shape):
     """tcgen05 transposed conv (8 output parity classes side by side in N) against the published operator."""
     D, H, Wd = shape
@@ -398,7 +398,7 @@ def test_deconv3d_tcgen05_vs_torch(cin, cout, shape):
 
 
 @pytest.mark.parametrize("st", [0, 1, 2])
-@pytest.mark.parametrize("hw", [(37, 200), (8, 128), (21, 300)])
+@pytest.mark.parametrize("hw", [(37, 200), (8, 128), (21, 300), (32, 40), (19, 100)])
 def test_visnet_tcgen05_vs_oracle(pretrained_sd, st, hw):
     """tcgen05 visibility net (3 chained tap-GEMM layers) against the oracle."""
     torch.manual_seed(st * 10 + hw[0])
@@ -413,3 +413,44 @@ def test_visnet_tcgen05_vs_oracle(pretrained_sd, st, hw):
     torch.cuda.synchronize()
     assert out.min() >= 0            # every pixel written exactly by its owner tile
     close(out.unsqueeze(1), ref, 4e-3, 1e-3)
+
+
+@pytest.mark.parametrize("hw", [(24, 80), (37, 200)])
+def test_dynamic_conv_tcgen05_split_precision(pretrained_sd, hw):
+    """Split-precision input (fp16 value + fp16 residual planes) with the producer's InstanceNorm + LeakyReLU applied on
+    load: must be clearly more accurate than the single-plane path, and both must match the oracle."""
+    import ctypes
+    cin, cout, ks, pre = W.DYN_LAYERS["conv10"]
+    torch.manual_seed(hw[1])
+    n = 2
+    x = 1.7 + 0.8 * torch.randn(n, cin, *hw)                       # raw pre-norm activations with a mean offset
+    epi = torch.tensor([[hw[1] * 1.7, -hw[0] * 0.6], [-30.0, hw[0] / 2.0]])
+    xin = torch.nn.functional.leaky_relu(O.instance_norm(x), 0.1)
+    ref_y, ref_nc = O.dynamic_conv(xin, pretrained_sd, pre, ks, epi, T)
+    w = W.pack_dynamic_conv(pretrained_sd, pre, cin, cout, ks, DEV)
+    w.tc = W.pack_dynamic_conv_tc(w)
+    nhwc = x.permute(0, 2, 3, 1).contiguous()
+    hi = nhwc.half()
+    lo = (nhwc - hi.float()).half()
+    stats = torch.stack((x.double().sum((2, 3)), (x.double() ** 2).sum((2, 3))), -1).contiguous()   # [n, C, 2]
+    kz = (ctypes.c_int * 2)(*ks)
+    errs = {}
+    for split in (1, 0):
+        planes = cu(torch.stack((hi, lo)) if split else hi.unsqueeze(0)).contiguous()
+        st = cu(stats)
+        if not split:   # statistics of what is actually stored
+            xs = hi.float().permute(0, 3, 1, 2).double()
+            st = cu(torch.stack((xs.sum((2, 3)), (xs ** 2).sum((2, 3))), -1).contiguous())
+        out = torch.empty(n, *hw, cout, device=DEV, dtype=torch.float16)
+        out_lo = torch.empty_like(out)
+        nc = torch.empty(n, *hw, device=DEV)
+        epi_c = cu(epi)
+        call("cds_dynamic_conv_tc", ptr(planes), n, None, ptr(st), 1, ptr(epi_c), 1.0, ptr(w.tc), None, ptr(w.gate), n, cin, cout,
+             hw[0], hw[1], 2, kz, T, split, ptr(out), ptr(out_lo), None, ptr(nc), None, 0, None)
+        torch.cuda.synchronize()
+        y = (out.float() + out_lo.float()).cpu().permute(0, 3, 1, 2)
+        errs[split] = (O.rel_l1(y, ref_y), O.rel_l1(nc.cpu().unsqueeze(1), ref_nc))
+    print("split-precision conv10 rel-L1 (out, curv): split", errs[1], " single", errs[0])
+    assert errs[0][0] < 4e-3 and errs[0][1] < 4e-3
+    assert errs[1][0] < 1e-3 and errs[1][1] < 1e-3
+    assert errs[1][0] < 0.7 * errs[0][0]
