@@ -67,6 +67,25 @@ __device__ __forceinline__ void accumulate_stats(const float (&vals)[NP][C], con
     }
 }
 
+constexpr int kChunks = 8;   // pixel chunks (of blockDim pixels) per block in the small 2-D conv kernels
+
+// same reduction for per-thread running (sum, sumsq) accumulators
+template <int C>
+__device__ __forceinline__ void accumulate_stats2(const float (&st)[2][C], double* __restrict__ stats, float* s_red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float s = warp_sum(st[0][c]), ss = warp_sum(st[1][c]);
+        if (lane == 0) { s_red[(warp * C + c) * 2] = s; s_red[(warp * C + c) * 2 + 1] = ss; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += (double)s_red[w * C * 2 + i];
+        atomicAdd(stats + i, t);
+    }
+}
+
 struct DynParams {
     const void* x;            // input activations
     const int* img_index;     // in_mode 1: image used by batch item n (ref image shared by several items)
@@ -309,13 +328,18 @@ __global__ void __launch_bounds__(128) conv3x3s2_kernel(const T* __restrict__ in
         else { s_norm[2 * c] = 0.f; s_norm[2 * c + 1] = 1.f; }
     }
     __syncthreads();
-    long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const T* src = in + (size_t)n * Hi * Wi * CIN;
+    float st[2][COUT];   // running (sum, sumsq) of this thread's outputs
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { st[0][c] = 0.f; st[1][c] = 0.f; }
+    // each block walks kChunks pixel chunks so the prologue (weights, fp64 norm coefficients) is amortised
+    for (int chunk = 0; chunk < kChunks; ++chunk) {
+    long long m = ((long long)blockIdx.x * kChunks + chunk) * blockDim.x + threadIdx.x;
     bool live = m < (long long)Ho * Wo;
     int ox = live ? (int)(m % Wo) : 0, oy = live ? (int)(m / Wo) : 0;
     float acc[1][COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[0][c] = 0.f;
-    const T* src = in + (size_t)n * Hi * Wi * CIN;
     if (live) {
         for (int ky = 0; ky < 3; ++ky) {
             int iy = 2 * oy - 1 + ky;
@@ -357,9 +381,11 @@ __global__ void __launch_bounds__(128) conv3x3s2_kernel(const T* __restrict__ in
                 Vec8<T>::store(out_lo + ((size_t)n * Ho * Wo + m) * COUT + c8 * 8, b);
             }
         }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { st[0][c] += acc[0][c]; st[1][c] += acc[0][c] * acc[0][c]; }
     }
-    bool valid[1] = {live};
-    if (out_stats) accumulate_stats<COUT, 1>(acc, valid, out_stats + (size_t)n * COUT * 2, s_red);
+    }
+    if (out_stats) accumulate_stats2<COUT>(st, out_stats + (size_t)n * COUT * 2, s_red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -388,7 +414,11 @@ __global__ void __launch_bounds__(128) conv1x1_cat_kernel(const T* __restrict__ 
         if (c >= CA && b_stats) norm_coeffs(b_stats, n, CB, c - CA, (double)H * W, s_norm[2 * c], s_norm[2 * c + 1]);
     }
     __syncthreads();
-    long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float st[2][COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { st[0][c] = 0.f; st[1][c] = 0.f; }
+    for (int chunk = 0; chunk < kChunks; ++chunk) {
+    long long m = ((long long)blockIdx.x * kChunks + chunk) * blockDim.x + threadIdx.x;
     bool live = m < (long long)H * W;
     int x = live ? (int)(m % W) : 0, y = live ? (int)(m / W) : 0;
     float acc[1][COUT];
@@ -424,9 +454,11 @@ __global__ void __launch_bounds__(128) conv1x1_cat_kernel(const T* __restrict__ 
             for (int j = 0; j < 8; ++j) yv[j] = acc[0][c8 * 8 + j];
             Vec8<T>::store(op + c8 * 8, yv);
         }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { st[0][c] += acc[0][c]; st[1][c] += acc[0][c] * acc[0][c]; }
     }
-    bool valid[1] = {live};
-    if (out_stats) accumulate_stats<COUT, 1>(acc, valid, out_stats + (size_t)n * COUT * 2, s_red);
+    }
+    if (out_stats) accumulate_stats2<COUT>(st, out_stats + (size_t)n * COUT * 2, s_red);
 }
 
 // InstanceNorm + activation materialised (the three stage features: InstanceNorm2d -> Tanh, module.py:223,230,232)
@@ -536,7 +568,7 @@ int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const f
     CDS_REQUIRE(in && wgt && out, CDS_EARG, "cds_conv2d_3x3s2: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0, CDS_ESHAPE, "cds_conv2d_3x3s2: bad shape");
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-    dim3 grid(cds_div_up((long long)Ho * Wo, 128), n);
+    dim3 grid(cds_div_up((long long)Ho * Wo, 128 * kChunks), n);
 #define CDS_GO(T, ci, co)                                                                                                   \
     {                                                                                                                        \
         size_t smem = sizeof(float) * (9 * ci * co + ci * 2 + 4 * co * 2);                                                   \
@@ -561,7 +593,7 @@ int cds_conv2d_1x1_cat(const void* a, const double* a_stats, int a_act, const vo
                        double* out_stats, cudaStream_t stream) {
     CDS_REQUIRE(a && b && wgt && out, CDS_EARG, "cds_conv2d_1x1_cat: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, CDS_ESHAPE, "cds_conv2d_1x1_cat: bad shape");
-    dim3 grid(cds_div_up((long long)H * W, 128), n);
+    dim3 grid(cds_div_up((long long)H * W, 128 * kChunks), n);
 #define CDS_GO(T, ca, cb, co)                                                                                                  \
     {                                                                                                                           \
         size_t smem = sizeof(float) * ((ca + cb) * co + (ca + cb) * 2 + 4 * co * 2);                                            \
