@@ -9,23 +9,110 @@
 // because the ref features depend on the pair's epipole, model.py:154-161); a thread owns one
 // (pixel, 8-channel chunk) so each bilinear tap is one 16-byte (fp16) load and the C/8 lanes of
 // a pixel reduce the channel sum with warp shuffles.
+//
+// Both kernels are instruction-issue bound (ncu: 78 % issue-active, IPC 3.1), so the work per gather is
+// trimmed: the C/8 lanes of a pixel SHARE the projection + bilinear-footprint arithmetic (each lane does it
+// for one plane / one view and broadcasts 6 words by shuffle), interior footprints take a branch-free fast
+// path, and the blend / dot products run as packed fp32x2 FMAs (FFMA2, sm_100).
 #include "cds_common.cuh"
 
 namespace {
 
 constexpr int kMaxViews = 8;
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2) ------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+    return d;
+}
+
+// 8 channels of one pixel as four fp32 pairs
 template <typename T>
-__device__ __forceinline__ void gather8(const T* __restrict__ fea, int w, int h, int C, const Taps& t, float (&out)[8]) {
-    int xa = min(max(t.x0, 0), w - 1), xb = min(max(t.x0 + 1, 0), w - 1);
-    int ya = min(max(t.y0, 0), h - 1), yb = min(max(t.y0 + 1, 0), h - 1);
-    float a[8], b[8], c[8], d[8];
-    Vec8<T>::load(fea + ((size_t)ya * w + xa) * C, a);
-    Vec8<T>::load(fea + ((size_t)ya * w + xb) * C, b);
-    Vec8<T>::load(fea + ((size_t)yb * w + xa) * C, c);
-    Vec8<T>::load(fea + ((size_t)yb * w + xb) * C, d);
+struct Pix8;
+template <>
+struct Pix8<__half> {
+    __device__ static __forceinline__ void load(const __half* p, float2 (&v)[4]) {
+        uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = t.w00 * a[i] + t.w01 * b[i] + t.w10 * c[i] + t.w11 * d[i];
+        for (int i = 0; i < 4; ++i) v[i] = __half22float2(h[i]);
+    }
+};
+template <>
+struct Pix8<float> {
+    __device__ static __forceinline__ void load(const float* p, float2 (&v)[4]) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+        v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+    }
+};
+
+// Bilinear footprint in gather form: pixel offset of the (clamped) top-left tap, whether the right / lower
+// neighbours are distinct pixels, and the four weights (0 for taps outside the image: zero padding,
+// warping.py:100-101).
+struct Foot {
+    int o00;     // ya * w + xa
+    int step;    // bit 0: xb != xa, bit 1: yb != ya
+    float w00, w01, w10, w11;
+};
+__device__ __forceinline__ Foot make_foot(float u, float v, int w, int h) {
+    Foot f;
+    // F2I saturates (NaN -> 0, huge -> INT_MIN/MAX), so wild coordinates fail the interior test and land in make_taps
+    int x0 = __float2int_rd(u), y0 = __float2int_rd(v);
+    if ((unsigned)x0 < (unsigned)(w - 1) && (unsigned)y0 < (unsigned)(h - 1)) {
+        float fx = u - (float)x0, fy = v - (float)y0;
+        float gx = 1.f - fx, gy = 1.f - fy;
+        f.o00 = y0 * w + x0;
+        f.step = 3;
+        f.w00 = gx * gy; f.w01 = fx * gy; f.w10 = gx * fy; f.w11 = fx * fy;
+    } else {
+        Taps t = make_taps(u, v, w, h);
+        int xa = min(max(t.x0, 0), w - 1), xb = min(max(t.x0 + 1, 0), w - 1);
+        int ya = min(max(t.y0, 0), h - 1), yb = min(max(t.y0 + 1, 0), h - 1);
+        f.o00 = ya * w + xa;
+        f.step = (xb != xa ? 1 : 0) | (yb != ya ? 2 : 0);
+        f.w00 = t.w00; f.w01 = t.w01; f.w10 = t.w10; f.w11 = t.w11;
+    }
+    return f;
+}
+// broadcast the footprint computed by lane `src` of the warp
+__device__ __forceinline__ Foot shfl_foot(const Foot& f, int src) {
+    Foot g;
+    g.o00 = __shfl_sync(0xffffffffu, f.o00, src);
+    g.step = __shfl_sync(0xffffffffu, f.step, src);
+    g.w00 = __shfl_sync(0xffffffffu, f.w00, src);
+    g.w01 = __shfl_sync(0xffffffffu, f.w01, src);
+    g.w10 = __shfl_sync(0xffffffffu, f.w10, src);
+    g.w11 = __shfl_sync(0xffffffffu, f.w11, src);
+    return g;
+}
+
+// bilinear blend of 8 channels at footprint f; fea points at (image, this thread's channel chunk)
+template <typename T, int C>
+__device__ __forceinline__ void gather8(const T* __restrict__ fea, int w, const Foot& f, float2 (&out)[4]) {
+    const T* p00 = fea + (size_t)(unsigned)(f.o00 * C);
+    const int dx = (f.step & 1) ? C : 0;
+    const int dy = (f.step & 2) ? w * C : 0;
+    float2 a[4], b[4], c[4], d[4];
+    Pix8<T>::load(p00, a);
+    Pix8<T>::load(p00 + dx, b);
+    Pix8<T>::load(p00 + dy, c);
+    Pix8<T>::load(p00 + dy + dx, d);
+    const float2 w00 = make_float2(f.w00, f.w00), w01 = make_float2(f.w01, f.w01);
+    const float2 w10 = make_float2(f.w10, f.w10), w11 = make_float2(f.w11, f.w11);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = ffma2(w11, d[i], ffma2(w10, c[i], ffma2(w01, b[i], fmul2(w00, a[i]))));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -39,19 +126,20 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
     const long long P = (long long)h * w;
     const long long total = (long long)V * B * P * LPP;
     long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    // total is padded by the host to a multiple of the block size only through this guard;
-    // lanes of one pixel are always in the same warp because LPP divides 32
+    // lanes of one pixel are always in the same warp because LPP divides 32; dead lanes of the last warp redo the
+    // last pixel so that every shuffle below is executed by the full warp
     bool live = gid < total;
     long long g = live ? gid : total - 1;
     int chunk = (int)(g % LPP);
     long long pix = g / LPP;
     int x = (int)(pix % w), y = (int)((pix / w) % h);
     int b = (int)((pix / P) % B), v = (int)(pix / (P * B));
+    const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
 
     const T* rf = ref_fea + (((size_t)v * B + b) * P + (size_t)y * w + x) * C + chunk * 8;
     const T* sf = src_fea + ((size_t)v * B + b) * P * C + chunk * 8;
-    float ref[8];
-    Vec8<T>::load(rf, ref);
+    float2 ref[4];
+    Pix8<T>::load(rf, ref);
     WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
     float rx, ry, rz;
     pixel_ray(k, (float)x, (float)y, rx, ry, rz);
@@ -59,86 +147,130 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
 
     // online softmax statistics: m = running max, S = sum e^(s-m), A = sum (s-m) e^(s-m)
     float m = -INFINITY, S = 0.f, A = 0.f;
-    for (int d = 0; d < D; ++d) {
-        float dep = __ldg(dp + (size_t)d * P);
-        float u, vv;
-        project_fast(k, rx, ry, rz, dep, u, vv);
-        Taps t = make_taps(u, vv, w, h);
-        float wv[8];
-        gather8<T>(sf, w, h, C, t, wv);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s += ref[i] * wv[i];
-#pragma unroll
-        for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (s > m) {
-            float delta = m - s;  // <= 0 (or -inf on the first plane)
-            float e = __expf(delta);
-            A = (d == 0) ? 0.f : e * (A + delta * S);
-            S = (d == 0) ? 0.f : S * e;
-            m = s;
+    for (int d0 = 0; d0 < D; d0 += LPP) {
+        // lane `chunk` of the pixel projects plane d0 + chunk (clamped when D is not a multiple of LPP)
+        Foot mine;
+        {
+            float dep = __ldg(dp + (size_t)min(d0 + chunk, D - 1) * P);
+            float u, vv;
+            project_fast(k, rx, ry, rz, dep, u, vv);
+            mine = make_foot(u, vv, w, h);
         }
-        float z = s - m;
-        float e = __expf(z);
-        S += e;
-        A += z * e;
+#pragma unroll
+        for (int j = 0; j < LPP; ++j) {
+            if (d0 + j >= D) break;   // warp-uniform
+            Foot f = LPP == 1 ? mine : shfl_foot(mine, lane_base + j);
+            float2 wv[4];
+            gather8<T, C>(sf, w, f, wv);
+            float2 s2 = fmul2(ref[0], wv[0]);
+#pragma unroll
+            for (int i = 1; i < 4; ++i) s2 = ffma2(ref[i], wv[i], s2);
+            float s = s2.x + s2.y;
+#pragma unroll
+            for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (s > m) {
+                float delta = m - s;  // <= 0 (or -inf on the first plane)
+                float e = __expf(delta);
+                const bool first = (d0 + j) == 0;
+                A = first ? 0.f : e * (A + delta * S);
+                S = first ? 0.f : S * e;
+                m = s;
+            }
+            float z = s - m;
+            float e = __expf(z);
+            S += e;
+            A += z * e;
+        }
     }
     if (live && chunk == 0) entropy[((size_t)v * B + b) * P + (size_t)y * w + x] = __logf(S) - A / S;
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass 2: volume[b, d, y, x, :] = sum_v vis_v * ref_v (.) warp_{v,d} / (sum_v vis_v + 1e-6)
+// Lane `chunk` of a pixel owns the projection of views chunk, chunk + LPP, ... (its rays and translations stay in
+// registers) and broadcasts each footprint to the pixel's other lanes.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int C>
-__global__ void __launch_bounds__(256, 4) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
+template <typename T, int C, int VMAX>
+__global__ void __launch_bounds__(256, VMAX <= 4 ? 3 : 2) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                         const float* __restrict__ coef, const float* __restrict__ depth,
                                                         const float* __restrict__ vis, int V, int B, int D, int h, int w,
                                                         T* __restrict__ volume) {
     constexpr int LPP = C / 8;
+    constexpr int OWN = (VMAX + LPP - 1) / LPP;   // views whose projection this lane may own (V <= VMAX)
     const long long P = (long long)h * w;
     const long long total = (long long)B * P * LPP;
-    long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (g >= total) return;
+    long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    bool live = gid < total;
+    long long g = live ? gid : total - 1;
     int chunk = (int)(g % LPP);
     long long pix = g / LPP;
     int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / P);
     size_t pofs = (size_t)y * w + x;
+    const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
 
-    float vw[kMaxViews];
+    // visibility weights of this pixel
     float vsum = 0.f;
+    float vw[VMAX];
 #pragma unroll
-    for (int v = 0; v < kMaxViews; ++v) {
+    for (int v = 0; v < VMAX; ++v) {
         vw[v] = (v < V) ? __ldg(vis + ((size_t)v * B + b) * P + pofs) : 0.f;
         if (v < V) vsum += vw[v];  // same accumulation order as the reference loop (model.py:59)
     }
-    float inv = 1.f / (vsum + 1e-6f);
+    const float inv = 1.f / (vsum + 1e-6f);
+    // per owned view: ray and translation
+    float orx[OWN], ory[OWN], orz[OWN], otx[OWN], oty[OWN], otz[OWN];
+#pragma unroll
+    for (int q = 0; q < OWN; ++q) {
+        int v = q * LPP + chunk;
+        if (v < V) {
+            WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
+            pixel_ray(k, (float)x, (float)y, orx[q], ory[q], orz[q]);
+            otx[q] = k.t[0]; oty[q] = k.t[1]; otz[q] = k.t[2] + 1e-6f;
+        } else {
+            orx[q] = ory[q] = orz[q] = otx[q] = oty[q] = 0.f; otz[q] = 1.f;
+        }
+    }
     const float* dp = depth + (size_t)b * D * P + pofs;
     // channel-blocked volume [B][C/8][D][h][w][8]: one 8-channel slab of a row is contiguous (what conv0's TMA wants)
     T* outp = volume + (((size_t)b * LPP + chunk) * D * P + pofs) * 8;
+    const T* rbase = ref_fea + ((size_t)b * P + pofs) * C + chunk * 8;
+    const T* sbase = src_fea + (size_t)b * P * C + chunk * 8;
+    const size_t vstride = (size_t)B * P * C;
 
     for (int d = 0; d < D; ++d) {
-        float dep = __ldg(dp + (size_t)d * P);
-        float acc[8];
+        const float dep = __ldg(dp + (size_t)d * P);
+        float2 acc[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int v = 0; v < kMaxViews; ++v) {
-            if (v < V) {
-                WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
-                float rx, ry, rz, u, vv;
-                pixel_ray(k, (float)x, (float)y, rx, ry, rz);
-                project_fast(k, rx, ry, rz, dep, u, vv);
-                Taps t = make_taps(u, vv, w, h);
-                float wv[8], ref[8];
-                gather8<T>(src_fea + ((size_t)v * B + b) * P * C + chunk * 8, w, h, C, t, wv);
-                Vec8<T>::load(ref_fea + (((size_t)v * B + b) * P + pofs) * C + chunk * 8, ref);
+        for (int q = 0; q < OWN; ++q) {
+            if (q * LPP < V) {   // warp-uniform
+                Foot mine;
+                {
+                    float px = orx[q] * dep + otx[q];
+                    float py = ory[q] * dep + oty[q];
+                    float iz = __frcp_rn(orz[q] * dep + otz[q]);
+                    mine = make_foot(px * iz, py * iz, w, h);
+                }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += (ref[i] * wv[i]) * vw[v];
+                for (int j = 0; j < LPP; ++j) {
+                    const int v = q * LPP + j;
+                    if (v < VMAX && v < V) {   // warp-uniform
+                        Foot f = LPP == 1 ? mine : shfl_foot(mine, lane_base + j);
+                        float2 wv[4], ref[4];
+                        gather8<T, C>(sbase + (size_t)v * vstride, w, f, wv);
+                        Pix8<T>::load(rbase + (size_t)v * vstride, ref);   // L1-resident after the first plane
+                        const float2 vv2 = make_float2(vw[v], vw[v]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i] = ffma2(fmul2(ref[i], wv[i]), vv2, acc[i]);
+                    }
+                }
             }
         }
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] *= inv;
-        Vec8<T>::store(outp + (size_t)d * P * 8, acc);
+        for (int i = 0; i < 4; ++i) { o[2 * i] = acc[i].x * inv; o[2 * i + 1] = acc[i].y * inv; }
+        if (live) Vec8<T>::store(outp + (size_t)d * P * 8, o);
     }
 }
 
@@ -176,10 +308,14 @@ int launch_aggregate(const void* ref, const void* src, const float* coef, const 
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
     T* o = (T*)volume;
+#define CDS_AGG(c)                                                                                              \
+    if (V <= 4) aggregate_kernel<T, c, 4><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);     \
+    else aggregate_kernel<T, c, kMaxViews><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);     \
+    break;
     switch (C) {
-        case 8: aggregate_kernel<T, 8><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); break;
-        case 16: aggregate_kernel<T, 16><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); break;
-        case 32: aggregate_kernel<T, 32><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); break;
+        case 8: CDS_AGG(8)
+        case 16: CDS_AGG(16)
+        case 32: CDS_AGG(32)
         default: cds_set_error("cds_costvol_aggregate: C must be 8, 16 or 32 (got %d)", C); return CDS_EUNSUPPORTED;
     }
     return cds_check_launch("cds_costvol_aggregate");
@@ -194,6 +330,7 @@ int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* c
     CDS_REQUIRE(ref_fea && src_fea && coef && depth && entropy, CDS_EARG, "cds_costvol_entropy: null pointer");
     CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
                 "cds_costvol_entropy: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31), CDS_ESHAPE, "cds_costvol_entropy: feature map too large for 32-bit offsets");
     if (dtype == CDS_F16) return launch_entropy<__half>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     if (dtype == CDS_F32) return launch_entropy<float>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     cds_set_error("cds_costvol_entropy: unknown dtype %d", dtype);
@@ -206,6 +343,7 @@ int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float*
     CDS_REQUIRE(ref_fea && src_fea && coef && depth && vis && volume, CDS_EARG, "cds_costvol_aggregate: null pointer");
     CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
                 "cds_costvol_aggregate: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31), CDS_ESHAPE, "cds_costvol_aggregate: feature map too large for 32-bit offsets");
     if (dtype == CDS_F16) return launch_aggregate<__half>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     if (dtype == CDS_F32) return launch_aggregate<float>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     cds_set_error("cds_costvol_aggregate: unknown dtype %d", dtype);
