@@ -18,6 +18,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
     int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+// same, allocating in L1 (gathers whose neighbouring taps / rows re-read the same lines)
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, bool valid) {
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }

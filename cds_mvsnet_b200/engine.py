@@ -188,6 +188,7 @@ class Regulariser:
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
         self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV3D", "1") != "0"
+        self.use_gtc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_GATHER", "1") != "0"
         self.tag = "cr"
 
     def _conv(self, name, x, B, D, H, W, stride, out):
@@ -199,6 +200,10 @@ class Regulariser:
                 and _lib.LIB.load().cds_conv3d_k3_tc_supported(l.cin, l.cout, D, H, W, stride)):
             call("cds_conv3d_k3_tc", ptr(x), ptr(l.extra["tc"]), ptr(l.bias), B, l.cin, l.cout, D, H, W, 1, ptr(out))
             return
+        if (self.use_gtc and self.storage == torch.float16 and "gtc" in l.extra
+                and _lib.LIB.load().cds_conv3d_k3_gtc_supported(l.cin, l.cout, stride)):
+            call("cds_conv3d_k3_gtc", ptr(x), ptr(l.extra["gtc"]), ptr(l.bias), B, l.cin, l.cout, D, H, W, stride, 1, ptr(out))
+            return
         call("cds_conv3d_k3", ptr(x), ptr(l.w), ptr(l.bias), B, l.cin, l.cout, D, H, W, stride, 1, self.dt, ptr(out))
 
     def _deconv(self, name, x, skip, B, D, H, W, out):
@@ -209,6 +214,10 @@ class Regulariser:
         if (self.use_tc and self.storage == torch.float16 and "tc" in l.extra
                 and _lib.LIB.load().cds_deconv3d_k3s2_tc_supported(l.cin, l.cout, D, H, W)):
             call("cds_deconv3d_k3s2_tc", ptr(x), ptr(l.extra["tc"]), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, ptr(out))
+            return
+        if (self.use_gtc and self.storage == torch.float16 and "gtc" in l.extra
+                and _lib.LIB.load().cds_deconv3d_k3s2_gtc_supported(l.cin, l.cout)):
+            call("cds_deconv3d_k3s2_gtc", ptr(x), ptr(l.extra["gtc"]), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, ptr(out))
             return
         call("cds_deconv3d_k3s2", ptr(x), ptr(l.w), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, self.dt, ptr(out))
 

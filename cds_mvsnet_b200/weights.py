@@ -262,6 +262,58 @@ def pack_deconv3d_tc(l: Conv3dWeights) -> torch.Tensor:
     return img.to(dtype=torch.float16, device=l.w.device).contiguous()
 
 
+def _hi_lo_columns(blk: torch.Tensor) -> torch.Tensor:
+    """[8 k, Cout] fp64 -> [8 k, 2*Cout]: fp16-rounded weights, then their rounding residual (summed in the epilogue)."""
+    hi = blk.to(torch.float16).to(torch.float64)
+    return torch.cat((hi, blk - hi), dim=1)
+
+
+def pack_conv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
+    """fp16 B-operand image for csrc/conv3d_gtc.cu (Conv3d stride 1|2): [mma][k-chunk 2][N/8][8 n][8 k], N = 2*Cout
+    (weights + residual columns).  Slab order as pack_conv3d_tc: Cin == 8: [tap0, zero, tap1, ..., tap26]; Cin > 8:
+    tap-major / channel-chunk minor; an MMA takes two consecutive slabs."""
+    ci, co = l.cin, l.cout
+    c8, N = ci // 8, 2 * l.cout
+    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout]
+    slabs = [(0, 0), None] + [(t, 0) for t in range(1, 27)] if c8 == 1 else [(t, c) for t in range(27) for c in range(c8)]
+    assert len(slabs) % 2 == 0
+    img = torch.zeros(len(slabs) // 2, 2, N // 8, 8, 8, dtype=torch.float64)
+    for s, sl in enumerate(slabs):
+        if sl is None:
+            continue
+        t, c = sl
+        img[s // 2, s % 2] = _hi_lo_columns(w[t, c * 8:(c + 1) * 8, :]).t().reshape(N // 8, 8, 8)
+    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+
+
+def pack_deconv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
+    """fp16 B-operand image for the transposed conv in csrc/conv3d_gtc.cu: the 8 output-parity classes (pd,ph,pw) one after
+    the other, each a dense conv over its input neighbours (sd,sh,sw) in {0..pd}x{0..ph}x{0..pw}; per axis parity 0 takes
+    tap k=1 (neighbour 0), parity 1 takes k=2 from neighbour 0 and k=0 from neighbour 1 (out[2i-1+k] += in[i] w[k]).
+    Layout per class [tap][chunk pair][k-chunk 2][N/8][8 n][8 k], N = 2*Cout (weights + residual columns)."""
+    ci, co = l.cin, l.cout
+    c8, N = ci // 8, 2 * l.cout
+    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout] folded
+
+    def tap(par, off):
+        return 1 if par == 0 else (2 if off == 0 else 0)
+
+    mmas = []
+    for cls in range(8):
+        pd, ph, pw = cls >> 2, (cls >> 1) & 1, cls & 1
+        for sd in range(pd + 1):
+            for sh in range(ph + 1):
+                for sw in range(pw + 1):
+                    wt = w[(tap(pd, sd) * 3 + tap(ph, sh)) * 3 + tap(pw, sw)]           # [Cin, Cout]
+                    for q in range(c8 // 2):
+                        m = torch.zeros(2, N // 8, 8, 8, dtype=torch.float64)
+                        for kc in range(2):
+                            c = 2 * q + kc
+                            m[kc] = _hi_lo_columns(wt[c * 8:(c + 1) * 8]).t().reshape(N // 8, 8, 8)
+                        mmas.append(m)
+    return torch.stack(mmas).to(dtype=torch.float16, device=l.w.device).contiguous()
+
+
 @dataclass
 class CostRegWeights:
     layers: dict          # name -> Conv3dWeights
@@ -276,6 +328,10 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
         layers[n].extra["tc"] = pack_conv3d_tc(layers[n])
     for n in ("conv9", "conv11"):
         layers[n].extra["tc"] = pack_deconv3d_tc(layers[n])
+    for n in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"):   # gather-form kernel (stride 2, small deep layers)
+        layers[n].extra["gtc"] = pack_conv3d_gtc(layers[n])
+    for n in ("conv7", "conv9"):
+        layers[n].extra["gtc"] = pack_deconv3d_gtc(layers[n])
     p = sd[prefix + ".prob.weight"].double()                        # [1,8,3,3,3]
     prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(dtype=torch.float32, device=device).contiguous()
     cw = CostRegWeights(layers, prob)

@@ -125,6 +125,18 @@ int cds_deconv3d_k3s2_tc_supported(int Cin, int Cout, int D, int H, int W);
 int cds_deconv3d_k3s2_tc_weight_halfs(int Cin, int Cout);
 int cds_deconv3d_k3s2_tc(const void* in, const void* wgt_packed, const float* bias, const void* skip, int B, int Cin, int Cout,
                          int D, int H, int W, void* out, cudaStream_t stream);
+/* Gather-form tensor-core Conv3d / Deconv3d blocks (csrc/conv3d_gtc.cu): same semantics as cds_conv3d_k3 (stride 1|2) and
+ * cds_deconv3d_k3s2, fp16 storage, any D/H/W; operands are gathered voxel by voxel (cp.async) so stride 2 and small deep
+ * volumes are covered.  wgt_packed: fp16 image [mma][k-chunk 2][2*Cout/8][8 n][8 k] whose columns [Cout, 2*Cout) hold the
+ * fp16 rounding residual of the folded weights (host: weights.py pack_conv3d_gtc / pack_deconv3d_gtc). */
+int cds_conv3d_k3_gtc_supported(int Cin, int Cout, int stride);
+int cds_conv3d_k3_gtc_weight_halfs(int Cin, int Cout);
+int cds_conv3d_k3_gtc(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H, int W,
+                      int stride, int relu, void* out, cudaStream_t stream);
+int cds_deconv3d_k3s2_gtc_supported(int Cin, int Cout);
+int cds_deconv3d_k3s2_gtc_weight_halfs(int Cin, int Cout);
+int cds_deconv3d_k3s2_gtc(const void* in, const void* wgt_packed, const float* bias, const void* skip, int B, int Cin, int Cout,
+                          int D, int H, int W, void* out, cudaStream_t stream);
 /* prob head: plain Conv3d(8,1,3,p=1,bias=False) (models/module.py:303) -> fp32 logits [B,D,H,W]. */
 int cds_prob_conv(const void* in, const float* wgt, int B, int Cin, int D, int H, int W, int dtype, float* logits,
                   cudaStream_t stream);

@@ -397,6 +397,57 @@ def test_deconv3d_tcgen05_vs_torch(cin, cout, shape):
     close(from_blocked(out.float().cpu()), ref, 8e-3, 2e-3)
 
 
+@pytest.mark.parametrize("cin,cout,stride", [(8, 16, 2), (16, 16, 1), (16, 32, 2), (32, 32, 1), (32, 64, 2), (64, 64, 1),
+                                             (8, 16, 1), (32, 32, 2)])
+@pytest.mark.parametrize("shape", [(5, 9, 11), (8, 16, 24), (2, 3, 133), (6, 37, 50)])
+def test_conv3d_gather_tcgen05_vs_torch(cin, cout, stride, shape):
+    """Gather-form tcgen05 Conv3d block (stride 1|2, weights fed as fp16 value + residual columns) against the published
+    operator on fp16-rounded activations and UNROUNDED weights; odd sizes exercise ceil(n/2), borders and partial tiles."""
+    D, H, Wd = shape
+    torch.manual_seed(cin * 100 + cout + Wd + stride)
+    x = torch.randn(2, cin, D, H, Wd).half().float()
+    w = torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5
+    b = torch.randn(cout)
+    ref = torch.relu(torch.nn.functional.conv3d(x, w, b, stride=stride, padding=1))
+    lw = W.Conv3dWeights(cin, cout, w.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous(), b)
+    packed = cu(W.pack_conv3d_gtc(lw))
+    lib = _lib.LIB.load()
+    assert lib.cds_conv3d_k3_gtc_supported(cin, cout, stride) == 1
+    assert packed.numel() == lib.cds_conv3d_k3_gtc_weight_halfs(cin, cout)
+    xc, bc = cu(to_blocked(x)).half(), cu(b)
+    out = torch.full(tuple(to_blocked(ref).shape), float("nan"), device=DEV, dtype=torch.float16)
+    call("cds_conv3d_k3_gtc", ptr(xc), ptr(packed), ptr(bc), 2, cin, cout, D, H, Wd, stride, 1, ptr(out))
+    torch.cuda.synchronize()
+    # output is rounded to fp16: half an ulp at |y| <= 8 is 4e-3
+    close(from_blocked(out.float().cpu()), ref, 6e-3, 2e-3)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 32), (32, 16)])
+@pytest.mark.parametrize("shape", [(3, 5, 7), (2, 4, 130), (6, 37, 50)])
+@pytest.mark.parametrize("with_skip", [True, False])
+def test_deconv3d_gather_tcgen05_vs_torch(cin, cout, shape, with_skip):
+    """Gather-form tcgen05 transposed conv (one output-parity class per blockIdx.y) against the published operator."""
+    D, H, Wd = shape
+    torch.manual_seed(cin + Wd)
+    x = torch.randn(2, cin, D, H, Wd).half().float()
+    w = torch.randn(cin, cout, 3, 3, 3) / (8 * cin) ** 0.5
+    b = torch.randn(cout)
+    skip = torch.randn(2, cout, 2 * D, 2 * H, 2 * Wd).half().float()
+    ref = torch.relu(torch.nn.functional.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1))
+    if with_skip:
+        ref = skip + ref
+    lw = W.Conv3dWeights(cin, cout, w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout).contiguous(), b)
+    packed = cu(W.pack_deconv3d_gtc(lw))
+    lib = _lib.LIB.load()
+    assert lib.cds_deconv3d_k3s2_gtc_supported(cin, cout) == 1
+    assert packed.numel() == lib.cds_deconv3d_k3s2_gtc_weight_halfs(cin, cout)
+    xc, sc, bc = cu(to_blocked(x)).half(), cu(to_blocked(skip)).half(), cu(b)
+    out = torch.full_like(sc, float("nan"))
+    call("cds_deconv3d_k3s2_gtc", ptr(xc), ptr(packed), ptr(bc), ptr(sc) if with_skip else None, 2, cin, cout, D, H, Wd, ptr(out))
+    torch.cuda.synchronize()
+    close(from_blocked(out.float().cpu()), ref, 8e-3, 2e-3)
+
+
 @pytest.mark.parametrize("st", [0, 1, 2])
 @pytest.mark.parametrize("hw", [(37, 200), (8, 128), (21, 300), (32, 40), (19, 100)])
 def test_visnet_tcgen05_vs_oracle(pretrained_sd, st, hw):
