@@ -1,0 +1,362 @@
+// Full-resolution regulariser convolutions (conv0: C -> 8, and the prob head 8 -> 1) as a PERSISTENT, d-rolling
+// tcgen05 pipeline with the kw taps folded into the GEMM's N dimension.
+//
+// Reference semantics: models/module.py:80-122 (Conv3d block k3 p1 s1 -> BN -> ReLU, wired at :305) and :303
+// (prob = plain Conv3d(8, 1, 3, padding=1, bias=False)).
+//
+// Why another kernel: with Cout = 8 a tap GEMM is bound by the tensor core re-reading its 4 KB A operand from shared
+// memory for every MMA (>= 32 cycles whatever N is), and conv3d_tc.cu additionally re-stages a 3-plane window per
+// tile and runs load -> MMA -> epilogue back to back.  Here
+//   * M = 128 consecutive voxels of a row (window origin x0-1), K = 9 (kd,kh) taps x Cin, and the three kw taps sit
+//     side by side in N: D[r][kw][co] = sum_{kd,kh,ci} in[r][kd,kh,ci] w[kd,kh,kw,ci,co]; the epilogue forms
+//     out[r] = D[r-1][0] + D[r][1] + D[r+1][2] with two warp shuffles per channel (+ a 2-value exchange through
+//     shared memory at the warp seams).  3x fewer MMAs / A-operand reads than one MMA per (kd,kh,kw) tap.
+//   * a CTA owns a (TY rows x 126 voxels) column of the volume and ROLLS along d: each input plane is fetched by TMA
+//     exactly once per column into a 4-slot ring ([slab][TY+2 rows][128 voxels][8 ch], zero-filled outside the volume
+//     = the conv padding), so the (kd) reuse never touches L2 again and loads overlap the MMAs of the previous plane;
+//   * warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (accumulators: a ring of 4 row units in TMEM),
+//     warps 2..5 epilogue (tcgen05.ld -> kw fold -> bias/ReLU -> fp16 NDHWC store, or fp32 logits for the prob head);
+//   * CTAs are persistent over columns (grid = min(columns, resident CTAs)), so barrier / TMEM / weight setup is paid once.
+// N columns: per kw, Cout columns of fp16-rounded weights then Cout columns of their rounding residual (summed in the
+// epilogue: effectively fp32-accurate weights at no extra A traffic); Cout = 8 -> N = 48, prob head -> N = 6 (16).
+// Weights (host: weights.py pack_conv3d_roll): [kd][mma][k-chunk 2][N/8][8 n][8 k] fp16; per kd the K slabs are
+// Cin = 8: [kh0, kh1], [kh2, zero]; Cin > 8: kh-major, channel-chunk pairs.
+#include <algorithm>
+#include <utility>
+
+#include "cds_common.cuh"
+#include "tc_common.cuh"
+#include "tma_host.h"
+
+namespace {
+
+constexpr int TX = 128;
+constexpr int TXO = TX - 2;
+constexpr int ROW_BYTES = TX * 16;
+constexpr int NR = 4;     // input-plane ring slots
+constexpr int NACC = 4;   // accumulator ring (row units)
+
+template <int CIN, int COUT, int TY_>
+struct RollCfg {
+    static constexpr int TY = TY_;
+    static constexpr int C8 = CIN / 8;
+    static constexpr int CW = 2 * COUT;                       // columns per kw: weights + residual
+    static constexpr int NCOL = 3 * CW;
+    static constexpr int NPAD = (NCOL + 15) / 16 * 16;
+    static constexpr int MMA_KD = C8 == 1 ? 2 : 3 * C8 / 2;   // MMAs per input plane
+    static constexpr int NMMA = 3 * MMA_KD;
+    static constexpr int ROWS = TY + 2;
+    static constexpr uint32_t SLAB = ROWS * ROW_BYTES;
+    static constexpr uint32_t SLOT = C8 * SLAB;
+    static constexpr uint32_t B_MMA = 2 * NPAD * 16;
+    static constexpr uint32_t B_BYTES = NMMA * B_MMA;
+    static constexpr uint32_t XCH_FLOATS = 2 * TY * 4 * 2 * COUT;   // [plane parity][unit][warp][up|down][co]
+    static constexpr uint32_t TMEM_COLS = NACC * NPAD <= 32 ? 32 : (NACC * NPAD <= 64 ? 64 : (NACC * NPAD <= 128 ? 128 : 256));
+    static constexpr int NBAR = 2 * NR + 2 * NACC + 1;
+    static constexpr size_t SMEM = (size_t)NR * SLOT + B_BYTES + XCH_FLOATS * 4 + NBAR * 8 + 16;
+};
+
+struct RollParams {
+    const __half* wgt;
+    const float* bias;   // [COUT] (conv0) or null (prob head)
+    __half* out;         // conv0: [D, H, W, 8] (one batch item)
+    float* logits;       // prob head: fp32 [D, H, W]
+    int D, H, W, relu;
+    int xt, yt;          // columns along x and y
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// all MMAs of one row unit: 3 planes x MMA_KD, every offset a compile-time constant
+template <class C, int KD, int J>
+__device__ __forceinline__ void issue_mma(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, uint32_t acc, bool elected) {
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t idesc = tc::instr_desc_f16(128, C::NPAD);
+    constexpr uint32_t off0 = C::C8 == 1 ? (uint32_t)(J == 0 ? 0 : 2 * ROW_BYTES)
+                                         : (uint32_t)((2 * (J % (C::C8 / 2))) * C::SLAB + (J / (C::C8 / 2)) * ROW_BYTES);
+    constexpr uint32_t lbo = C::C8 == 1 ? (uint32_t)(J == 0 ? ROW_BYTES : 16) : C::SLAB;
+    constexpr uint32_t a_const = (off0 >> 4) | ((lbo >> 4) << 16);
+    constexpr uint32_t b_const = (((uint32_t)(KD * C::MMA_KD + J) * C::B_MMA) >> 4) | (((uint32_t)(C::NPAD * 16) >> 4) << 16);
+    const uint64_t da = ((uint64_t)desc_hi << 32) | (a16[KD] + urow16 + a_const);
+    const uint64_t db = ((uint64_t)desc_hi << 32) | (b16 + b_const);
+    if (elected) tc::mma_f16(acc, da, db, idesc, !(KD == 0 && J == 0));
+}
+template <class C, int KD, int... J>
+__device__ __forceinline__ void issue_plane(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, uint32_t acc, bool elected,
+                                            std::integer_sequence<int, J...>) {
+    (issue_mma<C, KD, J>(a16, urow16, b16, acc, elected), ...);
+}
+template <class C>
+__device__ __forceinline__ void issue_unit(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, uint32_t acc, bool elected) {
+    issue_plane<C, 0>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
+    issue_plane<C, 1>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
+    issue_plane<C, 2>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
+}
+
+// tmap: 4-D view (2W x 8-byte elements, H, D, C/8) of one batch item's channel-blocked input, box (256, TY+2, 1, 1)
+template <int CIN, int COUT, int TY>
+__global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmap, const RollParams p) {
+    using C = RollCfg<CIN, COUT, TY>;
+    constexpr int C8 = C::C8, NPAD = C::NPAD;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + NR * C::SLOT;
+    float* xch = reinterpret_cast<float*>(sB + C::B_BYTES);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(xch + C::XCH_FLOATS);   // [NR]  plane landed
+    uint64_t* bar_empty = bar_full + NR;                                     // [NR]  plane no longer needed
+    uint64_t* acc_full = bar_empty + NR;                                     // [NACC] row unit accumulated
+    uint64_t* acc_empty = acc_full + NACC;                                   // [NACC] row unit drained (4 warps)
+    uint64_t* bar_b = acc_empty + NACC;                                      // weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+    const int ntiles = p.xt * p.yt;
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (threadIdx.x == 32) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) { tc::mbar_init(bar_full + i, 1); tc::mbar_init(bar_empty + i, 1); }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
+        tc::mbar_init(bar_b, 1);
+        tc::mbar_fence_init();
+        tc::tma_prefetch_desc(&tmap);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer: weights once, then every input plane of every column exactly once -------------------------
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(bar_b, C::B_BYTES);
+            tc::bulk_copy_g2s(sB_u, p.wgt, C::B_BYTES, bar_b);
+            uint32_t pc = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int x0 = max(0, min((tile % p.xt) * TXO, p.W - TXO));
+                const int y0 = (tile / p.xt) * TY;
+                for (int pl = -1; pl <= p.D; ++pl, ++pc) {
+                    const uint32_t slot = pc % NR;
+                    if (pc >= NR) tc::mbar_wait(bar_empty + slot, ((pc / NR) - 1) & 1);
+                    tc::mbar_expect_tx(bar_full + slot, C::SLOT);
+#pragma unroll
+                    for (int c8 = 0; c8 < C8; ++c8)
+                        tc::tma_load_4d(sA_u + slot * C::SLOT + c8 * C::SLAB, &tmap, bar_full + slot, 2 * (x0 - 1), y0 - 1, pl, c8);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer (warp converged, one elected lane issues) -----------------------------------------------------------
+        tc::mbar_wait(bar_b, 0);
+        tc::tc_fence_after();
+        const bool elected = tc::elect_one();
+        const uint32_t tmem_u = tc::uniform(tmem);
+        const uint32_t b16 = sB_u >> 4;
+        uint32_t pc_base = 0, uc = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int d = 0; d < p.D; ++d) {
+                // output plane d reads input planes d-1, d, d+1 = plane counters pc_base + d .. + 2
+                if (d == 0) {
+                    tc::mbar_wait(bar_full + pc_base % NR, (pc_base / NR) & 1);
+                    tc::mbar_wait(bar_full + (pc_base + 1) % NR, ((pc_base + 1) / NR) & 1);
+                }
+                const uint32_t pc2 = pc_base + d + 2;
+                tc::mbar_wait(bar_full + pc2 % NR, (pc2 / NR) & 1);
+                tc::tc_fence_after();
+                uint32_t a16[3];
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd) a16[kd] = (sA_u + ((pc_base + d + kd) % NR) * C::SLOT) >> 4;
+#pragma unroll 1
+                for (uint32_t u = 0; u < (uint32_t)TY; ++u, ++uc) {
+                    const uint32_t s = uc % NACC;
+                    tc::mbar_wait(acc_empty + s, ((uc / NACC) & 1) ^ 1);   // epilogue has drained this accumulator
+                    tc::tc_fence_after();
+                    issue_unit<C>(a16, (u * ROW_BYTES) >> 4, b16, tmem_u + s * NPAD, elected);
+                    if (elected) tc::mma_commit(acc_full + s);
+                    __syncwarp();
+                }
+                // plane d-1 is done with; the column's last output also retires planes D-1 and D
+                if (elected) tc::mma_commit(bar_empty + (pc_base + d) % NR);
+                if (d == p.D - 1 && elected) {
+                    tc::mma_commit(bar_empty + (pc_base + d + 1) % NR);
+                    tc::mma_commit(bar_empty + (pc_base + d + 2) % NR);
+                }
+                __syncwarp();
+            }
+            pc_base += p.D + 2;
+        }
+        // the last planes' release arrivals land in this CTA's shared memory: let them before the CTA may exit
+        if (pc_base > 0) tc::mbar_wait(bar_empty + (pc_base - 1) % NR, ((pc_base - 1) / NR) & 1);
+    } else {
+        // ---- epilogue warps: fold kw, bias / ReLU, store -----------------------------------------------------------------------
+        const int q = warp & 3;              // TMEM lane group this warp may read
+        const int r = q * 32 + lane;         // MMA row = window voxel r (x = x0 - 1 + r); rows 1..126 are outputs
+        float bias[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+        uint32_t uc = 0, planes = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int x0 = max(0, min((tile % p.xt) * TXO, p.W - TXO));
+            const int y0 = (tile / p.xt) * TY;
+            const int x = x0 - 1 + r;
+            const bool col_ok = r >= 1 && r <= TXO && x < p.W;
+#pragma unroll 1
+            for (int d = 0; d < p.D; ++d, ++planes) {
+                float* xb = xch + (planes & 1) * (TY * 4 * 2 * COUT);
+                float part[TY][COUT];
+#pragma unroll
+                for (int u = 0; u < TY; ++u, ++uc) {
+                    const uint32_t s = uc % NACC;
+                    tc::mbar_wait(acc_full + s, (uc / NACC) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + s * NPAD;
+                    float e0[COUT], e1[COUT], e2[COUT];
+                    if constexpr (COUT == 8) {
+                        uint32_t v[6][8];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) tc::tmem_ld8_nowait(taddr + i * 8, v[i]);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            e0[c] = __uint_as_float(v[0][c]) + __uint_as_float(v[1][c]);
+                            e1[c] = __uint_as_float(v[2][c]) + __uint_as_float(v[3][c]);
+                            e2[c] = __uint_as_float(v[4][c]) + __uint_as_float(v[5][c]);
+                        }
+                    } else {
+                        uint32_t v[8];
+                        tc::tmem_ld8_nowait(taddr, v);
+                        tc::tmem_ld_wait();
+                        e0[0] = __uint_as_float(v[0]) + __uint_as_float(v[1]);
+                        e1[0] = __uint_as_float(v[2]) + __uint_as_float(v[3]);
+                        e2[0] = __uint_as_float(v[4]) + __uint_as_float(v[5]);
+                    }
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + s);   // accumulator read: the MMA warp may refill it
+#pragma unroll
+                    for (int c = 0; c < COUT; ++c) {
+                        const float up = __shfl_up_sync(0xffffffffu, e0[c], 1);
+                        const float dn = __shfl_down_sync(0xffffffffu, e2[c], 1);
+                        part[u][c] = e1[c] + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+                    }
+                    // warp seams: row 32q+31's kw=0 term belongs to row 32(q+1); row 32q's kw=2 term to row 32q-1
+                    if (lane == 31) {
+#pragma unroll
+                        for (int c = 0; c < COUT; ++c) xb[((u * 4 + q) * 2 + 0) * COUT + c] = e0[c];
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int c = 0; c < COUT; ++c) xb[((u * 4 + q) * 2 + 1) * COUT + c] = e2[c];
+                    }
+                }
+                epilogue_barrier();
+#pragma unroll
+                for (int u = 0; u < TY; ++u) {
+                    if (lane == 0 && q > 0) {
+#pragma unroll
+                        for (int c = 0; c < COUT; ++c) part[u][c] += xb[((u * 4 + q - 1) * 2 + 0) * COUT + c];
+                    }
+                    if (lane == 31 && q < 3) {
+#pragma unroll
+                        for (int c = 0; c < COUT; ++c) part[u][c] += xb[((u * 4 + q + 1) * 2 + 1) * COUT + c];
+                    }
+                    const int y = y0 + u;
+                    if (col_ok && y < p.H) {
+                        const size_t vox = ((size_t)d * p.H + y) * p.W + x;
+                        if constexpr (COUT == 8) {
+                            float o[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float t = part[u][c] + bias[c];
+                                o[c] = p.relu ? fmaxf(t, 0.f) : t;
+                            }
+                            Vec8<__half>::store(p.out + vox * 8, o);
+                        } else {
+                            p.logits[vox] = part[u][0];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int CIN, int COUT, int TY>
+int launch_roll(const void* in, const void* wgt, const float* bias, int B, int D, int H, int W, int relu, void* out, cudaStream_t st) {
+    using C = RollCfg<CIN, COUT, TY>;
+    static_assert(C::SMEM <= 227 * 1024, "rolling-conv ring does not fit in shared memory");
+    auto kern = conv3d_roll_kernel<CIN, COUT, TY>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) { cds_set_error("cds_conv3d_k3_roll: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    RollParams p;
+    p.wgt = (const __half*)wgt;
+    p.bias = bias;
+    p.D = D; p.H = H; p.W = W; p.relu = relu;
+    p.xt = cds_div_up(W, TXO);
+    p.yt = cds_div_up(H, TY);
+    const int per_sm = (int)((227 * 1024) / C::SMEM) >= 2 && 2 * C::TMEM_COLS <= 512 ? 2 : 1;
+    const int grid = std::min(p.xt * p.yt, per_sm * sm_count());
+    for (int b = 0; b < B; ++b) {
+        const __half* base = (const __half*)in + (size_t)b * D * H * W * CIN;
+        CUtensorMap tmap;
+        const uint64_t dims[4] = {2 * (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)C::C8};
+        const uint64_t strides[4] = {0, (uint64_t)W * 16, (uint64_t)H * W * 16, (uint64_t)D * H * W * 16};
+        const uint32_t box[4] = {2 * TX, TY + 2, 1, 1};
+        if (!tma::make_u64(&tmap, base, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
+        p.out = COUT == 1 ? nullptr : (__half*)out + (size_t)b * D * H * W * COUT;
+        p.logits = COUT == 1 ? (float*)out + (size_t)b * D * H * W : nullptr;
+        kern<<<grid, 192, C::SMEM, st>>>(tmap, p);
+    }
+    return cds_check_launch("cds_conv3d_k3_roll");
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 when the rolling kernel covers the layer: stride-1 k3 conv with Cout = 8 (conv0) or the 8 -> 1 prob head
+int cds_conv3d_k3_roll_supported(int Cin, int Cout, int D, int H, int W) {
+    if (W < 8 || D < 1 || H < 1) return 0;
+    return (Cout == 8 && (Cin == 8 || Cin == 16 || Cin == 32)) || (Cin == 8 && Cout == 1);
+}
+
+int cds_conv3d_k3_roll_weight_halfs(int Cin, int Cout) {
+    const int c8 = Cin / 8, npad = (6 * Cout + 15) / 16 * 16;
+    return 3 * (c8 == 1 ? 2 : 3 * c8 / 2) * 2 * npad * 8;
+}
+
+// Cout == 8: out [B, D, H, W, 8] fp16 (bias + optional ReLU); Cout == 1: out = fp32 logits [B, D, H, W] (bias may be null)
+int cds_conv3d_k3_roll(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H, int W,
+                       int relu, void* out, cudaStream_t stream) {
+    CDS_REQUIRE(in && wgt_packed && out && (bias || Cout == 1), CDS_EARG, "cds_conv3d_k3_roll: null pointer");
+    CDS_REQUIRE(cds_conv3d_k3_roll_supported(Cin, Cout, D, H, W), CDS_EUNSUPPORTED,
+                "cds_conv3d_k3_roll: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d", Cin, Cout, D, H, W);
+    if (Cout == 1) return launch_roll<8, 1, 8>(in, wgt_packed, nullptr, B, D, H, W, 0, out, stream);
+    if (Cin == 8) return launch_roll<8, 8, 8>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
+    if (Cin == 16) return launch_roll<16, 8, 8>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
+    return launch_roll<32, 8, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
+}
+
+}  // extern "C"

@@ -189,6 +189,7 @@ class Regulariser:
         self.dt = _lib.dtype_code(storage)
         self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV3D", "1") != "0"
         self.use_gtc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_GATHER", "1") != "0"
+        self.use_roll = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_ROLL", "1") != "0"
         self.tag = "cr"
 
     def _conv(self, name, x, B, D, H, W, stride, out):
@@ -196,6 +197,10 @@ class Regulariser:
         e = _esize(self.storage)
         m_in, m_out = B * D * H * W, out.numel() // l.cout
         _lib.set_tag(f"{self.tag}.{name}", (2.0 * 27 * l.cin * l.cout * m_out, float((l.cin * m_in + l.cout * m_out) * e)))
+        if (self.use_roll and stride == 1 and self.storage == torch.float16 and "roll" in l.extra
+                and _lib.LIB.load().cds_conv3d_k3_roll_supported(l.cin, l.cout, D, H, W)):
+            call("cds_conv3d_k3_roll", ptr(x), ptr(l.extra["roll"]), ptr(l.bias), B, l.cin, l.cout, D, H, W, 1, ptr(out))
+            return
         if (self.use_tc and stride == 1 and self.storage == torch.float16 and "tc" in l.extra
                 and _lib.LIB.load().cds_conv3d_k3_tc_supported(l.cin, l.cout, D, H, W, stride)):
             call("cds_conv3d_k3_tc", ptr(x), ptr(l.extra["tc"]), ptr(l.bias), B, l.cin, l.cout, D, H, W, 1, ptr(out))
@@ -253,7 +258,11 @@ class Regulariser:
         self._deconv("conv9", u7, c2, B, D4, H4, W4, u9)
         self._deconv("conv11", u9, c0, B, D2, H2, W2, u11)
         m = B * D * H * W
-        if (self.use_tc and st == torch.float16 and self.cw.prob_tc is not None
+        if (self.use_roll and st == torch.float16 and self.cw.prob_roll is not None
+                and _lib.LIB.load().cds_conv3d_k3_roll_supported(b, 1, D, H, W)):
+            kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_conv3d_k3_roll", ptr(u11), ptr(self.cw.prob_roll), None,
+                  B, b, 1, D, H, W, 0, ptr(logits))
+        elif (self.use_tc and st == torch.float16 and self.cw.prob_tc is not None
                 and _lib.LIB.load().cds_conv3d_k3_tc_supported(b, 1, D, H, W, 1)):
             kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_conv3d_k3_tc", ptr(u11), ptr(self.cw.prob_tc), None,
                   B, b, 1, D, H, W, 0, ptr(logits))

@@ -286,6 +286,29 @@ def pack_conv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
     return img.to(dtype=torch.float16, device=l.w.device).contiguous()
 
 
+def pack_conv3d_roll(l: Conv3dWeights) -> torch.Tensor:
+    """fp16 B-operand image for csrc/conv3d_roll.cu (Conv3d k3 s1, Cout 8 or 1, kw folded into N):
+    [kd][mma][k-chunk 2][N/8][8 n][8 k]; column n = kw*2*Cout + j holds the fp16-rounded weight (j < Cout) or its rounding
+    residual (j >= Cout).  K slabs per kd: Cin == 8: [kh0, kh1], [kh2, zero]; Cin > 8: kh-major, channel-chunk pairs."""
+    ci, co = l.cin, l.cout
+    c8, cw = ci // 8, 2 * l.cout
+    npad = (3 * cw + 15) // 16 * 16
+    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout]
+    slabs = [(0, 0), (1, 0), (2, 0), None] if c8 == 1 else [(kh, c) for kh in range(3) for c in range(c8)]
+    mma_kd = len(slabs) // 2
+    img = torch.zeros(3 * mma_kd, 2, npad // 8, 8, 8, dtype=torch.float64)
+    for kd in range(3):
+        for s, sl in enumerate(slabs):
+            if sl is None:
+                continue
+            kh, c = sl
+            full = torch.zeros(8, npad, dtype=torch.float64)
+            for kw in range(3):
+                full[:, kw * cw:(kw + 1) * cw] = _hi_lo_columns(w[(kd * 3 + kh) * 3 + kw, c * 8:(c + 1) * 8, :])
+            img[kd * mma_kd + s // 2, s % 2] = full.t().reshape(npad // 8, 8, 8)
+    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+
+
 def pack_deconv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
     """fp16 B-operand image for the transposed conv in csrc/conv3d_gtc.cu: the 8 output-parity classes (pd,ph,pw) one after
     the other, each a dense conv over its input neighbours (sd,sh,sw) in {0..pd}x{0..ph}x{0..pw}; per axis parity 0 takes
@@ -319,6 +342,7 @@ class CostRegWeights:
     layers: dict          # name -> Conv3dWeights
     prob: torch.Tensor    # [27, 8]
     prob_tc: torch.Tensor | None = None
+    prob_roll: torch.Tensor | None = None
 
 
 def pack_costreg(sd, prefix, device) -> CostRegWeights:
@@ -326,6 +350,7 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
     layers.update({n: pack_conv3d(sd, f"{prefix}.{n}", True, device) for n in COSTREG_DECONVS})
     for n in ("conv0", "conv2", "conv4"):
         layers[n].extra["tc"] = pack_conv3d_tc(layers[n])
+    layers["conv0"].extra["roll"] = pack_conv3d_roll(layers["conv0"])
     for n in ("conv9", "conv11"):
         layers[n].extra["tc"] = pack_deconv3d_tc(layers[n])
     for n in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"):   # gather-form kernel (stride 2, small deep layers)
@@ -337,6 +362,7 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
     cw = CostRegWeights(layers, prob)
     if p.shape[1] == 8:   # tensor-core image of the prob head (8 -> 1)
         cw.prob_tc = pack_conv3d_tc(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), torch.zeros(1, device=device)))
+        cw.prob_roll = pack_conv3d_roll(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), torch.zeros(1, device=device)))
     return cw
 
 

@@ -137,6 +137,13 @@ int cds_deconv3d_k3s2_gtc_supported(int Cin, int Cout);
 int cds_deconv3d_k3s2_gtc_weight_halfs(int Cin, int Cout);
 int cds_deconv3d_k3s2_gtc(const void* in, const void* wgt_packed, const float* bias, const void* skip, int B, int Cin, int Cout,
                           int D, int H, int W, void* out, cudaStream_t stream);
+/* Persistent d-rolling tcgen05 form of the full-resolution stride-1 layers (csrc/conv3d_roll.cu): Cout == 8 (conv0, same
+ * semantics as cds_conv3d_k3, fp16 storage) and Cin == 8, Cout == 1 (the prob head: out = fp32 logits [B,D,H,W], bias NULL).
+ * wgt_packed: fp16 image [kd][mma][k-chunk 2][N/8][8 n][8 k], kw folded into N (host: weights.py pack_conv3d_roll). */
+int cds_conv3d_k3_roll_supported(int Cin, int Cout, int D, int H, int W);
+int cds_conv3d_k3_roll_weight_halfs(int Cin, int Cout);
+int cds_conv3d_k3_roll(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H, int W,
+                       int relu, void* out, cudaStream_t stream);
 /* prob head: plain Conv3d(8,1,3,p=1,bias=False) (models/module.py:303) -> fp32 logits [B,D,H,W]. */
 int cds_prob_conv(const void* in, const float* wgt, int B, int Cin, int D, int H, int W, int dtype, float* logits,
                   cudaStream_t stream);

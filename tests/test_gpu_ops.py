@@ -422,6 +422,37 @@ def test_conv3d_gather_tcgen05_vs_torch(cin, cout, stride, shape):
     close(from_blocked(out.float().cpu()), ref, 6e-3, 2e-3)
 
 
+@pytest.mark.parametrize("cin,cout", [(8, 8), (16, 8), (32, 8), (8, 1)])
+@pytest.mark.parametrize("shape", [(3, 5, 133), (8, 16, 256), (1, 4, 128), (4, 6, 50), (5, 19, 300), (2, 3, 126), (9, 40, 127)])
+def test_conv3d_rolling_tcgen05_vs_torch(cin, cout, shape):
+    """Persistent d-rolling tcgen05 Conv3d (kw folded into N, weights as fp16 value + residual columns) against the
+    published operator on fp16-rounded activations and UNROUNDED weights; shapes cover partial / overlapping x tiles,
+    H not a multiple of the row tile, single planes and several columns per CTA."""
+    D, H, Wd = shape
+    torch.manual_seed(cin * 100 + cout + Wd)
+    x = torch.randn(2, cin, D, H, Wd).half().float()
+    w = torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5
+    b = torch.randn(cout) if cout > 1 else torch.zeros(1)
+    ref = torch.nn.functional.conv3d(x, w, b if cout > 1 else None, stride=1, padding=1)
+    lw = W.Conv3dWeights(cin, cout, w.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous(), b)
+    packed = cu(W.pack_conv3d_roll(lw))
+    lib = _lib.LIB.load()
+    assert lib.cds_conv3d_k3_roll_supported(cin, cout, D, H, Wd) == 1
+    assert packed.numel() == lib.cds_conv3d_k3_roll_weight_halfs(cin, cout)
+    xc, bc = cu(to_blocked(x)).half(), cu(b)
+    if cout == 1:
+        out = torch.full((2, D, H, Wd), float("nan"), device=DEV, dtype=torch.float32)
+        call("cds_conv3d_k3_roll", ptr(xc), ptr(packed), None, 2, cin, 1, D, H, Wd, 0, ptr(out))
+        torch.cuda.synchronize()
+        close(out.cpu(), ref[:, 0], 2e-4, 1e-4)
+    else:
+        ref = torch.relu(ref)
+        out = torch.full((2, 1, D, H, Wd, 8), float("nan"), device=DEV, dtype=torch.float16)
+        call("cds_conv3d_k3_roll", ptr(xc), ptr(packed), ptr(bc), 2, cin, cout, D, H, Wd, 1, ptr(out))
+        torch.cuda.synchronize()
+        close(from_blocked(out.float().cpu()), ref, 6e-3, 2e-3)
+
+
 @pytest.mark.parametrize("cin,cout", [(64, 32), (32, 16)])
 @pytest.mark.parametrize("shape", [(3, 5, 7), (2, 4, 130), (6, 37, 50)])
 @pytest.mark.parametrize("with_skip", [True, False])
