@@ -14,8 +14,8 @@
 //   * a CTA owns a (TY rows x 126 voxels) column of the volume and ROLLS along d: each input plane is fetched by TMA
 //     exactly once per column into a 4-slot ring ([slab][TY+2 rows][128 voxels][8 ch], zero-filled outside the volume
 //     = the conv padding), so the (kd) reuse never touches L2 again and loads overlap the MMAs of the previous plane;
-//   * warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (accumulators: a ring of 4 row units in TMEM),
-//     warps 2..5 epilogue (tcgen05.ld -> kw fold -> bias/ReLU -> fp16 NDHWC store, or fp32 logits for the prob head);
+//   * warp roles (608 threads): warp 0 TMA producer, warps 1-2 MMA issuers on alternating row units (accumulators: a
+//     ring of 8 row units in TMEM), warps 3..18 epilogue, four groups of four (one warp per TMEM lane quadrant) (tcgen05.ld -> kw fold -> bias/ReLU -> fp16 NDHWC store, or fp32 logits for the prob head);
 //   * CTAs are persistent over columns (grid = min(columns, resident CTAs)), so barrier / TMEM / weight setup is paid once.
 // N columns: per kw, Cout columns of fp16-rounded weights then Cout columns of their rounding residual (summed in the
 // epilogue: effectively fp32-accurate weights at no extra A traffic); Cout = 8 -> N = 48, prob head -> N = 6 (16).
@@ -33,8 +33,10 @@ namespace {
 constexpr int TX = 128;
 constexpr int TXO = TX - 2;
 constexpr int ROW_BYTES = TX * 16;
-constexpr int NR = 4;     // input-plane ring slots
-constexpr int NACC = 4;   // accumulator ring (row units)
+constexpr int NACC = 8;   // accumulator ring (row units)
+constexpr int NEG = 4;    // epilogue warp groups (4 warps each); group g drains the row units u = g (mod NEG) of every plane
+constexpr int NMW = 2;    // MMA-issuing warps (one thread's issue stream, ~80 cycles per small MMA, is the limit otherwise)
+constexpr int NTHREADS = 32 * (1 + NMW) + NEG * 128;
 
 template <int CIN, int COUT, int TY_>
 struct RollCfg {
@@ -51,7 +53,14 @@ struct RollCfg {
     static constexpr uint32_t B_MMA = 2 * NPAD * 16;
     static constexpr uint32_t B_BYTES = NMMA * B_MMA;
     static constexpr uint32_t XCH_FLOATS = 2 * TY * 4 * 2 * COUT;   // [plane parity][unit][warp][up|down][co]
-    static constexpr uint32_t TMEM_COLS = NACC * NPAD <= 32 ? 32 : (NACC * NPAD <= 64 ? 64 : (NACC * NPAD <= 128 ? 128 : 256));
+    static_assert(TY % NEG == 0, "row units must split evenly over the epilogue groups");
+    static constexpr uint32_t TMEM_COLS = NACC * NPAD <= 32 ? 32 : (NACC * NPAD <= 64 ? 64 : (NACC * NPAD <= 128 ? 128 : (NACC * NPAD <= 256 ? 256 : 512)));
+    static_assert(NACC * NPAD <= 512, "accumulator ring exceeds TMEM");
+    // input-plane ring: 3 planes are live, the rest is prefetch depth (a TMA round trip to DRAM is longer than one plane's MMAs)
+    static constexpr uint32_t FIXED = B_BYTES + XCH_FLOATS * 4 + (2 * 8 + 2 * NACC + 1) * 8 + 16;
+    static constexpr int NR_FIT = (int)((227 * 1024 - FIXED) / SLOT);
+    static constexpr int NR = NR_FIT > 8 ? 8 : NR_FIT;
+    static_assert(NR >= 4, "input-plane ring needs at least 4 slots");
     static constexpr int NBAR = 2 * NR + 2 * NACC + 1;
     static constexpr size_t SMEM = (size_t)NR * SLOT + B_BYTES + XCH_FLOATS * 4 + NBAR * 8 + 16;
 };
@@ -68,11 +77,21 @@ struct RollParams {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void epilogue_barrier(int group) { asm volatile("bar.sync %0, 128;\n" ::"r"(group + 1) : "memory"); }
+// producer-side wait: not latency critical, so back off instead of stealing issue slots from the epilogue warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = tc::smem_u32(bar);
+    for (uint32_t spin = 0; !tc::mbar_try_wait(a, parity); ++spin) {
+        __nanosleep(64);
+        if (spin > (1u << 22)) __trap();
+    }
+}
 
-// all MMAs of one row unit: 3 planes x MMA_KD, every offset a compile-time constant
-template <class C, int KD, int J>
-__device__ __forceinline__ void issue_mma(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, uint32_t acc, bool elected) {
+// All MMAs of G consecutive row units, INTERLEAVED: for every (kd, slab pair) one MMA per unit, so that back-to-back MMAs
+// target different accumulators (a chain of dependent small-N MMAs on one accumulator runs at the tensor pipe's
+// accumulate latency, not at its throughput).  Every offset is a compile-time constant.
+template <class C, int G, int KD, int J>
+__device__ __forceinline__ void issue_mma(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, const uint32_t (&acc)[G], bool elected) {
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
     constexpr uint32_t idesc = tc::instr_desc_f16(128, C::NPAD);
     constexpr uint32_t off0 = C::C8 == 1 ? (uint32_t)(J == 0 ? 0 : 2 * ROW_BYTES)
@@ -80,27 +99,32 @@ __device__ __forceinline__ void issue_mma(const uint32_t (&a16)[3], uint32_t uro
     constexpr uint32_t lbo = C::C8 == 1 ? (uint32_t)(J == 0 ? ROW_BYTES : 16) : C::SLAB;
     constexpr uint32_t a_const = (off0 >> 4) | ((lbo >> 4) << 16);
     constexpr uint32_t b_const = (((uint32_t)(KD * C::MMA_KD + J) * C::B_MMA) >> 4) | (((uint32_t)(C::NPAD * 16) >> 4) << 16);
-    const uint64_t da = ((uint64_t)desc_hi << 32) | (a16[KD] + urow16 + a_const);
     const uint64_t db = ((uint64_t)desc_hi << 32) | (b16 + b_const);
-    if (elected) tc::mma_f16(acc, da, db, idesc, !(KD == 0 && J == 0));
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const uint64_t da = ((uint64_t)desc_hi << 32) | (a16[KD] + urow16 + (uint32_t)g * (ROW_BYTES >> 4) + a_const);
+        if (elected) tc::mma_f16(acc[g], da, db, idesc, !(KD == 0 && J == 0));
+    }
 }
-template <class C, int KD, int... J>
-__device__ __forceinline__ void issue_plane(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, uint32_t acc, bool elected,
+template <class C, int G, int KD, int... J>
+__device__ __forceinline__ void issue_plane(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, const uint32_t (&acc)[G], bool elected,
                                             std::integer_sequence<int, J...>) {
-    (issue_mma<C, KD, J>(a16, urow16, b16, acc, elected), ...);
+    (issue_mma<C, G, KD, J>(a16, urow16, b16, acc, elected), ...);
 }
-template <class C>
-__device__ __forceinline__ void issue_unit(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, uint32_t acc, bool elected) {
-    issue_plane<C, 0>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
-    issue_plane<C, 1>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
-    issue_plane<C, 2>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
+template <class C, int G>
+__device__ __forceinline__ void issue_units(const uint32_t (&a16)[3], uint32_t urow16, uint32_t b16, const uint32_t (&acc)[G], bool elected) {
+    issue_plane<C, G, 0>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
+    issue_plane<C, G, 1>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
+    issue_plane<C, G, 2>(a16, urow16, b16, acc, elected, std::make_integer_sequence<int, C::MMA_KD>{});
 }
 
 // tmap: 4-D view (2W x 8-byte elements, H, D, C/8) of one batch item's channel-blocked input, box (256, TY+2, 1, 1)
 template <int CIN, int COUT, int TY>
-__global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmap, const RollParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmap, const RollParams p) {
     using C = RollCfg<CIN, COUT, TY>;
-    constexpr int C8 = C::C8, NPAD = C::NPAD;
+    constexpr int C8 = C::C8, NPAD = C::NPAD, NR = C::NR;
+    constexpr int G = 1;   // row units whose MMAs are interleaved by one issuer
+    static_assert(TY % (G * NMW) == 0 && NACC % G == 0, "unit groups must tile the row tile and the accumulator ring");
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + NR * C::SLOT;
@@ -119,7 +143,7 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
     if (warp == 0) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     if (threadIdx.x == 32) {
 #pragma unroll
-        for (int i = 0; i < NR; ++i) { tc::mbar_init(bar_full + i, 1); tc::mbar_init(bar_empty + i, 1); }
+        for (int i = 0; i < NR; ++i) { tc::mbar_init(bar_full + i, 1); tc::mbar_init(bar_empty + i, NMW); }
 #pragma unroll
         for (int i = 0; i < NACC; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
         tc::mbar_init(bar_b, 1);
@@ -142,7 +166,7 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                 const int y0 = (tile / p.xt) * TY;
                 for (int pl = -1; pl <= p.D; ++pl, ++pc) {
                     const uint32_t slot = pc % NR;
-                    if (pc >= NR) tc::mbar_wait(bar_empty + slot, ((pc / NR) - 1) & 1);
+                    if (pc >= NR) mbar_wait_relaxed(bar_empty + slot, ((pc / NR) - 1) & 1);
                     tc::mbar_expect_tx(bar_full + slot, C::SLOT);
 #pragma unroll
                     for (int c8 = 0; c8 < C8; ++c8)
@@ -150,14 +174,15 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp <= NMW) {
+        const uint32_t mw = (uint32_t)warp - 1;   // this issuer takes the row units u = mw (mod NMW)
         // ---- MMA issuer (warp converged, one elected lane issues) -----------------------------------------------------------
         tc::mbar_wait(bar_b, 0);
         tc::tc_fence_after();
         const bool elected = tc::elect_one();
         const uint32_t tmem_u = tc::uniform(tmem);
         const uint32_t b16 = sB_u >> 4;
-        uint32_t pc_base = 0, uc = 0;
+        uint32_t pc_base = 0, uc0 = 0;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -174,12 +199,20 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd) a16[kd] = (sA_u + ((pc_base + d + kd) % NR) * C::SLOT) >> 4;
 #pragma unroll 1
-                for (uint32_t u = 0; u < (uint32_t)TY; ++u, ++uc) {
-                    const uint32_t s = uc % NACC;
-                    tc::mbar_wait(acc_empty + s, ((uc / NACC) & 1) ^ 1);   // epilogue has drained this accumulator
+                for (uint32_t u = mw * G; u < (uint32_t)TY; u += G * NMW) {
+                    const uint32_t uc = uc0 + u;
+                    uint32_t acc[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const uint32_t s = (uc + g) % NACC;
+                        tc::mbar_wait(acc_empty + s, (((uc + g) / NACC) & 1) ^ 1);   // epilogue has drained this accumulator
+                        acc[g] = tmem_u + s * NPAD;
+                    }
                     tc::tc_fence_after();
-                    issue_unit<C>(a16, (u * ROW_BYTES) >> 4, b16, tmem_u + s * NPAD, elected);
-                    if (elected) tc::mma_commit(acc_full + s);
+                    issue_units<C, G>(a16, (u * ROW_BYTES) >> 4, b16, acc, elected);
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        if (elected) tc::mma_commit(acc_full + (uc + g) % NACC);
                     __syncwarp();
                 }
                 // plane d-1 is done with; the column's last output also retires planes D-1 and D
@@ -189,19 +222,22 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                     tc::mma_commit(bar_empty + (pc_base + d + 2) % NR);
                 }
                 __syncwarp();
+                uc0 += TY;
             }
             pc_base += p.D + 2;
         }
         // the last planes' release arrivals land in this CTA's shared memory: let them before the CTA may exit
-        if (pc_base > 0) tc::mbar_wait(bar_empty + (pc_base - 1) % NR, ((pc_base - 1) / NR) & 1);
+        if (mw == 0 && pc_base > 0) tc::mbar_wait(bar_empty + (pc_base - 1) % NR, ((pc_base - 1) / NR) & 1);
     } else {
         // ---- epilogue warps: fold kw, bias / ReLU, store -----------------------------------------------------------------------
         const int q = warp & 3;              // TMEM lane group this warp may read
+        const int grp = (warp - 1 - NMW) >> 2;   // epilogue group: row units u = grp (mod NEG)
         const int r = q * 32 + lane;         // MMA row = window voxel r (x = x0 - 1 + r); rows 1..126 are outputs
+        constexpr int UPG = TY / NEG;        // row units per group and plane
         float bias[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
-        uint32_t uc = 0, planes = 0;
+        uint32_t uc0 = 0, planes = 0;        // unit counter at the start of the current plane
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int x0 = max(0, min((tile % p.xt) * TXO, p.W - TXO));
@@ -209,11 +245,13 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
             const int x = x0 - 1 + r;
             const bool col_ok = r >= 1 && r <= TXO && x < p.W;
 #pragma unroll 1
-            for (int d = 0; d < p.D; ++d, ++planes) {
+            for (int d = 0; d < p.D; ++d, ++planes, uc0 += TY) {
                 float* xb = xch + (planes & 1) * (TY * 4 * 2 * COUT);
-                float part[TY][COUT];
+                float part[UPG][COUT];
 #pragma unroll
-                for (int u = 0; u < TY; ++u, ++uc) {
+                for (int i = 0; i < UPG; ++i) {
+                    const int u = i * NEG + grp;
+                    const uint32_t uc = uc0 + u;
                     const uint32_t s = uc % NACC;
                     tc::mbar_wait(acc_full + s, (uc / NACC) & 1);
                     tc::tc_fence_after();
@@ -222,7 +260,7 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                     if constexpr (COUT == 8) {
                         uint32_t v[6][8];
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) tc::tmem_ld8_nowait(taddr + i * 8, v[i]);
+                        for (int j = 0; j < 6; ++j) tc::tmem_ld8_nowait(taddr + j * 8, v[j]);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -245,7 +283,7 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                     for (int c = 0; c < COUT; ++c) {
                         const float up = __shfl_up_sync(0xffffffffu, e0[c], 1);
                         const float dn = __shfl_down_sync(0xffffffffu, e2[c], 1);
-                        part[u][c] = e1[c] + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+                        part[i][c] = e1[c] + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
                     }
                     // warp seams: row 32q+31's kw=0 term belongs to row 32(q+1); row 32q's kw=2 term to row 32q-1
                     if (lane == 31) {
@@ -257,16 +295,17 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                         for (int c = 0; c < COUT; ++c) xb[((u * 4 + q) * 2 + 1) * COUT + c] = e2[c];
                     }
                 }
-                epilogue_barrier();
+                epilogue_barrier(grp);   // the group's four warps have published their seam values of this plane
 #pragma unroll
-                for (int u = 0; u < TY; ++u) {
+                for (int i = 0; i < UPG; ++i) {
+                    const int u = i * NEG + grp;
                     if (lane == 0 && q > 0) {
 #pragma unroll
-                        for (int c = 0; c < COUT; ++c) part[u][c] += xb[((u * 4 + q - 1) * 2 + 0) * COUT + c];
+                        for (int c = 0; c < COUT; ++c) part[i][c] += xb[((u * 4 + q - 1) * 2 + 0) * COUT + c];
                     }
                     if (lane == 31 && q < 3) {
 #pragma unroll
-                        for (int c = 0; c < COUT; ++c) part[u][c] += xb[((u * 4 + q + 1) * 2 + 1) * COUT + c];
+                        for (int c = 0; c < COUT; ++c) part[i][c] += xb[((u * 4 + q + 1) * 2 + 1) * COUT + c];
                     }
                     const int y = y0 + u;
                     if (col_ok && y < p.H) {
@@ -275,12 +314,12 @@ __global__ void __launch_bounds__(192, 1) conv3d_roll_kernel(const __grid_consta
                             float o[8];
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
-                                const float t = part[u][c] + bias[c];
+                                const float t = part[i][c] + bias[c];
                                 o[c] = p.relu ? fmaxf(t, 0.f) : t;
                             }
                             Vec8<__half>::store(p.out + vox * 8, o);
                         } else {
-                            p.logits[vox] = part[u][0];
+                            p.logits[vox] = part[i][0];
                         }
                     }
                 }
@@ -316,8 +355,7 @@ int launch_roll(const void* in, const void* wgt, const float* bias, int B, int D
     p.D = D; p.H = H; p.W = W; p.relu = relu;
     p.xt = cds_div_up(W, TXO);
     p.yt = cds_div_up(H, TY);
-    const int per_sm = (int)((227 * 1024) / C::SMEM) >= 2 && 2 * C::TMEM_COLS <= 512 ? 2 : 1;
-    const int grid = std::min(p.xt * p.yt, per_sm * sm_count());
+    const int grid = std::min(p.xt * p.yt, sm_count());   // one persistent CTA per SM
     for (int b = 0; b < B; ++b) {
         const __half* base = (const __half*)in + (size_t)b * D * H * W * CIN;
         CUtensorMap tmap;
@@ -327,7 +365,7 @@ int launch_roll(const void* in, const void* wgt, const float* bias, int B, int D
         if (!tma::make_u64(&tmap, base, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
         p.out = COUT == 1 ? nullptr : (__half*)out + (size_t)b * D * H * W * COUT;
         p.logits = COUT == 1 ? (float*)out + (size_t)b * D * H * W : nullptr;
-        kern<<<grid, 192, C::SMEM, st>>>(tmap, p);
+        kern<<<grid, NTHREADS, C::SMEM, st>>>(tmap, p);
     }
     return cds_check_launch("cds_conv3d_k3_roll");
 }
