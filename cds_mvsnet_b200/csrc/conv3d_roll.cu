@@ -35,7 +35,7 @@ constexpr int TXO = TX - 2;
 constexpr int ROW_BYTES = TX * 16;
 constexpr int NACC = 8;   // accumulator ring (row units)
 constexpr int NEG = 4;    // epilogue warp groups (4 warps each); group g drains the row units u = g (mod NEG) of every plane
-constexpr int NMW = 2;    // MMA-issuing warps (one thread's issue stream, ~80 cycles per small MMA, is the limit otherwise)
+constexpr int NMW = 4;    // MMA-issuing warps (one thread's issue stream, ~80 cycles per small MMA, is the limit otherwise)
 constexpr int NTHREADS = 32 * (1 + NMW) + NEG * 128;
 
 template <int CIN, int COUT, int TY_>
