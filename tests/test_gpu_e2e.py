@@ -122,3 +122,32 @@ def test_patch_rebinds_reference_names(pretrained_sd):
     import models.module as rmod
     C.patch(rm, rmod)
     assert rm.homo_warping_3D is C.homo_warping_3D and rmod.DynamicConv is C.DynamicConv
+
+
+def test_depth_map_stream_matches_direct_call(pretrained_sd):
+    """DepthMapStream (double-buffered host<->device copies on side streams) returns the same maps as the direct call for
+    several different work items in flight (same kernels; the InstanceNorm statistics are accumulated with atomics, so two
+    runs agree to re-association noise, not bit for bit)."""
+    from cds_mvsnet_b200.streaming import DepthMapStream
+    cfg = dict(W=160, H=128, N=3, ndepths=(16, 8, 8), ratios=(4.0, 1.5, 0.75), B=1, Dtot=192, interval=2.65)
+    model = build(pretrained_sd, cfg["ndepths"], cfg["ratios"], torch.float16)
+    items = [synthetic.make_sample(cfg, "plane" if i % 2 else "noise", seed=i) for i in range(5)]
+    direct = [{k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in run(model, s).items() if isinstance(v, dict)} for s in items]
+    stream = DepthMapStream(model, temperature=T)
+    got, prev = [], None
+    for s in items:
+        t = stream.submit(s.imgs, s.proj_matrices, s.depth_values)
+        if prev is not None:
+            got.append({k: v.clone() for k, v in stream.result(prev).items()})
+        prev = t
+    got.append({k: v.clone() for k, v in stream.result(prev).items()})
+    assert len(got) == len(items)
+    for d, g in zip(direct, got):
+        for st, maps in d.items():
+            for name, ref in maps.items():
+                err = O.rel_l1(g[f"{st}.{name}"], ref)
+                assert err < 2e-5, (st, name, err)
+    with pytest.raises(ValueError):
+        stream.result(0)          # overwritten two submits ago
+    with pytest.raises(ValueError):
+        stream.submit(items[0].imgs.to(DEV), items[0].proj_matrices, items[0].depth_values)
