@@ -123,17 +123,17 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
                                                       const float* __restrict__ coef, const float* __restrict__ depth,
                                                       int V, int B, int D, int h, int w, float* __restrict__ entropy) {
     constexpr int LPP = C / 8;  // lanes per pixel
-    const long long P = (long long)h * w;
-    const long long total = (long long)V * B * P * LPP;
-    long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    // lanes of one pixel are always in the same warp because LPP divides 32; dead lanes of the last warp redo the
-    // last pixel so that every shuffle below is executed by the full warp
-    bool live = gid < total;
-    long long g = live ? gid : total - 1;
-    int chunk = (int)(g % LPP);
-    long long pix = g / LPP;
-    int x = (int)(pix % w), y = (int)((pix / w) % h);
-    int b = (int)((pix / P) % B), v = (int)(pix / (P * B));
+    // 32-bit indexing (the host checks h*w*C < 2^31): blockIdx.y = (view, batch item), blockIdx.x tiles that image's
+    // pixels.  Lanes of one pixel sit in the same warp because LPP divides 32; dead lanes of an image's last block redo
+    // its last pixel so that every shuffle below is executed by full warps.
+    const int P = h * w;
+    const int v = blockIdx.y / B, b = blockIdx.y % B;
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    const bool live = gid < P * LPP;
+    const int g = live ? gid : P * LPP - 1;
+    const int chunk = g % LPP;
+    const int pix = g / LPP;
+    const int x = pix % w, y = pix / w;
     const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
 
     const T* rf = ref_fea + (((size_t)v * B + b) * P + (size_t)y * w + x) * C + chunk * 8;
@@ -147,11 +147,15 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
 
     // online softmax statistics: m = running max, S = sum e^(s-m), A = sum (s-m) e^(s-m)
     float m = -INFINITY, S = 0.f, A = 0.f;
+    // the hypothesis of the NEXT step is fetched one step ahead: it streams from DRAM, and the gathers that depend on
+    // it would otherwise see two memory latencies back to back
+    float dep_next = __ldg(dp + (size_t)min(chunk, D - 1) * P);
     for (int d0 = 0; d0 < D; d0 += LPP) {
         // lane `chunk` of the pixel projects plane d0 + chunk (clamped when D is not a multiple of LPP)
         Foot mine;
         {
-            float dep = __ldg(dp + (size_t)min(d0 + chunk, D - 1) * P);
+            const float dep = dep_next;
+            dep_next = __ldg(dp + (size_t)min(d0 + LPP + chunk, D - 1) * P);
             float u, vv;
             project_fast(k, rx, ry, rz, dep, u, vv);
             mine = make_foot(u, vv, w, h);
@@ -197,15 +201,16 @@ __global__ void __launch_bounds__(256, VMAX <= 4 ? 3 : 2) aggregate_kernel(const
                                                         T* __restrict__ volume) {
     constexpr int LPP = C / 8;
     constexpr int OWN = (VMAX + LPP - 1) / LPP;   // views whose projection this lane may own (V <= VMAX)
-    const long long P = (long long)h * w;
-    const long long total = (long long)B * P * LPP;
-    long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    bool live = gid < total;
-    long long g = live ? gid : total - 1;
-    int chunk = (int)(g % LPP);
-    long long pix = g / LPP;
-    int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / P);
-    size_t pofs = (size_t)y * w + x;
+    // 32-bit indexing: blockIdx.y = batch item, blockIdx.x tiles its pixels (see entropy_kernel)
+    const int P = h * w;
+    const int b = blockIdx.y;
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    const bool live = gid < P * LPP;
+    const int g = live ? gid : P * LPP - 1;
+    const int chunk = g % LPP;
+    const int pix = g / LPP;
+    const int x = pix % w, y = pix / w;
+    const size_t pofs = (size_t)pix;
     const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
 
     // visibility weights of this pixel
@@ -237,8 +242,10 @@ __global__ void __launch_bounds__(256, VMAX <= 4 ? 3 : 2) aggregate_kernel(const
     const T* sbase = src_fea + (size_t)b * P * C + chunk * 8;
     const size_t vstride = (size_t)B * P * C;
 
+    float dep_next = __ldg(dp);
     for (int d = 0; d < D; ++d) {
-        const float dep = __ldg(dp + (size_t)d * P);
+        const float dep = dep_next;
+        dep_next = __ldg(dp + (size_t)min(d + 1, D - 1) * P);   // one plane ahead (see entropy_kernel)
         float2 acc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
@@ -287,8 +294,7 @@ __global__ void nc_mean_kernel(const float* __restrict__ ref_nc, const float* __
 template <typename T>
 int launch_entropy(const void* ref, const void* src, const float* coef, const float* depth, int V, int B, int C, int D,
                    int h, int w, float* entropy, cudaStream_t st) {
-    long long total = (long long)V * B * h * w * (C / 8);
-    int blocks = cds_div_up(total, 256);
+    dim3 blocks(cds_div_up((long long)h * w * (C / 8), 256), V * B);
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
     switch (C) {
@@ -303,8 +309,7 @@ int launch_entropy(const void* ref, const void* src, const float* coef, const fl
 template <typename T>
 int launch_aggregate(const void* ref, const void* src, const float* coef, const float* depth, const float* vis, int V,
                      int B, int C, int D, int h, int w, void* volume, cudaStream_t st) {
-    long long total = (long long)B * h * w * (C / 8);
-    int blocks = cds_div_up(total, 256);
+    dim3 blocks(cds_div_up((long long)h * w * (C / 8), 256), B);
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
     T* o = (T*)volume;
@@ -330,7 +335,8 @@ int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* c
     CDS_REQUIRE(ref_fea && src_fea && coef && depth && entropy, CDS_EARG, "cds_costvol_entropy: null pointer");
     CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
                 "cds_costvol_entropy: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
-    CDS_REQUIRE((long long)h * w * C < (1ll << 31), CDS_ESHAPE, "cds_costvol_entropy: feature map too large for 32-bit offsets");
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B <= 65535, CDS_ESHAPE,
+                "cds_costvol_entropy: feature map too large for 32-bit offsets");
     if (dtype == CDS_F16) return launch_entropy<__half>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     if (dtype == CDS_F32) return launch_entropy<float>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     cds_set_error("cds_costvol_entropy: unknown dtype %d", dtype);
@@ -343,7 +349,8 @@ int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float*
     CDS_REQUIRE(ref_fea && src_fea && coef && depth && vis && volume, CDS_EARG, "cds_costvol_aggregate: null pointer");
     CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
                 "cds_costvol_aggregate: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
-    CDS_REQUIRE((long long)h * w * C < (1ll << 31), CDS_ESHAPE, "cds_costvol_aggregate: feature map too large for 32-bit offsets");
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && B <= 65535, CDS_ESHAPE,
+                "cds_costvol_aggregate: feature map too large for 32-bit offsets");
     if (dtype == CDS_F16) return launch_aggregate<__half>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     if (dtype == CDS_F32) return launch_aggregate<float>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     cds_set_error("cds_costvol_aggregate: unknown dtype %d", dtype);
