@@ -283,9 +283,19 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
 #pragma unroll
         for (int c = 0; c < (REG_STATS ? COUT : 1); ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
 
+        // the curvature accumulator is read-modify-written per pixel: its old value is fetched one row unit ahead, so that
+        // the DRAM round trip overlaps the previous unit's work instead of sitting in every unit's critical path
+        auto load_nc = [&](int u) {
+            const int gy = y0 + u;
+            const bool ok = u < TY && r < TXO && gy < p.H && gx < p.W && gx >= (int)blockIdx.x * TXO;
+            return (ok && p.nc_sq && p.nc_mode != 0) ? __ldcg(p.nc_sq + ((size_t)n * p.H + gy) * p.W + gx) : 0.f;
+        };
+        float nc_next = load_nc(0);
 #pragma unroll 1
         for (int u = 0; u < TY; ++u) {
             const int s = u & 1;
+            const float nc_old = nc_next;
+            nc_next = load_nc(u + 1);
             tc::mbar_wait(bar_full + s, (u >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
@@ -383,8 +393,8 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
                 if (p.norm_curv) p.norm_curv[m] = nc;
                 if (p.nc_sq) {
                     if (p.nc_mode == 0) p.nc_sq[m] = nc * nc;
-                    else if (p.nc_mode == 1) p.nc_sq[m] = p.nc_sq[m] + nc * nc;
-                    else p.nc_sq[m] = (p.nc_sq[m] + nc * nc) / 3.f;
+                    else if (p.nc_mode == 1) p.nc_sq[m] = nc_old + nc * nc;
+                    else p.nc_sq[m] = (nc_old + nc * nc) / 3.f;
                 }
                 if (p.nc_abs) p.nc_abs[m] = fabsf(nc);
             }
