@@ -45,7 +45,12 @@ struct Cfg {
     static constexpr int HALO = (KMAX - 1) / 2;
     static constexpr int TXO = TX - 2 * HALO;    // valid outputs per row unit
     // per branch: COUT feature columns, (a,b,c) from fp16-rounded curvature weights, (a,b,c) from their residuals
-    static constexpr int NPAD = (COUT_ + 6 + 15) / 16 * 16;
+    // two-branch layers (everything but conv00 / conv01) also carry the fp16 rounding RESIDUAL of the feature weights in
+    // COUT extra columns per branch, summed in the epilogue: the depth error of the fp16 path is dominated by operand
+    // rounding in these cheap layers, and they are not MMA-bound
+    static constexpr bool WLO = K2_ == 0;
+    static constexpr int FCOLS = (WLO ? 2 : 1) * COUT_;         // feature columns per branch; curvature columns follow
+    static constexpr int NPAD = (FCOLS + 6 + 15) / 16 * 16;
     // Branches are embedded in the KMAX x KMAX tap grid.  The tensor core re-reads the 4 KB A operand from shared
     // memory for every MMA (>= 32 cycles whatever N is), so one wide MMA per tap pair beats one narrow MMA per
     // branch and tap.  Taps inside the second-largest kernel's support (KIN x KIN) feed ALL branches (N = NK*NPAD,
@@ -150,7 +155,9 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
     constexpr uint32_t A_BYTES = (SPLIT ? 2 : 1) * C8 * CHUNK;
     constexpr uint32_t B_BYTES = C::B_BYTES;
     constexpr uint32_t STAGE_COLS = C::NALL;                        // accumulator columns per row unit
-    constexpr uint32_t TMEM_COLS = 2 * STAGE_COLS <= 64 ? 64 : (2 * STAGE_COLS <= 128 ? 128 : 256);
+    constexpr uint32_t NSTG = 2 * STAGE_COLS <= 256 ? 2 : 1;        // accumulator stages (one when two would take the whole TMEM)
+    constexpr uint32_t TMEM_COLS = NSTG * STAGE_COLS <= 64 ? 64 : (NSTG * STAGE_COLS <= 128 ? 128 : 256);
+    static_assert(NSTG * STAGE_COLS <= 256, "accumulators exceed the TMEM budget of two resident CTAs");
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + A_BYTES;
@@ -263,8 +270,8 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
         const uint32_t tmem_u = tc::uniform(tmem);
 #pragma unroll 1
         for (uint32_t u = 0; u < (uint32_t)TY; ++u) {
-            const uint32_t s = u & 1;
-            tc::mbar_wait(bar_empty + s, ((u >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+            const uint32_t s = u % NSTG;
+            tc::mbar_wait(bar_empty + s, ((u / NSTG) & 1) ^ 1);   // epilogue has drained this accumulator stage
             tc::tc_fence_after();
             const uint32_t a_base = (sA_u + u * ROW_BYTES) >> 4;
             const uint32_t acc = tmem_u + s * STAGE_COLS;
@@ -293,16 +300,16 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
         float nc_next = load_nc(0);
 #pragma unroll 1
         for (int u = 0; u < TY; ++u) {
-            const int s = u & 1;
+            const int s = u % (int)NSTG;
             const float nc_old = nc_next;
             nc_next = load_nc(u + 1);
-            tc::mbar_wait(bar_full + s, (u >> 1) & 1);
+            tc::mbar_wait(bar_full + s, (u / (int)NSTG) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
             // 1. curvature columns of every branch -> gate weights
             uint32_t ar[NK][8];
 #pragma unroll
-            for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + b * NPAD + COUT, ar[b]);
+            for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + b * NPAD + C::FCOLS, ar[b]);
             tc::tmem_ld_wait();
 
             const int gy = y0 + u;
@@ -353,6 +360,16 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
                 uint32_t yr[NK][8];
 #pragma unroll
                 for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + b * NPAD + c8 * 8, yr[b]);
+                if constexpr (C::WLO) {   // product with the feature weights' fp16 rounding residual
+                    uint32_t yl[NK][8];
+#pragma unroll
+                    for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + b * NPAD + COUT + c8 * 8, yl[b]);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int b = 0; b < NK; ++b)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) yr[b][c] = __float_as_uint(__uint_as_float(yr[b][c]) + __uint_as_float(yl[b][c]));
+                }
                 tc::tmem_ld_wait();
                 float out[8];
 #pragma unroll
@@ -499,7 +516,7 @@ int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kerne
 }
 
 int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks) {
-    int kmax = 0, kin = 0, c8 = Cin / 8, npad = (Cout + 6 + 15) / 16 * 16;
+    int kmax = 0, kin = 0, c8 = Cin / 8, npad = ((num_kernels == 2 ? 2 : 1) * Cout + 6 + 15) / 16 * 16;
     for (int i = 0; i < num_kernels; ++i) kmax = ks[i] > kmax ? ks[i] : kmax;
     for (int i = 0; i < num_kernels; ++i) if (ks[i] < kmax && ks[i] > kin) kin = ks[i];
     int nin = kin * kin, nring = kmax * kmax - nin;
@@ -534,10 +551,10 @@ int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const
     switch (lid) {
         case 1: return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8>(x, n_images, p, n, stream);
         case 2: return launch_dyn_tc<Cfg<3, 5, 7, 8, 8>, 8>(x, n_images, p, n, stream);
-        case 3: return launch_dyn_tc<Cfg<1, 3, 0, 8, 8>, 8>(x, n_images, p, n, stream);
+        case 3: return launch_dyn_tc<Cfg<1, 3, 0, 8, 8>, 16>(x, n_images, p, n, stream);
         case 4: return launch_dyn_tc<Cfg<3, 5, 0, 16, 16>, 8>(x, n_images, p, n, stream);
         case 5: return launch_dyn_tc<Cfg<1, 3, 0, 16, 16>, 8>(x, n_images, p, n, stream);
-        default: return launch_dyn_tc<Cfg<1, 3, 0, 32, 32>, 8>(x, n_images, p, n, stream);
+        default: return launch_dyn_tc<Cfg<1, 3, 0, 32, 32>, 4>(x, n_images, p, n, stream);
     }
 }
 

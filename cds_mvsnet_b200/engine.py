@@ -68,6 +68,7 @@ class FeatureExtractor:
         # opt-in: hi/lo fp16 activation planes into conv10/conv11 (4x lower error in those layers at 2x their MMAs; the
         # end-to-end gain on the worst-case input is within sample noise)
         self.split_precision = os.environ.get("CDS_SPLIT", "0") == "1"
+        self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
         self._buf = None
 
     def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
@@ -97,6 +98,31 @@ class FeatureExtractor:
              ptr(w.w_att), ptr(w.w_conv), ptr(w.bias), ptr(w.gate), n, w.cin, w.cout, H, W, len(w.ksizes),
              _ksizes(w.ksizes), float(T), self.dt, ptr(out), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode,
              ptr(nc_abs))
+
+    def _down(self, name, x, x_stats, w32, n, cin, cout, H, W, out, out_stats, split):
+        """3x3 stride-2 conv of FeatureNet.downsample1/2 (out: [1 or 2 planes, n, H/2, W/2, cout])."""
+        e = _esize(self.storage)
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        _lib.set_tag("feat." + name, (2.0 * 9 * cin * cout * n * Ho * Wo, float(n * (H * W * cin + Ho * Wo * cout) * e)))
+        if (self.use_tc2d and self.storage == torch.float16 and name in self.fw.tc
+                and _lib.LIB.load().cds_conv2d_3x3s2_tc_supported(cin, cout)):
+            call("cds_conv2d_3x3s2_tc", ptr(x), ptr(x_stats), ACT_LRELU, ptr(self.fw.tc[name]), n, cin, cout, H, W, ptr(out[0]),
+                 ptr(out[1]) if split else None, ptr(out_stats))
+            return
+        call("cds_conv2d_3x3s2", ptr(x), ptr(x_stats), ACT_LRELU, ptr(w32), n, cin, cout, H, W, self.dt, ptr(out[0]),
+             ptr(out[1]) if split else None, ptr(out_stats))
+
+    def _inner(self, name, a, a_stats, a_act, b, b_stats, w32, n, ca, cb, cout, H, W, out, out_stats):
+        """1x1 conv over cat(nearest-up2(a), b) of FeatureNet.inner1/2."""
+        e = _esize(self.storage)
+        _lib.set_tag("feat." + name, (2.0 * (ca + cb) * cout * n * H * W, float(n * ((H // 2) * (W // 2) * ca + H * W * (cb + cout)) * e)))
+        if (self.use_tc2d and self.storage == torch.float16 and name in self.fw.tc
+                and _lib.LIB.load().cds_conv2d_1x1_cat_tc_supported(ca, cb, cout)):
+            call("cds_conv2d_1x1_cat_tc", ptr(a), ptr(a_stats), a_act, ptr(b), ptr(b_stats), ACT_LRELU, ptr(self.fw.tc[name]),
+                 n, ca, cb, cout, H, W, ptr(out), ptr(out_stats))
+            return
+        call("cds_conv2d_1x1_cat", ptr(a), ptr(a_stats), a_act, ptr(b), ptr(b_stats), ACT_LRELU, ptr(w32), n, ca, cb, cout, H, W,
+             self.dt, ptr(out), ptr(out_stats))
 
     def _split_ok(self, H2, W2):
         w = self.fw.dyn["conv10"]
@@ -149,32 +175,24 @@ class FeatureExtractor:
         self._dyn("conv00", imgs, 1, img_index, None, ACT_NONE, epipoles, 1.0, n, H, W, T, raw00, sv(0, 8), ncsq[2], 0, None)
         self._dyn("conv01", raw00, 0, None, sv(0, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, raw01, sv(1, 8), ncsq[2], 1, None)
         # 1/2 resolution
-        kcall("feat.downsample1", 2.0 * 9 * 8 * 16 * n * H2 * W2, n * (H * W * 8 + H2 * W2 * 16) * e,
-              "cds_conv2d_3x3s2", ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.downsample1), n, 8, 16, H, W, dt, ptr(rawd1[0]),
-              ptr(rawd1[1]) if split else None, ptr(sv(2, 16)))
+        self._down("downsample1", raw01, sv(1, 8), fw.downsample1, n, 8, 16, H, W, rawd1, sv(2, 16), split)
         self._dyn("conv10", rawd1, 0, None, sv(2, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw10[0], sv(3, 16), ncsq[1], 0, None,
                   split_in=split, out_lo=raw10[1] if split else None)
         self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11, sv(4, 16), ncsq[1], 1, None,
                   split_in=split)
         # 1/4 resolution
-        kcall("feat.downsample2", 2.0 * 9 * 16 * 32 * n * H4 * W4, n * (H2 * W2 * 16 + H4 * W4 * 32) * e,
-              "cds_conv2d_3x3s2", ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.downsample2), n, 16, 32, H2, W2, dt, ptr(rawd2), None,
-              ptr(sv(5, 32)))
+        self._down("downsample2", raw11, sv(4, 16), fw.downsample2, n, 16, 32, H2, W2, rawd2.unsqueeze(0), sv(5, 32), False)
         self._dyn("conv20", rawd2, 0, None, sv(5, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw20, sv(6, 32), ncsq[0], 0, None)
         self._dyn("conv21", raw20, 0, None, sv(6, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw21, sv(7, 32), ncsq[0], 1, None)
         # stage-1 output
         self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1, sv(8, 32), ncsq[0], 2, ncab[0])
         kcall("feat.act1", 0, 2 * n * H4 * W4 * 32 * e, "cds_instnorm_act", ptr(rawo1), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
         # stage-2 output: inner1 over cat(up2(conv21), conv11)
-        kcall("feat.inner1", 2.0 * 48 * 16 * n * H2 * W2, n * (H4 * W4 * 32 + 2 * H2 * W2 * 16) * e,
-              "cds_conv2d_1x1_cat", ptr(raw21), ptr(sv(7, 32)), ACT_LRELU, ptr(raw11), ptr(sv(4, 16)), ACT_LRELU, ptr(fw.inner1),
-             n, 32, 16, 16, H2, W2, dt, ptr(rawi1), ptr(sv(9, 16)))
+        self._inner("inner1", raw21, sv(7, 32), ACT_LRELU, raw11, sv(4, 16), fw.inner1, n, 32, 16, 16, H2, W2, rawi1, sv(9, 16))
         self._dyn("out2", rawi1, 0, None, sv(9, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, rawo2, sv(10, 16), ncsq[1], 2, ncab[1])
         kcall("feat.act2", 0, 2 * n * H2 * W2 * 16 * e, "cds_instnorm_act", ptr(rawo2), ptr(sv(10, 16)), ACT_TANH, n, 16, H2, W2, dt, ptr(fea2))
         # stage-3 output: inner2 over cat(up2(stage-2 feature), conv01)
-        kcall("feat.inner2", 2.0 * 24 * 8 * n * H * W, n * (H2 * W2 * 16 + 2 * H * W * 8) * e,
-              "cds_conv2d_1x1_cat", ptr(fea2), None, ACT_NONE, ptr(raw01), ptr(sv(1, 8)), ACT_LRELU, ptr(fw.inner2),
-             n, 16, 8, 8, H, W, dt, ptr(rawi2), ptr(sv(11, 8)))
+        self._inner("inner2", fea2, None, ACT_NONE, raw01, sv(1, 8), fw.inner2, n, 16, 8, 8, H, W, rawi2, sv(11, 8))
         self._dyn("out3", rawi2, 0, None, sv(11, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, rawo3, sv(12, 8), ncsq[2], 2, ncab[2])
         kcall("feat.act3", 0, 2 * n * H * W * 8 * e, "cds_instnorm_act", ptr(rawo3), ptr(sv(12, 8)), ACT_TANH, n, 8, H, W, dt, ptr(fea3))
         return {0: (fea1, ncsq[0], ncab[0]), 1: (fea2, ncsq[1], ncab[1]), 2: (fea3, ncsq[2], ncab[2])}

@@ -73,7 +73,8 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     """fp16 B-operand image for csrc/dynconv_tc.cu (Cin 3 is zero-padded to 8).
 
     Every branch is embedded in the kmax x kmax tap grid.  Branch b owns N columns [b*NPAD, (b+1)*NPAD) with
-    NPAD = roundup16(Cout + 6): Cout feature channels, (a, b, c) rounded to fp16, the rounding residuals of (a, b, c).
+    NPAD = roundup16(F + 6): F feature columns (Cout; for the two-branch layers 2*Cout = fp16-rounded weights followed by
+    their rounding residuals), then (a, b, c) rounded to fp16, then the rounding residuals of (a, b, c).
     K = 16 per MMA = two 8-channel slabs: for Cin <= 8 two consecutive taps ([tap0, zero pad], [tap1, tap2], ...), for
     Cin > 8 two channel chunks of one tap.  First the MMAs of the inner taps (support of the second-largest kernel;
     all branches, N = K*NPAD), then those of the outer ring (largest kernel only, N = NPAD); per MMA
@@ -82,7 +83,9 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     c8 = max(1, cin // 8)
     att, conv = w.w_att.detach().double().cpu(), w.w_conv.detach().double().cpu()
     K, kmax = len(w.ksizes), max(w.ksizes)
-    npad = (cout + 6 + 15) // 16 * 16
+    wlo = K == 2                                  # two-branch layers also carry the feature weights' fp16 residual
+    fcols = (2 if wlo else 1) * cout               # feature columns per branch; the curvature columns follow
+    npad = (fcols + 6 + 15) // 16 * 16
     ntap = kmax * kmax
     full = torch.zeros(ntap, c8 * 8, npad * K, dtype=torch.float64)           # [tap, k (cin), n]
     t0 = 0
@@ -92,11 +95,16 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
             for kx in range(k):
                 t = (ky + o) * kmax + (kx + o)
                 src = t0 + ky * k + kx
-                full[t, :cin, npad * b:npad * b + cout] = conv[src]
+                if wlo:
+                    chi = conv[src].to(torch.float16).to(torch.float64)
+                    full[t, :cin, npad * b:npad * b + cout] = chi
+                    full[t, :cin, npad * b + cout:npad * b + 2 * cout] = conv[src] - chi
+                else:
+                    full[t, :cin, npad * b:npad * b + cout] = conv[src]
                 a = att[src][:, :3]
                 hi = a.to(torch.float16).to(torch.float64)
-                full[t, :cin, npad * b + cout:npad * b + cout + 3] = hi
-                full[t, :cin, npad * b + cout + 3:npad * b + cout + 6] = a - hi
+                full[t, :cin, npad * b + fcols:npad * b + fcols + 3] = hi
+                full[t, :cin, npad * b + fcols + 3:npad * b + fcols + 6] = a - hi
         t0 += k * k
     if cin == 3:   # image layer: channels 3..5 of the operand carry the image's fp16 rounding residual (cds_image_to_nhwc8)
         full[:, 3:6, :] = full[:, 0:3, :]
@@ -366,6 +374,25 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
     return cw
 
 
+def pack_conv2d_gtc(w: torch.Tensor) -> torch.Tensor:
+    """fp16 B-operand image for csrc/conv2d_gtc.cu from tap-major weights [taps, Cin, Cout] (3x3 s2: 9 taps; 1x1: 1 tap):
+    [mma][k-chunk 2][N/8][8 n][8 k], N = 2*Cout (weights + fp16 rounding residual columns); K slabs tap-major / 8-channel
+    chunk minor, zero-padded to an even count; an MMA takes two consecutive slabs."""
+    taps, ci, co = w.shape
+    c8, N = ci // 8, 2 * co
+    w = w.detach().to(torch.float64).cpu()
+    slabs = [(t, c) for t in range(taps) for c in range(c8)]
+    if len(slabs) % 2:
+        slabs.append(None)
+    img = torch.zeros(len(slabs) // 2, 2, N // 8, 8, 8, dtype=torch.float64)
+    for s, sl in enumerate(slabs):
+        if sl is None:
+            continue
+        t, c = sl
+        img[s // 2, s % 2] = _hi_lo_columns(w[t, c * 8:(c + 1) * 8, :]).t().reshape(N // 8, 8, 8)
+    return img.to(dtype=torch.float16).contiguous()
+
+
 @dataclass
 class FeatureWeights:
     dyn: dict             # name -> DynWeights
@@ -373,16 +400,21 @@ class FeatureWeights:
     downsample2: torch.Tensor
     inner1: torch.Tensor  # [48,16]
     inner2: torch.Tensor  # [24,8]
+    tc: dict = field(default_factory=dict)   # name -> fp16 tensor-core operand image (csrc/conv2d_gtc.cu)
 
 
 def pack_feature(sd, device) -> FeatureWeights:
     dyn = {n: pack_dynamic_conv(sd, pre, ci, co, ks, device) for n, (ci, co, ks, pre) in DYN_LAYERS.items()}
     for n in dyn:
         dyn[n].tc = pack_dynamic_conv_tc(dyn[n])
-    return FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
-                          pack_conv2d(sd, "feature.downsample2.conv.weight", device),
-                          pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16).contiguous(),
-                          pack_conv2d(sd, "feature.inner2.conv.weight", device).reshape(24, 8).contiguous())
+    fw = FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
+                        pack_conv2d(sd, "feature.downsample2.conv.weight", device),
+                        pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16).contiguous(),
+                        pack_conv2d(sd, "feature.inner2.conv.weight", device).reshape(24, 8).contiguous())
+    fw.tc = {"downsample1": pack_conv2d_gtc(fw.downsample1).to(device), "downsample2": pack_conv2d_gtc(fw.downsample2).to(device),
+             "inner1": pack_conv2d_gtc(fw.inner1.reshape(1, 48, 16)).to(device),
+             "inner2": pack_conv2d_gtc(fw.inner2.reshape(1, 24, 8)).to(device)}
+    return fw
 
 
 @dataclass

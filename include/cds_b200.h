@@ -197,6 +197,18 @@ int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const f
 int cds_conv2d_1x1_cat(const void* a, const double* a_stats, int a_act, const void* b, const double* b_stats, int b_act,
                        const float* wgt, int n, int Ca, int Cb, int Cout, int H, int W, int dtype, void* out,
                        double* out_stats, cudaStream_t stream);
+/* Tensor-core (tcgen05) forms of the two plain 2-D convs above, fp16 storage (csrc/conv2d_gtc.cu): same semantics, the
+ * operand is gathered + normalised per output pixel; wgt_packed = fp16 image [mma][k-chunk 2][2*Cout/8][8 n][8 k] with the
+ * weights' fp16 rounding residual in columns [Cout, 2*Cout) (host: weights.py pack_conv2d_gtc). */
+int cds_conv2d_3x3s2_tc_supported(int Cin, int Cout);
+int cds_conv2d_3x3s2_tc_weight_halfs(int Cin, int Cout);
+int cds_conv2d_3x3s2_tc(const void* in, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin, int Cout, int H,
+                        int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
+int cds_conv2d_1x1_cat_tc_supported(int Ca, int Cb, int Cout);
+int cds_conv2d_1x1_cat_tc_weight_halfs(int Ca, int Cb, int Cout);
+int cds_conv2d_1x1_cat_tc(const void* a, const double* a_stats, int a_act, const void* b, const double* b_stats, int b_act,
+                          const void* wgt_packed, int n, int Ca, int Cb, int Cout, int H, int W, void* out, double* out_stats,
+                          cudaStream_t stream);
 /* InstanceNorm2d(affine=False, eps 1e-5, biased variance) + activation, materialised. */
 int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C, int H, int W, int dtype, void* out,
                      cudaStream_t stream);

@@ -479,6 +479,73 @@ def test_deconv3d_gather_tcgen05_vs_torch(cin, cout, shape, with_skip):
     close(from_blocked(out.float().cpu()), ref, 8e-3, 2e-3)
 
 
+def _in_norm_lrelu(x, eps=1e-5):
+    """InstanceNorm2d(affine=False) + LeakyReLU(0.1) of an NHWC tensor, and the (sum, sumsq) statistics the kernels consume."""
+    m = x.mean(dim=(1, 2), keepdim=True)
+    v = x.var(dim=(1, 2), unbiased=False, keepdim=True)
+    y = torch.nn.functional.leaky_relu((x - m) / torch.sqrt(v + eps), 0.1)
+    stats = torch.stack((x.double().sum(dim=(1, 2)), (x.double() ** 2).sum(dim=(1, 2))), dim=-1)   # [n, C, 2]
+    return y, stats.contiguous()
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 16), (16, 32)])
+@pytest.mark.parametrize("hw", [(32, 40), (37, 51), (64, 130)])
+def test_conv2d_3x3s2_tcgen05_vs_torch(cin, cout, hw):
+    """FeatureNet.downsample1/2 on the tensor cores: InstanceNorm + LeakyReLU applied on load, 3x3 stride-2 conv, raw output +
+    statistics, against torch on the same fp16-stored input (odd sizes: ceil(n/2) outputs, partial tiles, borders)."""
+    H, Wd = hw
+    torch.manual_seed(cin + H)
+    x = (torch.randn(3, H, Wd, cin) * 2 + 0.5).half().float()
+    w = torch.randn(cout, cin, 3, 3) / (9 * cin) ** 0.5
+    xn, stats = _in_norm_lrelu(x)
+    ref = torch.nn.functional.conv2d(xn.permute(0, 3, 1, 2), w, stride=2, padding=1).permute(0, 2, 3, 1).contiguous()
+    packed = cu(W.pack_conv2d_gtc(w.permute(2, 3, 1, 0).reshape(9, cin, cout)))
+    lib = _lib.LIB.load()
+    assert lib.cds_conv2d_3x3s2_tc_supported(cin, cout) == 1
+    assert packed.numel() == lib.cds_conv2d_3x3s2_tc_weight_halfs(cin, cout)
+    out = torch.full(tuple(ref.shape), float("nan"), device=DEV, dtype=torch.float16)
+    ostats = torch.zeros(3, cout, 2, device=DEV, dtype=torch.float64)
+    xc, sc = cu(x).half(), cu(stats)     # named: a temporary inside the argument list would be freed before the launch
+    out_lo = torch.full_like(out, float("nan"))
+    call("cds_conv2d_3x3s2_tc", ptr(xc), ptr(sc), _lib.ACT_LRELU, ptr(packed), 3, cin, cout, H, Wd, ptr(out), ptr(out_lo), ptr(ostats))
+    torch.cuda.synchronize()
+    # value + residual planes together carry the fp32 result to ~22 bits
+    close(out.float().cpu() + out_lo.float().cpu(), ref, 3e-4, 1e-4)
+    # operands are rounded to fp16 after normalisation (|x| <~ 4 -> 1e-3 abs), 9*cin terms
+    close(out.float().cpu(), ref, 6e-3, 2e-3)
+    ref_stats = torch.stack((ref.double().sum(dim=(1, 2)), (ref.double() ** 2).sum(dim=(1, 2))), dim=-1)
+    torch.testing.assert_close(ostats.cpu(), ref_stats, atol=0.02 * ref[0, :, :, 0].numel() ** 0.5, rtol=5e-3)
+
+
+@pytest.mark.parametrize("ca,cb,cout,a_norm", [(32, 16, 16, True), (16, 8, 8, False)])
+@pytest.mark.parametrize("hw", [(32, 40), (38, 50), (64, 130)])
+def test_conv2d_1x1_cat_tcgen05_vs_torch(ca, cb, cout, a_norm, hw):
+    """FeatureNet.inner1/2 on the tensor cores: 1x1 conv over cat(nearest-up2(a), b), both normalised on load (inner2 takes
+    the already-activated stage-2 feature as is)."""
+    H, Wd = hw
+    torch.manual_seed(ca + H)
+    a = (torch.randn(2, H // 2, Wd // 2, ca) * (2 if a_norm else 0.5)).half().float()
+    b = (torch.randn(2, H, Wd, cb) * 3 - 1).half().float()
+    w = torch.randn(ca + cb, cout) / (ca + cb) ** 0.5
+    an, a_stats = _in_norm_lrelu(a) if a_norm else (a, None)
+    bn, b_stats = _in_norm_lrelu(b)
+    up = an.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    ref = torch.cat((up, bn), dim=-1) @ w
+    packed = cu(W.pack_conv2d_gtc(w.reshape(1, ca + cb, cout)))
+    lib = _lib.LIB.load()
+    assert lib.cds_conv2d_1x1_cat_tc_supported(ca, cb, cout) == 1
+    assert packed.numel() == lib.cds_conv2d_1x1_cat_tc_weight_halfs(ca, cb, cout)
+    out = torch.full(tuple(ref.shape), float("nan"), device=DEV, dtype=torch.float16)
+    ostats = torch.zeros(2, cout, 2, device=DEV, dtype=torch.float64)
+    ac, bc, asc, bsc = cu(a).half(), cu(b).half(), (cu(a_stats) if a_norm else None), cu(b_stats)
+    call("cds_conv2d_1x1_cat_tc", ptr(ac), ptr(asc), _lib.ACT_LRELU if a_norm else _lib.ACT_NONE,
+         ptr(bc), ptr(bsc), _lib.ACT_LRELU, ptr(packed), 2, ca, cb, cout, H, Wd, ptr(out), ptr(ostats))
+    torch.cuda.synchronize()
+    close(out.float().cpu(), ref, 6e-3, 2e-3)
+    ref_stats = torch.stack((ref.double().sum(dim=(1, 2)), (ref.double() ** 2).sum(dim=(1, 2))), dim=-1)
+    torch.testing.assert_close(ostats.cpu(), ref_stats, atol=0.02 * ref[0, :, :, 0].numel() ** 0.5, rtol=5e-3)
+
+
 @pytest.mark.parametrize("st", [0, 1, 2])
 @pytest.mark.parametrize("hw", [(37, 200), (8, 128), (21, 300), (32, 40), (19, 100)])
 def test_visnet_tcgen05_vs_oracle(pretrained_sd, st, hw):
