@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
         const int r = lg * 32 + lane;            // MMA row = pixel x0 + r (valid while r < TXO)
         const int gx = x0 + r;
         const float ex = __ldg(p.epipole + 2 * n) * p.epi_scale, ey = __ldg(p.epipole + 2 * n + 1) * p.epi_scale;
-        constexpr bool REG_STATS = COUT <= 16;   // per-thread statistics accumulators only while they fit in registers
+        constexpr bool REG_STATS = true;   // per-thread statistics accumulators only while they fit in registers
         float st_sum[REG_STATS ? COUT : 1], st_sq[REG_STATS ? COUT : 1];
 #pragma unroll
         for (int c = 0; c < (REG_STATS ? COUT : 1); ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
