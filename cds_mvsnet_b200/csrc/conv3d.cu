@@ -213,22 +213,46 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const float* __res
     int b = (int)(i / P);
     long long p = i % P;
     const float* lp = logits + (size_t)b * D * P + p;
-    float m = 0.f, S = 1.f;
-    if (!is_prob) {
+    const float* dpp = per_pixel ? depth + (size_t)b * D * P + p : depth + (size_t)b * D;
+    const size_t dstride = per_pixel ? (size_t)P : 1;
+    float m = 0.f, inv = 1.f, ed = 0.f, ei = 0.f;
+    if (!is_prob && !prob_out) {
+        // one pass, online softmax: running max m, S = sum e^(l-m), and the two expectations rescaled together
+        float S = 0.f;
         m = -INFINITY;
-        for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(lp + (size_t)d * P));
-        S = 0.f;
-        for (int d = 0; d < D; ++d) S += __expf(__ldg(lp + (size_t)d * P) - m);
-    }
-    float inv = 1.f / S;
-    float ed = 0.f, ei = 0.f;
-    for (int d = 0; d < D; ++d) {
-        float l = __ldg(lp + (size_t)d * P);
-        float pr = is_prob ? l : __expf(l - m) * inv;
-        float dep = per_pixel ? __ldg(depth + (size_t)b * D * P + (size_t)d * P + p) : __ldg(depth + (size_t)b * D + d);
-        ed += pr * dep;
-        ei += pr * (float)d;
-        if (prob_out) prob_out[(size_t)b * D * P + (size_t)d * P + p] = pr;
+        for (int d = 0; d < D; ++d) {
+            const float l = __ldg(lp + (size_t)d * P);
+            const float dep = __ldg(dpp + (size_t)d * dstride);
+            if (l > m) {
+                const float r = __expf(m - l);   // 0 on the first plane (m = -inf)
+                S *= r; ed *= r; ei *= r;
+                m = l;
+            }
+            const float e = __expf(l - m);
+            S += e;
+            ed += e * dep;
+            ei += e * (float)d;
+        }
+        inv = 1.f / S;
+        ed *= inv;
+        ei *= inv;
+    } else {
+        float S = 1.f;
+        if (!is_prob) {
+            m = -INFINITY;
+            for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(lp + (size_t)d * P));
+            S = 0.f;
+            for (int d = 0; d < D; ++d) S += __expf(__ldg(lp + (size_t)d * P) - m);
+        }
+        inv = 1.f / S;
+        for (int d = 0; d < D; ++d) {
+            float l = __ldg(lp + (size_t)d * P);
+            float pr = is_prob ? l : __expf(l - m) * inv;
+            float dep = __ldg(dpp + (size_t)d * dstride);
+            ed += pr * dep;
+            ei += pr * (float)d;
+            if (prob_out) prob_out[(size_t)b * D * P + (size_t)d * P + p] = pr;
+        }
     }
     if (depth_out) depth_out[i] = ed;
     if (conf_out) {
