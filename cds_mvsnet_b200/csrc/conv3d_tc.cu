@@ -271,25 +271,37 @@ __global__ void __launch_bounds__(128) deconv3d_tc_kernel(const __grid_constant_
     const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
     const size_t Mo = (size_t)Do * Ho * Wo;
     const bool own = r < TXI && xi < p.W && xi >= (int)blockIdx.x * TXI;   // tiles overlap at the right edge: one owner per voxel
+    float bias[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bias[c] = __ldg(p.bias + c);
 #pragma unroll 1
     for (int u = 0; u < TY; ++u) {
         const int yi = y0 + u;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)u * N;
+        const bool live = own && yi < p.H;
+        const size_t o000 = ((size_t)(2 * d) * Ho + 2 * yi) * Wo + 2 * xi;   // output voxel of parity (0,0,0)
 #pragma unroll
-        for (int par = 0; par < 8; ++par) {
-            const int pd = par >> 2, ph = (par >> 1) & 1, pw = par & 1;
+        for (int c8 = 0; c8 < COUT / 8; ++c8) {
+            // the whole 2x2x2 cell of skip values is fetched up front: the loads do not depend on the accumulators, and a
+            // DRAM round trip per parity class in the store loop's critical path is what used to bound this kernel
+            uint4 sk[8];
 #pragma unroll
-            for (int c8 = 0; c8 < COUT / 8; ++c8) {
+            for (int par = 0; par < 8; ++par) {
+                const size_t o = ((size_t)c8 * Mo + o000 + ((size_t)(par >> 2) * Ho + ((par >> 1) & 1)) * Wo + (par & 1)) * 8;
+                sk[par] = (live && p.skip) ? __ldcs(reinterpret_cast<const uint4*>(p.skip + o)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int par = 0; par < 8; ++par) {
                 float v[8];
                 tc::tmem_ld8(taddr + par * COUT + c8 * 8, v);
-                if (own && yi < p.H) {
-                    const size_t o = ((size_t)c8 * Mo + ((size_t)(2 * d + pd) * Ho + 2 * yi + ph) * Wo + 2 * xi + pw) * 8;
-                    float sk[8];
-                    if (p.skip) Vec8<__half>::load(p.skip + o, sk);
+                if (live) {
+                    const size_t o = ((size_t)c8 * Mo + o000 + ((size_t)(par >> 2) * Ho + ((par >> 1) & 1)) * Wo + (par & 1)) * 8;
+                    const __half2* sh = reinterpret_cast<const __half2*>(&sk[par]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float t = fmaxf(v[i] + __ldg(p.bias + c8 * 8 + i), 0.f);
-                        v[i] = p.skip ? sk[i] + t : t;
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 s2 = __half22float2(sh[i]);
+                        v[2 * i] = s2.x + fmaxf(v[2 * i] + bias[c8 * 8 + 2 * i], 0.f);
+                        v[2 * i + 1] = s2.y + fmaxf(v[2 * i + 1] + bias[c8 * 8 + 2 * i + 1], 0.f);
                     }
                     Vec8<__half>::store(p.out + o, v);
                 }
