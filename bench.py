@@ -333,7 +333,12 @@ def main():
         roof = {"bound": "tensor", "achieved": top["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": top["tflops"] / pk["tensor"]}
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": top["gbs"] / pk["hbm"]}
-    roof.update({"traffic": None, "kernel": f"{top['kernel']}[{top['tag']}]", "share_of_step": top["share"],
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram read + write bytes per launch)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{top['kernel']}[{top['tag']}]@{args.workload}")
+    roof.update({"traffic": traffic, "kernel": f"{top['kernel']}[{top['tag']}]", "share_of_step": top["share"],
                  "ms_per_launch": top["ms_per_launch"], "peak_source": pk["src"],
                  "algorithmic": {"gflop_per_launch": top["alg_gflop"], "mb_per_launch": top["alg_mb"]}})
     if args.kernel_table:
