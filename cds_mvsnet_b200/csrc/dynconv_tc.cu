@@ -96,6 +96,7 @@ struct DynTcParams {
     float* nc_sq;             // [n][H][W] or NULL
     float* nc_abs;            // [n][H][W] or NULL
     int in_act, nc_mode, H, W;
+    int pair_v, pair_b;       // GRP > 1: items are (side, v, b); the side-0 items v*pair_b + b of batch item b share one image
     float epi_scale, inv_temperature;
 };
 
@@ -147,8 +148,13 @@ __device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uin
 // SPLIT: the input arrives as two fp16 planes (value + rounding residual, i.e. ~22-bit activations); both are normalised
 // together, re-split and fed to the tensor cores as twice as many K slabs (same weights).  Used for the layers the
 // depth output is most sensitive to (conv10, conv11).
-template <class C, int TY, bool SPLIT>
-__global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+// GRP > 1 (conv00): the batch is (side, v, b) pairs of (reference image seen with pair v's epipole, source image v).  The
+// reference image's branch convolutions do not depend on the epipole -- only the gate does -- so one CTA
+// runs the MMAs of a reference tile ONCE and its epilogue up to GRP times, once per pair: 5 instead of 8 images' worth of
+// tensor work at N = 5.
+template <class C, int TY, bool SPLIT, int GRP = 1>
+__global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+    static_assert(GRP == 1 || (C::COUT == 8 && !SPLIT), "shared-image groups are implemented for the 8-channel image layer");
     constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO, C8 = C::C8, CIN = C::CIN, COUT = C::COUT, NPAD = C::NPAD;
     constexpr int ROWS = TY + 2 * HALO;
     constexpr uint32_t CHUNK = ROWS * ROW_BYTES;                    // one 8-channel slab of the window
@@ -166,12 +172,24 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
     uint64_t* bar_empty = bar_load + 3;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
     float* s_norm = reinterpret_cast<float*>(bar_load + 6);   // [CIN][2] mean, rstd
-    float* s_red = s_norm + 2 * CIN;                          // [4 warps][COUT][2]
-    float* s_gate = s_red + 4 * COUT * 2;                     // W1f [4][NK], b1 [4], W2 [NK][4]  (<= 28 floats)
+    float* s_red = s_norm + 2 * CIN;                          // [GRP][4 warps][COUT][2]
+    float* s_gate = s_red + GRP * 4 * COUT * 2;               // W1f [4][NK], b1 [4], W2 [NK][4]  (<= 28 floats)
     float* s_bias = s_gate + 28;                              // [NK][COUT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.z;
+    // items of this CTA: n, n + nstr, ... (cnt of them); they all read image img_index[n]
+    int n = blockIdx.z, cnt = 1, nstr = 0;
+    if constexpr (GRP > 1) {
+        const int parts = (p.pair_v + GRP - 1) / GRP, z = blockIdx.z;
+        if (z < p.pair_b * parts) {
+            const int v0 = (z / p.pair_b) * GRP;
+            n = v0 * p.pair_b + z % p.pair_b;
+            cnt = min(GRP, p.pair_v - v0);
+            nstr = p.pair_b;
+        } else {
+            n = p.pair_v * p.pair_b + (z - p.pair_b * parts);
+        }
+    }
     const int x0 = max(0, min((int)blockIdx.x * TXO, p.W - TXO));   // last tile overlaps its neighbour; W < TXO: one partial tile
     const int y0 = blockIdx.y * TY;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
@@ -197,7 +215,7 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + 8 * NK + 4) s_gate[threadIdx.x - 96] = __ldg(p.gate + threadIdx.x - 96);
     if (threadIdx.x >= 128 && threadIdx.x < 128 + NK * COUT) s_bias[threadIdx.x - 128] = p.bias ? __ldg(p.bias + threadIdx.x - 128) : 0.f;
-    for (int i = threadIdx.x; i < 4 * COUT * 2; i += 192) s_red[i] = 0.f;
+    for (int i = threadIdx.x; i < GRP * 4 * COUT * 2; i += 192) s_red[i] = 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -278,6 +296,116 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
             issue_unit<C, (int)CHUNK, SPLIT>(a_base, sB_u >> 4, acc, elected);
             if (elected) tc::mma_commit(bar_full + s);
             __syncwarp();
+        }
+    } else if (warp >= 2 && GRP > 1) {
+        // ---- epilogue of a shared-image group: the accumulators of a row unit are pulled into registers once (which frees
+        // the TMEM stage at once), then gated / blended / stored once per item of the group with that item's epipole ---------
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane;
+        const int gx = x0 + r;
+        float ex[GRP], ey[GRP];
+#pragma unroll
+        for (int it = 0; it < GRP; ++it) {
+            const int nn = n + min(it, cnt - 1) * nstr;
+            ex[it] = __ldg(p.epipole + 2 * nn) * p.epi_scale;
+            ey[it] = __ldg(p.epipole + 2 * nn + 1) * p.epi_scale;
+        }
+        float st_sum[GRP][COUT], st_sq[GRP][COUT];
+#pragma unroll
+        for (int it = 0; it < GRP; ++it)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) { st_sum[it][c] = 0.f; st_sq[it][c] = 0.f; }
+#pragma unroll 1
+        for (int u = 0; u < TY; ++u) {
+            const int s = u % (int)NSTG;
+            tc::mbar_wait(bar_full + s, (u / (int)NSTG) & 1);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
+            uint32_t ar[NK][8], yr[NK][8];
+#pragma unroll
+            for (int b = 0; b < NK; ++b) {
+                tc::tmem_ld8_nowait(taddr + b * NPAD + C::FCOLS, ar[b]);
+                tc::tmem_ld8_nowait(taddr + b * NPAD, yr[b]);
+            }
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + s);   // everything is in registers: the stage may be refilled
+            const int gy = y0 + u;
+            const bool valid = r < TXO && gy < p.H && gx < p.W && gx >= (int)blockIdx.x * TXO;
+            float ca[NK], cb[NK], cc[NK], yb[NK][8];
+#pragma unroll
+            for (int b = 0; b < NK; ++b) {
+                ca[b] = __uint_as_float(ar[b][0]) + __uint_as_float(ar[b][3]);
+                cb[b] = __uint_as_float(ar[b][1]) + __uint_as_float(ar[b][4]);
+                cc[b] = __uint_as_float(ar[b][2]) + __uint_as_float(ar[b][5]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) yb[b][c] = __uint_as_float(yr[b][c]) + s_bias[b * COUT + c];
+            }
+#pragma unroll
+            for (int it = 0; it < GRP; ++it) {
+                if (it < cnt) {   // warp-uniform
+                    float uu = (float)gx - ex[it], vv = (float)gy - ey[it];
+                    const float rinv = __frcp_rn(sqrtf(uu * uu + vv * vv) + 1e-6f);
+                    uu *= rinv;
+                    vv *= rinv;
+                    float curv[NK];
+#pragma unroll
+                    for (int b = 0; b < NK; ++b) curv[b] = (ca[b] * (uu * uu) + cb[b] * (2.f * uu * vv)) + cc[b] * (vv * vv);
+                    float hdn[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = s_gate[4 * NK + j];
+#pragma unroll
+                        for (int b = 0; b < NK; ++b) t += s_gate[j * NK + b] * curv[b];
+                        hdn[j] = fmaxf(t, 0.f);
+                    }
+                    float wgt[NK], mx = -INFINITY;
+#pragma unroll
+                    for (int b = 0; b < NK; ++b) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) t += s_gate[4 * NK + 4 + b * 4 + j] * hdn[j];
+                        wgt[b] = t * p.inv_temperature;
+                        mx = fmaxf(mx, wgt[b]);
+                    }
+                    float den = 0.f, nc = 0.f;
+#pragma unroll
+                    for (int b = 0; b < NK; ++b) { wgt[b] = __expf(wgt[b] - mx); den += wgt[b]; }
+                    const float dinv = __frcp_rn(den);
+#pragma unroll
+                    for (int b = 0; b < NK; ++b) { wgt[b] *= dinv; nc += curv[b] * wgt[b]; }
+                    float out[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) out[c] = 0.f;
+#pragma unroll
+                    for (int b = 0; b < NK; ++b)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) out[c] += wgt[b] * yb[b][c];
+                    if (valid) {
+                        const size_t m = ((size_t)(n + it * nstr) * p.H + gy) * p.W + gx;
+                        Vec8<__half>::store(p.out_raw + m * COUT, out);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) { st_sum[it][c] += out[c]; st_sq[it][c] += out[c] * out[c]; }
+                        if (p.norm_curv) p.norm_curv[m] = nc;
+                        if (p.nc_sq) {
+                            if (p.nc_mode == 0) p.nc_sq[m] = nc * nc;
+                            else if (p.nc_mode == 1) p.nc_sq[m] = p.nc_sq[m] + nc * nc;
+                            else p.nc_sq[m] = (p.nc_sq[m] + nc * nc) / 3.f;
+                        }
+                        if (p.nc_abs) p.nc_abs[m] = fabsf(nc);
+                    }
+                }
+            }
+        }
+        if (p.out_stats) {
+#pragma unroll
+            for (int it = 0; it < GRP; ++it)
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    const float a = warp_sum(st_sum[it][c]), q = warp_sum(st_sq[it][c]);
+                    if (lane == 0) { s_red[((it * 4 + lg) * COUT + c) * 2] = a; s_red[((it * 4 + lg) * COUT + c) * 2 + 1] = q; }
+                }
         }
     } else if (warp >= 2) {
         // ---- epilogue: gate + blend, one pixel per thread ---------------------------------------------------------
@@ -428,10 +556,11 @@ __global__ void __launch_bounds__(192, (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2)) dy
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (p.out_stats && threadIdx.x < COUT * 2) {
+    if (p.out_stats && threadIdx.x < cnt * COUT * 2) {
+        const int it = threadIdx.x / (COUT * 2), j = threadIdx.x % (COUT * 2);
         double t = 0.0;
-        for (int w = 0; w < 4; ++w) t += (double)s_red[w * COUT * 2 + threadIdx.x];
-        atomicAdd(p.out_stats + (size_t)n * COUT * 2 + threadIdx.x, t);
+        for (int w = 0; w < 4; ++w) t += (double)s_red[(it * 4 + w) * COUT * 2 + j];
+        atomicAdd(p.out_stats + (size_t)(n + it * nstr) * COUT * 2 + j, t);
     }
     if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -456,13 +585,13 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long H
     }
 }
 
-template <class C, int TY, bool SPLIT = false>
+template <class C, int TY, bool SPLIT = false, int GRP = 1>
 int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cudaStream_t st) {
     constexpr size_t smem = (size_t)(SPLIT ? 2 : 1) * C::C8 * (TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 +
-                            (2 * C::CIN + 8 * C::COUT + 28 + C::NK * C::COUT) * 4 + 16;
+                            (2 * C::CIN + GRP * 8 * C::COUT + 28 + C::NK * C::COUT) * 4 + 16;
     static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
     static_assert(!SPLIT || C::C8 > 1, "split-precision input is implemented for the multi-chunk layers");
-    auto kern = dynconv_tc_kernel<C, TY, SPLIT>;
+    auto kern = dynconv_tc_kernel<C, TY, SPLIT, GRP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cds_set_error("cds_dynamic_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     CUtensorMap tmap;
@@ -480,7 +609,9 @@ int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cuda
         ok = tma::make_f16(&tmap, x, 5, dims, strides, box);
     }
     if (!ok) return CDS_EUNSUPPORTED;
-    dim3 grid(cds_div_up(p.W, C::TXO), cds_div_up(p.H, TY), n);
+    // GRP > 1: one CTA column per group of up to GRP same-image items + one per remaining (source image) item
+    const int nz = GRP > 1 ? p.pair_b * ((p.pair_v + GRP - 1) / GRP) + p.pair_v * p.pair_b : n;
+    dim3 grid(cds_div_up(p.W, C::TXO), cds_div_up(p.H, TY), nz);
     kern<<<grid, 192, smem, st>>>(tmap, p);
     return cds_check_launch("cds_dynamic_conv_tc");
 }
@@ -524,11 +655,40 @@ int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const i
     return (mma_in * 2 * (num_kernels * npad) + mma_ring * 2 * npad) * 8;
 }
 
+static int dynamic_conv_tc_impl(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
+                        const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
+                        int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
+                        int split_in, void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq,
+                        int nc_mode, float* nc_abs, int pair_v, int pair_b, cudaStream_t stream);
+
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
                         const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
                         int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
                         int split_in, void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq,
                         int nc_mode, float* nc_abs, cudaStream_t stream) {
+    return dynamic_conv_tc_impl(x, n_images, img_index, in_stats, in_act, epipole, epi_scale, wgt_packed, bias, gate, n, Cin, Cout, H, W,
+                                num_kernels, kernel_sizes, temperature, split_in, out_raw, out_lo, out_stats, norm_curv, nc_sq, nc_mode,
+                                nc_abs, 0, 0, stream);
+}
+
+// The image layer (conv00) over the (side, v, b) pair batch of the cascade: n = 2*V*B items, item (0, v, b) = the reference
+// image of batch item b seen with pair v's epipole, item (1, v, b) = source image v; img_index must map the V side-0 items of
+// a batch item to one image.  Same results as cds_dynamic_conv_tc; the reference image's convolutions run once per batch item.
+int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index, const float* epipole, float epi_scale,
+                              const void* wgt_packed, const float* bias, const float* gate, int V, int B, int Cin, int Cout, int H, int W,
+                              int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, double* out_stats,
+                              float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream) {
+    CDS_REQUIRE(V >= 1 && B >= 1 && img_index, CDS_EARG, "cds_dynamic_conv_tc_pairs: bad pair batch");
+    return dynamic_conv_tc_impl(x, n_images, img_index, nullptr, 0, epipole, epi_scale, wgt_packed, bias, gate, 2 * V * B, Cin, Cout, H, W,
+                                num_kernels, kernel_sizes, temperature, 0, out_raw, nullptr, out_stats, norm_curv, nc_sq, nc_mode, nc_abs,
+                                V, B, stream);
+}
+
+static int dynamic_conv_tc_impl(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,
+                        const float* epipole, float epi_scale, const void* wgt_packed, const float* bias, const float* gate,
+                        int n, int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
+                        int split_in, void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq,
+                        int nc_mode, float* nc_abs, int pair_v, int pair_b, cudaStream_t stream) {
     CDS_REQUIRE(x && epipole && wgt_packed && gate && out_raw && kernel_sizes, CDS_EARG, "cds_dynamic_conv_tc: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && n_images > 0, CDS_ESHAPE, "cds_dynamic_conv_tc: bad batch");
     CDS_REQUIRE(temperature > 0.f, CDS_EARG, "cds_dynamic_conv_tc: temperature must be positive");
@@ -542,7 +702,12 @@ int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const
     p.inv_temperature = 1.f / temperature;
     p.out_lo = (__half*)out_lo;
     p.in_lo_images = n_images;
+    p.pair_v = pair_v; p.pair_b = pair_b;
     const int lid = layer_id(Cin, Cout, num_kernels, kernel_sizes);
+    if (pair_v > 0) {
+        CDS_REQUIRE(lid == 1 && !in_stats, CDS_EUNSUPPORTED, "cds_dynamic_conv_tc_pairs: implemented for the image layer (3,7,11)");
+        return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8, false, 4>(x, n_images, p, n, stream);
+    }
     if (split_in) {
         CDS_REQUIRE(lid == 4 && in_stats, CDS_EUNSUPPORTED,
                     "cds_dynamic_conv_tc: split-precision input is implemented for the 16->16 (3,5) layers with input statistics");

@@ -70,6 +70,8 @@ class FeatureExtractor:
         self.split_precision = os.environ.get("CDS_SPLIT", "0") == "1"
         self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
         self._buf = None
+        self.pairs = None   # (V, B) when the batch is the cascade's (side, v, b) pair batch
+        self.share_ref = os.environ.get("CDS_SHARE_REF", "1") != "0"
 
     def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
              nc_mode, nc_abs, norm_curv=None, split_in=False, out_lo=None):
@@ -88,6 +90,12 @@ class FeatureExtractor:
                 img8 = self._buf.get("f.img8", (n_images, H, W, 8), torch.float16)
                 call("cds_image_to_nhwc8", ptr(x), n_images, H, W, ptr(img8))
                 x = img8
+            if in_mode == 1 and self.pairs is not None and self.share_ref and not split_in:
+                V, B = self.pairs   # the reference image's convolutions are shared by its V pairs
+                call("cds_dynamic_conv_tc_pairs", ptr(x), n_images, ptr(img_index), ptr(epi), float(epi_scale), ptr(w.tc), ptr(w.bias),
+                     ptr(w.gate), V, B, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T), ptr(out), ptr(out_stats),
+                     ptr(norm_curv), ptr(nc_sq), nc_mode, ptr(nc_abs))
+                return
             call("cds_dynamic_conv_tc", ptr(x), n_images, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
                  ptr(w.tc), ptr(w.bias), ptr(w.gate), n, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T),
                  int(split_in), ptr(out), ptr(out_lo), ptr(out_stats),
@@ -129,11 +137,12 @@ class FeatureExtractor:
         return bool(self.use_tc and self.split_precision and w.tc is not None and self.storage == torch.float16
                     and _lib.LIB.load().cds_dynamic_conv_tc_supported(16, 16, H2, W2, 2, _ksizes(w.ksizes)))
 
-    def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature):
+    def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature, pairs=None):
         """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
         Returns {stage: (fea [n,h,w,C] storage dtype, nc_sq [n,h,w] fp32, nc_abs [n,h,w] fp32)}."""
         st, dt = self.storage, self.dt
         self._buf = buf
+        self.pairs = pairs
         imgs = imgs.reshape(-1, 3, H, W)
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         e = _esize(st)
@@ -390,7 +399,7 @@ class CascadeEngine:
                     idx[1, v, b] = b * N + v + 1
             self._imgidx = idx.reshape(-1).to(dev)
             self._imgidx_key = key
-        feats = self.features.run(self.buf, imgs, self._imgidx, epi, n, H, W, temperature)
+        feats = self.features.run(self.buf, imgs, self._imgidx, epi, n, H, W, temperature, pairs=(V, B))
         outputs, depth = {}, None
         for s in range(len(self.ndepths)):
             o = self.stage(s, feats[s], coef[s], depth_values, depth, B, V, H, W)

@@ -190,6 +190,14 @@ int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const
                         int split_in, void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq,
                         int nc_mode, float* nc_abs, cudaStream_t stream);
 /* FeatureNet.downsample1/2 (models/module.py:214,218): 3x3 stride 2 pad 1, wgt [9][Cin][Cout]. */
+/* The image layer (conv00) over the cascade's pair batch: n = 2*V*B items ordered (side, v, b), item (0,v,b) = the reference
+ * image of batch item b seen with pair v's epipole (models/model.py:154-161 recomputes it per pair), item (1,v,b) = source
+ * image v; img_index maps the V side-0 items of a batch item to one image.  Results equal cds_dynamic_conv_tc on the same
+ * batch; the reference image's branch convolutions (which do not depend on the epipole) run once per batch item. */
+int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index, const float* epipole, float epi_scale,
+                              const void* wgt_packed, const float* bias, const float* gate, int V, int B, int Cin, int Cout, int H, int W,
+                              int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, double* out_stats,
+                              float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream);
 int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
                      int W, int dtype, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
 /* FeatureNet.inner1/2 (models/module.py:253-254,260-261): 1x1 conv over cat(nearest-up2(a), b);

@@ -359,6 +359,52 @@ def test_dynamic_conv_tcgen05_vs_oracle(pretrained_sd, name, hw):
     assert O.rel_l1(outs[True][0], outs[False][0]) < 4e-3
 
 
+@pytest.mark.parametrize("V,B,hw", [(4, 1, (24, 150)), (2, 2, (17, 130)), (5, 1, (8, 40)), (1, 1, (9, 128))])
+def test_dynamic_conv_pairs_matches_plain(pretrained_sd, V, B, hw):
+    """conv00 over the cascade's (side, v, b) pair batch with the reference image's convolutions shared between its V pairs
+    (cds_dynamic_conv_tc_pairs) against the plain per-item entry on the same batch: same kernels, so agreement is to
+    fp32 re-association of the statistics only."""
+    import ctypes
+    cin, cout, ks, pre = W.DYN_LAYERS["conv00"]
+    H, Wd = hw
+    torch.manual_seed(V * 10 + B)
+    N = V + 1
+    imgs = torch.rand(B * N, 3, H, Wd)
+    n = 2 * V * B
+    idx = torch.empty(2, V, B, dtype=torch.int32)
+    for v in range(V):
+        for b in range(B):
+            idx[0, v, b], idx[1, v, b] = b * N, b * N + v + 1
+    epi = torch.randn(n, 2) * Wd
+    w = W.pack_dynamic_conv(pretrained_sd, pre, cin, cout, ks, DEV)
+    w.tc = W.pack_dynamic_conv_tc(w)
+    img8 = torch.empty(B * N, H, Wd, 8, device=DEV, dtype=torch.float16)
+    imgs_c, idx_c, epi_c = cu(imgs), cu(idx.reshape(-1)), cu(epi)
+    call("cds_image_to_nhwc8", ptr(imgs_c), B * N, H, Wd, ptr(img8))
+    kz = (ctypes.c_int * 3)(*ks)
+    res = []
+    for pairs in (False, True):
+        out = torch.full((n, H, Wd, cout), float("nan"), device=DEV, dtype=torch.float16)
+        stats = torch.zeros(n, cout, 2, device=DEV, dtype=torch.float64)
+        nc = torch.full((n, H, Wd), float("nan"), device=DEV)
+        ncsq = torch.full((n, H, Wd), float("nan"), device=DEV)
+        if pairs:
+            call("cds_dynamic_conv_tc_pairs", ptr(img8), B * N, ptr(idx_c), ptr(epi_c), 1.0, ptr(w.tc), ptr(w.bias), ptr(w.gate), V, B,
+                 8, cout, H, Wd, 3, kz, T, ptr(out), ptr(stats), ptr(nc), ptr(ncsq), 0, None)
+        else:
+            call("cds_dynamic_conv_tc", ptr(img8), B * N, ptr(idx_c), None, 0, ptr(epi_c), 1.0, ptr(w.tc), ptr(w.bias), ptr(w.gate), n,
+                 8, cout, H, Wd, 3, kz, T, 0, ptr(out), None, ptr(stats), ptr(nc), ptr(ncsq), 0, None)
+        torch.cuda.synchronize()
+        res.append((out.float().cpu(), stats.cpu(), nc.cpu(), ncsq.cpu()))
+    assert torch.equal(res[0][0], res[1][0])                      # same MMAs, same epilogue arithmetic
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-6, atol=1e-3)
+    # and both follow the oracle
+    x_items = torch.stack([imgs[int(i)] for i in idx.reshape(-1)])
+    ref_y, _ = O.dynamic_conv(x_items, pretrained_sd, pre, ks, epi, T)
+    assert O.rel_l1(res[1][0].permute(0, 3, 1, 2), ref_y) < 4e-3
+
+
 def test_prob_head_tcgen05_vs_torch():
     """8 -> 1 prob conv on the tensor cores (hi + residual fp16 weights) against the published operator."""
     torch.manual_seed(11)
