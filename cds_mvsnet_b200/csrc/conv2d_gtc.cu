@@ -5,7 +5,7 @@
 // (models/module.py:66-69), and emit raw output + per-(image, channel) sum / sum-of-squares for the next consumer.
 //
 // One CTA walks kTiles tiles of 128 consecutive output pixels of one image; thread r owns pixel r of the tile:
-//   1. gather: for every K slab (tap x 8-channel chunk) the thread loads its pixel's 16 bytes, normalises, activates,
+//   1. gather (issued one tile ahead): for every K slab (tap x 8-channel chunk) the thread loads its pixel's 16 bytes, normalises, activates,
 //      rounds to fp16 and stores them at [slab][r] of the tcgen05 K-major no-swizzle A image (zero outside the image:
 //      the conv pads the ACTIVATED tensor);
 //   2. one elected thread issues the MMAs (M = 128, K = 16 = two slabs, N = 2*Cout) into TMEM and commits;
@@ -130,17 +130,11 @@ __global__ void __launch_bounds__(128) conv2d_gtc_kernel(const G2Params p) {
     const __half* a_img = p.a + (size_t)n * (MODE == 0 ? (size_t)p.Hi * p.Wi : (size_t)(p.Ho / 2) * (p.Wo / 2)) * CA;
     const __half* b_img = MODE == 1 ? p.b + (size_t)n * P * CB : nullptr;
 
-#pragma unroll 1
-    for (int t = 0; t < kTiles; ++t) {
-        const int m0 = (blockIdx.x * kTiles + t) * 128;
-        if (m0 >= P) break;   // block-uniform
-        const int m = m0 + r;
-        const bool live = m < P;
+    // gather of one tile: the thread's NREAL 16-byte pieces (zeros where the tap falls outside the image / the tile ends)
+    auto gather = [&](int t, uint4 (&raw)[NREAL], bool (&ok)[NREAL]) {
+        const int m = (blockIdx.x * kTiles + t) * 128 + r;
+        const bool live = t < kTiles && m < P;
         const int ox = live ? m % p.Wo : 0, oy = live ? m / p.Wo : 0;
-
-        // ---- 1. gather + normalise -> A image ---------------------------------------------------------------------
-        uint4 raw[NREAL];
-        bool ok[NREAL];
 #pragma unroll
         for (int s = 0; s < NREAL; ++s) {
             const __half* src;
@@ -156,6 +150,23 @@ __global__ void __launch_bounds__(128) conv2d_gtc_kernel(const G2Params p) {
             }
             raw[s] = ok[s] ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
         }
+    };
+    // the NEXT tile's loads are issued before this tile's MMAs / epilogue (when they fit in registers), so that the DRAM
+    // round trip is not in every tile's critical path
+    constexpr bool PREFETCH = NREAL <= 9;
+    uint4 raw[NREAL];
+    bool ok[NREAL];
+    gather(0, raw, ok);
+
+#pragma unroll 1
+    for (int t = 0; t < kTiles; ++t) {
+        const int m0 = (blockIdx.x * kTiles + t) * 128;
+        if (m0 >= P) break;   // block-uniform
+        const int m = m0 + r;
+        const bool live = m < P;
+
+        // ---- 1. normalise -> A image --------------------------------------------------------------------------------
+        if (!PREFETCH && t > 0) gather(t, raw, ok);
 #pragma unroll
         for (int s = 0; s < NREAL; ++s) {
             const int c8 = MODE == 0 ? s % C8 : s;
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(128) conv2d_gtc_kernel(const G2Params p) {
             *reinterpret_cast<uint4*>(sA + s * kSlab + r * 16) = v;
             *reinterpret_cast<uint4*>(sA + (NSLAB + s) * kSlab + r * 16) = lo;
         }
+        if (PREFETCH) gather(t + 1, raw, ok);
         tc::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's operand reads
         tc::tc_fence_before();     // (the previous tile's TMEM loads are ordered before the MMAs below)
         __syncthreads();
