@@ -203,7 +203,8 @@ def main():
 
     storage = getattr(torch, args.storage)
     model = C.CDSMVSNet(refine=False, ndepths=cfg["ndepths"], depth_interals_ratio=cfg["ratios"], storage=storage)
-    model.load_state_dict(load_weights())
+    sd = load_weights()
+    model.load_state_dict({k: v for k, v in sd.items() if k in model.state_dict()})   # fewer stages (cfg1): fewer entries
     model = model.to(dev).eval()
 
     # every rank works on its own depth map (different seed => different work item)
