@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int TX = 128, TXO = TX - 6, TY = 8;
+constexpr int TX = 128, TXO = TX - 6, TY = 4;
 constexpr int ROW_BYTES = TX * 16;
 constexpr int R_IN = TY + 6, R_A1 = TY + 4, R_A2 = TY + 2;
 constexpr uint32_t X_BYTES = 2 * R_A2 * ROW_BYTES;       // in8 (R_IN rows, 1 slab) then a2 (2 slabs x R_A2 rows)
@@ -26,7 +26,7 @@ constexpr uint32_t Y_BYTES = 2 * R_A1 * ROW_BYTES;       // a1
 constexpr int MMA_L1 = 5, MMA_L23 = 9;
 constexpr uint32_t W_BYTES = (MMA_L1 + 2 * MMA_L23) * 2 * 16 * 16;
 static_assert(X_BYTES >= R_IN * ROW_BYTES, "in8 must fit in the region a2 re-uses");
-constexpr uint32_t TMEM_COLS = 256;                      // R_A1 * 16 = 192 columns needed at most
+constexpr uint32_t TMEM_COLS = 128;                      // R_A1 * 16 = 128 columns needed at most
 
 struct VisTcParams {
     const float* entropy;   // [n][H][W]
@@ -89,7 +89,9 @@ __device__ __forceinline__ void act16(uint32_t taddr, const float* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
+constexpr int NT = 256;   // 8 warps: two per TMEM lane quadrant share each layer's epilogue rows; all eight issue MMAs
+
+__global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sX = smem;
     uint8_t* sY = smem + X_BYTES;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
     if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     if (threadIdx.x == 32) {
         tc::mbar_init(bar_w, 1);
-        for (int i = 0; i < 3; ++i) tc::mbar_init(bar_mma + i, 4);
+        for (int i = 0; i < 3; ++i) tc::mbar_init(bar_mma + i, NT / 32);
         tc::mbar_fence_init();
     }
     if (threadIdx.x < 65) s_f[threadIdx.x] = __ldg(p.fparams + threadIdx.x);
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
         tc::bulk_copy_g2s(sW_u, p.wgt, W_BYTES, bar_w);
     }
     // ---- stage the two fp32 input maps as hi/lo fp16 slabs (zero outside the image) -------------------------------
-    for (int i = threadIdx.x; i < R_IN * TX; i += 128) {
+    for (int i = threadIdx.x; i < R_IN * TX; i += NT) {
         const int px = i % TX, ry = i / TX;
         const int gx = xs + px, gy = y0 - 3 + ry;
         float e = 0.f, c = 0.f;
@@ -147,21 +149,22 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
 
     const uint32_t warp_u = tc::uniform((uint32_t)warp), tmem_u = tc::uniform(tmem);
     const bool elected = tc::elect_one();
-    const int j = warp * 32 + lane;                    // MMA row; its result is pixel j + 1 of the output buffer
+    const int quad = warp & 3, half = warp >> 2;       // TMEM lane quadrant of this warp; which half of the row units it drains
+    const int j = quad * 32 + lane;                    // MMA row; its result is pixel j + 1 of the output buffer
     const int gx1 = xs + j + 1;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
 
     // ---- layer 1: in8 -> a1 ------------------------------------------------------------------------------------------
     tc::tc_fence_after();
 #pragma unroll 1
-    for (uint32_t u = warp_u; u < (uint32_t)R_A1; u += 4)
+    for (uint32_t u = warp_u; u < (uint32_t)R_A1; u += NT / 32)
         issue_l1((sX_u + u * ROW_BYTES) >> 4, sW_u >> 4, tmem_u + u * 16, elected, std::make_integer_sequence<int, MMA_L1>{});
     if (elected) tc::mma_commit(bar_mma);
     __syncwarp();
     tc::mbar_wait(bar_mma, 0);
     tc::tc_fence_after();
 #pragma unroll 1
-    for (int u = 0; u < R_A1; ++u) {
+    for (int u = half; u < R_A1; u += 2) {
         const int gy = y0 - 2 + u;
         uint4 lo, hi;
         act16(lane_addr + u * 16, s_f, gx1 >= 0 && gx1 < p.W && gy >= 0 && gy < p.H, lo, hi);
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
 
     // ---- layer 2: a1 -> a2 (re-using the in8 region) ------------------------------------------------------------------
 #pragma unroll 1
-    for (uint32_t u = warp_u; u < (uint32_t)R_A2; u += 4)
+    for (uint32_t u = warp_u; u < (uint32_t)R_A2; u += NT / 32)
         issue_l23<R_A1 * ROW_BYTES, MMA_L1>((sY_u + u * ROW_BYTES) >> 4, sW_u >> 4, tmem_u + u * 16, elected,
                                            std::make_integer_sequence<int, MMA_L23>{});
     if (elected) tc::mma_commit(bar_mma + 1);
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
     tc::mbar_wait(bar_mma + 1, 0);
     tc::tc_fence_after();
 #pragma unroll 1
-    for (int u = 0; u < R_A2; ++u) {
+    for (int u = half; u < R_A2; u += 2) {
         const int gy = y0 - 1 + u;
         uint4 lo, hi;
         act16(lane_addr + u * 16, s_f + 16, gx1 >= 0 && gx1 < p.W && gy >= 0 && gy < p.H, lo, hi);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
 
     // ---- layer 3 + 1x1 + sigmoid ---------------------------------------------------------------------------------------
 #pragma unroll 1
-    for (uint32_t u = warp_u; u < (uint32_t)TY; u += 4)
+    for (uint32_t u = warp_u; u < (uint32_t)TY; u += NT / 32)
         issue_l23<R_A2 * ROW_BYTES, MMA_L1 + MMA_L23>((sX_u + u * ROW_BYTES) >> 4, sW_u >> 4, tmem_u + u * 16, elected,
                                                      std::make_integer_sequence<int, MMA_L23>{});
     if (elected) tc::mma_commit(bar_mma + 2);
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(128) visnet_tc_kernel(VisTcParams p) {
     tc::tc_fence_after();
     const bool col_ok = j >= 2 && j < TX - 4 && gx1 < p.W && gx1 >= (int)blockIdx.x * TXO;   // one owner tile per pixel
 #pragma unroll 1
-    for (int u = 0; u < TY; ++u) {
+    for (int u = half; u < TY; u += 2) {
         const int gy = y0 + u;
         uint32_t r0[8], r1[8];
         tc::tmem_ld8_nowait(lane_addr + u * 16, r0);
@@ -246,7 +249,7 @@ int cds_visnet_tc(const float* entropy, const float* curv, const void* wgt_packe
     if (e != cudaSuccess) { cds_set_error("cds_visnet_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     VisTcParams p{entropy, curv, (const __half*)wgt_packed, fparams, vis, h, w};
     dim3 grid(cds_div_up(w, TXO), cds_div_up(h, TY), n);
-    visnet_tc_kernel<<<grid, 128, smem, stream>>>(p);
+    visnet_tc_kernel<<<grid, NT, smem, stream>>>(p);
     return cds_check_launch("cds_visnet_tc");
 }
 
