@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 
     constexpr uint32_t A_BYTES = (SPLIT ? 2 : 1) * C8 * CHUNK;
     constexpr uint32_t B_BYTES = C::B_BYTES;
     constexpr uint32_t STAGE_COLS = C::NALL;                        // accumulator columns per row unit
-    constexpr uint32_t NSTG = 2 * STAGE_COLS <= 256 ? 2 : 1;        // accumulator stages (one when two would take the whole TMEM)
+    // accumulator stages: two (the MMAs of unit u+1 overlap the epilogue of unit u) unless that would cost a resident CTA its
+    // TMEM; measured: the MMA-heavy (3,5) layers prefer 2 stages x 2 CTAs, the k=(1,3) 16-channel layer 1 stage x 3 CTAs
+    constexpr uint32_t NSTG = (2 * STAGE_COLS <= 128 || (C::KMAX >= 5 && 2 * STAGE_COLS <= 256)) ? 2 : 1;
     constexpr uint32_t TMEM_COLS = NSTG * STAGE_COLS <= 64 ? 64 : (NSTG * STAGE_COLS <= 128 ? 128 : 256);
     static_assert(NSTG * STAGE_COLS <= 256, "accumulators exceed the TMEM budget of two resident CTAs");
     extern __shared__ __align__(128) uint8_t smem[];
