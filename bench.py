@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--storage", default="float16", choices=["float16", "float32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the forward launch by launch instead of replaying a CUDA graph")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -221,7 +222,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_graph = not args.no_graph
+
     def step_device():
+        # one CUDA-graph launch per forward (inputs copied device->device into the graph's static tensors every step)
+        if use_graph:
+            return engine.forward_graph(d_imgs, d_proj, d_dv, TEMPERATURE)
         return engine.forward(d_imgs, d_proj, d_dv, TEMPERATURE)
 
     for _ in range(args.warmup):
@@ -251,7 +257,7 @@ def main():
     with _lib.LaunchProfile() as prof:
         ev2.record()
         for _ in range(args.steps):
-            step_device()
+            engine.forward(d_imgs, d_proj, d_dv, TEMPERATURE)   # launch by launch: a graph node cannot carry an event pair
         ev3.record()
     barrier()
     ms_instrumented = ev2.elapsed_time(ev3)
@@ -376,6 +382,7 @@ def main():
         "config": {"workload": workload_name(args.workload, cfg), "storage": f"{args.storage} activations, fp32 accumulate",
                    "weights": "pretrained both_dtu_blended (tests/golden/weights_both_dtu_blended.npz)",
                    "parallelism": f"replicas x{world}, work-list sharding, no collective",
+                   "launch": "one CUDA graph per forward" if use_graph else "launch by launch",
                    "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "roofline_region": f"the same {args.steps} steps repeated with a CUDA-event pair around every launch "
                                       f"({ms_instrumented / args.steps:.3f} ms/step instrumented)",

@@ -44,8 +44,9 @@ def _flatten(out):
 
 
 class DepthMapStream:
-    def __init__(self, model, temperature=0.001, depth=2):
+    def __init__(self, model, temperature=0.001, depth=2, use_graph=True):
         self.model = model
+        self.use_graph = use_graph      # replay the forward as one CUDA graph (captured on the first item of a shape)
         self.temperature = float(temperature)
         self.slots = [_Slot() for _ in range(depth)]
         self.n = 0
@@ -81,7 +82,9 @@ class DepthMapStream:
             slot.ev_in.record(self.s_in)
         # ---- kernels on the caller's stream
         compute.wait_event(slot.ev_in)
-        out = _flatten(self.model.engine(dev).forward(slot.dev_in[0], slot.dev_in[1], slot.dev_in[2], self.temperature))
+        engine = self.model.engine(dev)
+        run = engine.forward_graph if self.use_graph else engine.forward
+        out = _flatten(run(slot.dev_in[0], slot.dev_in[1], slot.dev_in[2], self.temperature))
         if slot.dev_out is None:
             slot.dev_out = {k: torch.empty_like(v) for k, v in out.items()}
             slot.host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}

@@ -151,3 +151,21 @@ def test_depth_map_stream_matches_direct_call(pretrained_sd):
         stream.result(0)          # overwritten two submits ago
     with pytest.raises(ValueError):
         stream.submit(items[0].imgs.to(DEV), items[0].proj_matrices, items[0].depth_values)
+
+
+def test_forward_graph_matches_eager(pretrained_sd):
+    """The CUDA-graph replay of the cascade returns what the launch-by-launch forward returns (several inputs through one
+    captured graph; re-association noise of the atomically accumulated statistics only)."""
+    cfg = dict(W=160, H=128, N=3, ndepths=(16, 8, 8), ratios=(4.0, 1.5, 0.75), B=1, Dtot=192, interval=2.65)
+    model = build(pretrained_sd, cfg["ndepths"], cfg["ratios"], torch.float16)
+    eng = model.engine(torch.device(DEV, 0))
+    for seed in range(3):
+        s = synthetic.make_sample(cfg, "plane" if seed % 2 else "noise", seed=seed)
+        args = (s.imgs.to(DEV), {k: v.to(DEV) for k, v in s.proj_matrices.items()}, s.depth_values.to(DEV), T)
+        eager = {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in eng.forward(*args).items() if isinstance(v, dict)}
+        graphed = eng.forward_graph(*args)
+        torch.cuda.synchronize()
+        for st, maps in eager.items():
+            for name, ref in maps.items():
+                err = O.rel_l1(graphed[st][name].cpu(), ref.cpu())
+                assert err < 2e-5, (seed, st, name, err)
