@@ -219,3 +219,40 @@ def random_state_dict(ndepths=(48, 32, 8), seed: int = 123, cr_base: int = 8) ->
             bn(f"{cr}.{name}.bn", co)
         sd[f"{cr}.prob.weight"] = conv_w(1, b, 3, 3, 3)
     return sd
+
+
+def make_fusion_sample(H: int, W: int, n_src: int, seed: int = 0, batch: int = 1):
+    """Inputs of the geometric-consistency filter (reference fusion.py / test.py:326-352) for the synthetic rig: per-view depth
+    maps of the slanted plane of the "plane" family (analytic, in every camera), perturbed so that the masks are mixed
+    (Gaussian noise on all maps, gross outliers and zeroed pixels on patches), cams [.,2,4,4] = (extrinsic, K with [1,3,3]=1)
+    and 3-channel confidences.  Returns dict of fp32 tensors shaped as test.py's TTDataset yields them."""
+    rng = np.random.default_rng(seed)
+    K, extr = make_cameras(n_src + 1, H, W)
+    nrm = np.array([0.15, -0.1, 1.0]); nrm /= np.linalg.norm(nrm)
+    d0 = 650.0 * nrm[2]                       # plane n.X = d0 in the reference (= world) frame, 650 mm at the principal ray
+    Kinv = np.linalg.inv(K)
+    ys, xs = np.meshgrid(np.arange(H) + 0.5, np.arange(W) + 0.5, indexing="ij")
+    rays = np.stack([xs, ys, np.ones_like(xs)], -1) @ Kinv.T          # [H, W, 3], z = 1
+    depths, cams = [], []
+    for i, E in enumerate(extr):
+        R, t = E[:3, :3], E[:3, 3]
+        C = -R.T @ t
+        # X_w = R^T (depth * ray) + C  ->  n.X_w = d0
+        dep = (d0 - nrm @ C) / (rays @ (R @ nrm))
+        dep = dep + rng.normal(0.0, 0.4, dep.shape)
+        y0, x0 = rng.integers(0, H // 2), rng.integers(0, W // 2)
+        dep[y0:y0 + H // 6, x0:x0 + W // 6] *= 1.0 + 0.05 * rng.random()          # a patch that fails the depth test
+        y1, x1 = rng.integers(0, H // 2), rng.integers(0, W // 2)
+        dep[y1:y1 + H // 8, x1:x1 + W // 8] = 0.0                                   # a patch masked out by the confidence filter
+        depths.append(dep.astype(np.float32))
+        cam = np.zeros((2, 4, 4), dtype=np.float32)
+        cam[0] = E.astype(np.float32)
+        cam[1, :3, :3] = K.astype(np.float32)
+        cam[1, 3, 3] = 1.0
+        cams.append(cam)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    rep = lambda x: x.unsqueeze(0).repeat(batch, *([1] * x.dim())).contiguous()
+    conf = rng.random((n_src + 1, 3, H, W)).astype(np.float32)
+    return {"ref_depth": rep(t(depths[0])[None]), "src_depths": rep(t(np.stack(depths[1:]))[:, None]),
+            "ref_cam": rep(t(cams[0])), "src_cams": rep(t(np.stack(cams[1:]))),
+            "ref_conf": rep(t(conf[0])), "src_confs": rep(t(conf[1:]))}

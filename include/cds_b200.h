@@ -224,6 +224,25 @@ int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C
 int cds_nchw_to_nhwc(const float* in, int n, int C, int H, int W, int dtype, void* out, cudaStream_t stream);
 int cds_nhwc_to_nchw(const void* in, int n, int C, int H, int W, int dtype, float* out, cudaStream_t stream);
 
+/* ---- next row: geometric-consistency filter, the step after the depth-inference path ----------- */
+/* Reference: fusion.py:49-117 (get_reproj, project_img, vis_filter, ave_fusion, prob_filter), driven by test.py:326-352.
+ * cams are [.,2,4,4] = (extrinsic, intrinsic in [1,:3,:3]).  cds_fusion_setup turns (ref_cam [n,2,4,4], srcs_cam [n,v,2,4,4])
+ * into mats [n,v,100] (matrices + fp64-computed inverses, cds_fusion_mats_floats(n, v) floats).  cds_geometric_filter does
+ * get_reproj + vis_filter + ave_fusion + back-projection in one pass; every output may be NULL: reproj_xyd [n,v,3,h,w],
+ * in_range [n,v,h,w], masks [n,v,h,w] (fp32 0/1), vis_mask [n,h,w] uint8, ave [n,h,w], points [n,3,h,w] (world frame). */
+int cds_fusion_mats_floats(int n, int v);
+int cds_fusion_setup(const float* ref_cam, const float* srcs_cam, int n, int v, float* mats, cudaStream_t stream);
+int cds_geometric_filter(const float* ref_depth, const float* srcs_depth, const float* mats, int n, int v, int h, int w,
+                         float img_dist_thresh, float depth_thresh, float vthresh, float* reproj_xyd, float* in_range, float* masks,
+                         unsigned char* vis_mask, float* ave, float* points, cudaStream_t stream);
+/* vis_filter / ave_fusion on materialised reprojections (masks_in NULL: masks computed, else used as given). */
+int cds_vis_filter(const float* ref_depth, const float* reproj_xyd, const float* in_range, const float* masks_in, int n, int v, int h,
+                   int w, float img_dist_thresh, float depth_thresh, float vthresh, float* masks_out, unsigned char* vis_mask,
+                   float* ave, cudaStream_t stream);
+/* prob_filter: mask = AND_c prob[:,c] > thresholds[c] (thresholds on the HOST, C <= 4); optional depth_inout *= mask. */
+int cds_prob_filter(const float* prob, const float* thresholds, int n, int C, int h, int w, unsigned char* mask, float* depth_inout,
+                    cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
