@@ -137,7 +137,7 @@ class FeatureExtractor:
         return bool(self.use_tc and self.split_precision and w.tc is not None and self.storage == torch.float16
                     and _lib.LIB.load().cds_dynamic_conv_tc_supported(16, 16, H2, W2, 2, _ksizes(w.ksizes)))
 
-    def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature, pairs=None):
+    def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature, pairs=None, after_stage1=None):
         """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
         Returns {stage: (fea [n,h,w,C] storage dtype, nc_sq [n,h,w] fp32, nc_abs [n,h,w] fp32)}."""
         st, dt = self.storage, self.dt
@@ -196,6 +196,8 @@ class FeatureExtractor:
         # stage-1 output
         self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1, sv(8, 32), ncsq[0], 2, ncab[0])
         kcall("feat.act1", 0, 2 * n * H4 * W4 * 32 * e, "cds_instnorm_act", ptr(rawo1), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
+        if after_stage1 is not None:   # the stage-1 feature is complete: the caller may start stage 1 on another stream
+            after_stage1((fea1, ncsq[0], ncab[0]))
         # stage-2 output: inner1 over cat(up2(conv21), conv11)
         self._inner("inner1", raw21, sv(7, 32), ACT_LRELU, raw11, sv(4, 16), fw.inner1, n, 32, 16, 16, H2, W2, rawi1, sv(9, 16))
         self._dyn("out2", rawi1, 0, None, sv(9, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, rawo2, sv(10, 16), ncsq[1], 2, ncab[1])
@@ -313,6 +315,8 @@ class CascadeEngine:
         self.features = FeatureExtractor(weights.feature, storage)
         self.regs = [Regulariser(cw, storage) for cw in weights.costreg]
         self.use_tc = os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_VIS", "1") != "0"
+        self.overlap = os.environ.get("CDS_OVERLAP", "1") != "0"   # stage 1 on a side stream under the feature heads
+        self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.launches = 0
 
     # -- pieces -------------------------------------------------------------------------------
@@ -431,10 +435,28 @@ class CascadeEngine:
                     idx[1, v, b] = b * N + v + 1
             self._imgidx = idx.reshape(-1).to(dev)
             self._imgidx_key = key
-        feats = self.features.run(self.buf, imgs, self._imgidx, epi, n, H, W, temperature, pairs=(V, B))
-        outputs, depth = {}, None
+        outputs, stage1 = {}, {}
+        overlap = self.overlap and len(self.ndepths) > 1
+
+        def start_stage1(feat1):
+            # Stage 1 only needs the quarter-resolution feature: it runs on a side stream while this stream finishes the
+            # half / full resolution heads of the feature extractor (disjoint buffers; joined before stage 2).  Its deep
+            # regulariser layers are small grids, so the two streams fill each other's gaps.
+            main = torch.cuda.current_stream(dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                stage1["out"] = self.stage(0, feat1, coef[0], depth_values, None, B, V, H, W)
+            stage1["main"] = main
+
+        feats = self.features.run(self.buf, imgs, self._imgidx, epi, n, H, W, temperature, pairs=(V, B),
+                                  after_stage1=start_stage1 if overlap else None)
+        depth = None
         for s in range(len(self.ndepths)):
-            o = self.stage(s, feats[s], coef[s], depth_values, depth, B, V, H, W)
+            if s == 0 and overlap:
+                stage1["main"].wait_stream(self._side)
+                o = stage1["out"]
+            else:
+                o = self.stage(s, feats[s], coef[s], depth_values, depth, B, V, H, W)
             depth = o["depth"]
             outputs[f"stage{s + 1}"] = o
             outputs.update(o)
