@@ -104,10 +104,15 @@ def cpu_oracle_rate(cfg, n_threads, budget_s=25.0, steps=1, warmup=0):
     O.FAST_GATHER = True   # gather through ATen grid_sample, as the reference itself does
     torch.set_num_threads(n_threads)
     sd = load_weights()
+    refine = bool(cfg.get("refine", False))
+    if refine:
+        zr = np.load(os.path.join(ROOT, "tests", "golden", "weights_refine_both_dtu_blended.npz"))
+        sd.update({k: torch.from_numpy(zr[k]) for k in zr.files})
+    q = 64 if refine else 32
     full_px = cfg["H"] * cfg["W"]
     ladder = [(cfg["H"], cfg["W"])]
     for f in (2, 4, 8):
-        h, w = max(32, (cfg["H"] // f) // 32 * 32), max(32, (cfg["W"] // f) // 32 * 32)
+        h, w = max(q, (cfg["H"] // f) // q * q), max(q, (cfg["W"] // f) // q * q)
         if (h, w) != ladder[-1]:
             ladder.append((h, w))
 
@@ -116,7 +121,7 @@ def cpu_oracle_rate(cfg, n_threads, budget_s=25.0, steps=1, warmup=0):
         s = synthetic.make_sample(c, "noise", seed=0)
         t0 = time.perf_counter()
         with torch.no_grad():
-            O.cdsmvsnet_forward(sd, s.imgs, s.proj_matrices, s.depth_values, c["ndepths"], c["ratios"], TEMPERATURE)
+            O.cdsmvsnet_forward(sd, s.imgs, s.proj_matrices, s.depth_values, c["ndepths"], c["ratios"], TEMPERATURE, refine=refine)
         return time.perf_counter() - t0
 
     # calibrate on the smallest rung, then take the largest rung whose predicted total fits the budget
@@ -162,7 +167,7 @@ def run_reference_arm(args, cfg, rank, world):
 
 def workload_name(key, cfg):
     return (f"{key}: CDSMVSNet.forward {cfg['W']}x{cfg['H']} N={cfg['N']} D={'/'.join(str(d) for d in cfg['ndepths'])} "
-            f"ratios={'/'.join(str(r) for r in cfg['ratios'])} B={cfg['B']} refine=False T={TEMPERATURE}")
+            f"ratios={'/'.join(str(r) for r in cfg['ratios'])} B={cfg['B']} refine={bool(cfg.get('refine', False))} T={TEMPERATURE}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -203,8 +208,12 @@ def main():
     torch.set_grad_enabled(False)
 
     storage = getattr(torch, args.storage)
-    model = C.CDSMVSNet(refine=False, ndepths=cfg["ndepths"], depth_interals_ratio=cfg["ratios"], storage=storage)
+    refine = bool(cfg.get("refine", False))
+    model = C.CDSMVSNet(refine=refine, ndepths=cfg["ndepths"], depth_interals_ratio=cfg["ratios"], storage=storage)
     sd = load_weights()
+    if refine:
+        zr = np.load(os.path.join(ROOT, "tests", "golden", "weights_refine_both_dtu_blended.npz"))
+        sd.update({k: torch.from_numpy(zr[k]) for k in zr.files})
     model.load_state_dict({k: v for k, v in sd.items() if k in model.state_dict()})   # fewer stages (cfg1): fewer entries
     model = model.to(dev).eval()
 

@@ -7,7 +7,7 @@ behind the reference's own Python call surface.
 Importing the package never touches the GPU; the first op call loads ``libcds_b200.so`` (built by
 ``python -m cds_mvsnet_b200.build``) and raises if it or a B200 is missing -- there is no fallback.
 """
-from .modules import (CDSMVSNet, CostRegNet, DynamicConv, FeatureNet, StageNet, conf_regression,  # noqa: F401
+from .modules import (CDSMVSNet, CostRegNet, DynamicConv, FeatureNet, Refinement, StageNet, conf_regression,  # noqa: F401
                       depth_regression, homo_warping_3D, patch)
 
 __version__ = "0.1.0"

@@ -301,11 +301,47 @@ class Regulariser:
         return logits
 
 
+class Refiner:
+    """Refinement network (models/module.py:318-370) on csrc/refine.cu: seven launches, fp32 planar."""
+
+    def __init__(self, rw):
+        self.rw = rw
+
+    def run(self, buf: Buffers, img, depth0, lo, hi, post, B, H, W):
+        """img [B,3,H,W] fp32, depth0 [B,H/2,W/2], lo / hi / post [B] (post may be None) -> refined [B,H,W] (a Buffers tensor)."""
+        if H % 2 or W % 2:
+            raise RuntimeError(f"Refinement needs even H, W (got {H}x{W})")
+        h, w, f32, rw = H // 2, W // 2, torch.float32, self.rw
+        dn = buf.get("rf.depth_n", (B, h, w), f32)
+        c0 = buf.get("rf.conv0", (B, 8, H, W), f32)
+        c1 = buf.get("rf.conv1", (B, 8, h, w), f32)
+        c2 = buf.get("rf.conv2", (B, 8, h, w), f32)
+        dc = buf.get("rf.deconv", (B, 8, H, W), f32)
+        c3 = buf.get("rf.conv3", (B, 8, H, W), f32)
+        out = buf.get("rf.refined", (B, H, W), f32)
+        P, p = B * H * W, B * h * w
+        kcall("refine.prescale", 0, 8 * p, "cds_refine_prescale", ptr(depth0), ptr(lo), ptr(hi), B, h, w, ptr(dn))
+        kcall("refine.conv0", 2.0 * 27 * 8 * P, 4 * P * 11, "cds_conv2d_3x3_f32", ptr(img), None, ptr(rw["conv0"][0]), ptr(rw["conv0"][1]),
+              B, 3, 0, 8, H, W, 1, ptr(c0))
+        kcall("refine.conv1", 2.0 * 9 * 8 * p, 4 * p * 9, "cds_conv2d_3x3_f32", ptr(dn), None, ptr(rw["conv1"][0]), ptr(rw["conv1"][1]),
+              B, 1, 0, 8, h, w, 1, ptr(c1))
+        kcall("refine.conv2", 2.0 * 72 * 8 * p, 4 * p * 16, "cds_conv2d_3x3_f32", ptr(c1), None, ptr(rw["conv2"][0]), ptr(rw["conv2"][1]),
+              B, 8, 0, 8, h, w, 1, ptr(c2))
+        kcall("refine.deconv", 2.0 * 18 * 8 * P, 4 * (p * 8 + P * 8), "cds_deconv2d_k3s2_f32", ptr(c2), ptr(rw["deconv"][0]),
+              ptr(rw["deconv"][1]), B, 8, h, w, ptr(dc))
+        kcall("refine.conv3", 2.0 * 144 * 8 * P, 4 * P * 24, "cds_conv2d_3x3_f32", ptr(dc), ptr(c0), ptr(rw["conv3"][0]), ptr(rw["conv3"][1]),
+              B, 8, 8, 8, H, W, 1, ptr(c3))
+        kcall("refine.final", 2.0 * 72 * P, 4 * P * 9 + 4 * p, "cds_refine_final", ptr(c3), ptr(rw["res"]), ptr(dn), ptr(lo), ptr(hi),
+              ptr(post), B, h, w, ptr(out))
+        return out
+
+
 class CascadeEngine:
     """The whole CDSMVSNet.forward (refine=False, eval) on the CUDA kernels."""
 
-    def __init__(self, weights: ModelWeights, ndepths, ratios, storage=torch.float16, device=None):
+    def __init__(self, weights: ModelWeights, ndepths, ratios, storage=torch.float16, device=None, refine_weights=None):
         self.w = weights
+        self.refiner = Refiner(refine_weights) if refine_weights is not None else None   # refine=True (models/model.py:209-216)
         self.ndepths = tuple(int(d) for d in ndepths)
         self.ratios = tuple(float(r) for r in ratios)
         self.storage = storage
@@ -418,11 +454,21 @@ class CascadeEngine:
         B, N, _, H, W = imgs.shape
         if N < 2:
             raise AssertionError("need at least one source view")
-        if H % 32 or W % 32:
-            raise RuntimeError(f"H and W must be divisible by 32 (got {H}x{W}); see SURVEY.md 8c fixture 6")
         V = N - 1
         dev = self.device
         imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
+        full_imgs, Hf, Wf = imgs, H, W
+        if self.refiner is not None:
+            # refine=True: the cascade works at half resolution on nearest-subsampled images (models/model.py:145-147: the
+            # default F.interpolate picks pixel (2i, 2j)); the Refinement network restores the full resolution at the end
+            if H % 64 or W % 64:
+                raise RuntimeError(f"refine=True needs H and W divisible by 64 (got {H}x{W}); see SURVEY.md 8c fixture 6")
+            H, W = H // 2, W // 2
+            half = self.buf.get("rf.imgs_half", (B, N, 3, H, W), torch.float32)
+            half.copy_(imgs[..., ::2, ::2])
+            imgs = half
+        if H % 32 or W % 32:
+            raise RuntimeError(f"H and W must be divisible by 32 (got {H}x{W}); see SURVEY.md 8c fixture 6")
         depth_values = depth_values.to(device=dev, dtype=torch.float32).contiguous()
         coef, epi = self.camera_setup(proj_matrices, B, N)
         n = 2 * V * B
@@ -460,5 +506,17 @@ class CascadeEngine:
             depth = o["depth"]
             outputs[f"stage{s + 1}"] = o
             outputs.update(o)
-        outputs["refined_depth"] = depth
+        if self.refiner is not None:
+            # models/model.py:210-216: depths in units of the plane interval go through the net, the result is scaled back
+            iv = self.buf.get("rf.interval", (3, B), torch.float32)          # rows: interval, dmin / interval, dmax / interval
+            torch.sub(depth_values[:, 1], depth_values[:, 0], out=iv[0])
+            torch.div(depth_values[:, 0], iv[0], out=iv[1])
+            torch.div(depth_values[:, -1], iv[0], out=iv[2])
+            d0 = self.buf.get("rf.depth0", (B, H, W), torch.float32)
+            torch.div(depth, iv[0].view(B, 1, 1), out=d0)
+            ref_img = self.buf.get("rf.ref_img", (B, 3, Hf, Wf), torch.float32)
+            ref_img.copy_(full_imgs[:, 0])
+            outputs["refined_depth"] = self.refiner.run(self.buf, ref_img, d0, iv[1], iv[2], iv[0], B, Hf, Wf)
+        else:
+            outputs["refined_depth"] = depth
         return outputs

@@ -317,6 +317,33 @@ class _ConvBnReLU2d(nn.Module):
         self.bn = nn.BatchNorm2d(co)
 
 
+class Refinement(_CachedModule):
+    """Drop-in for models/module.py:318-370 (same parameter names: conv0..conv3.{conv,bn}, deconv, bn, res)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0, self.conv1, self.conv2 = _ConvBnReLU2d(3, 8), _ConvBnReLU2d(1, 8), _ConvBnReLU2d(8, 8)
+        self.deconv = nn.ConvTranspose2d(8, 8, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False)
+        self.bn = nn.BatchNorm2d(8)
+        self.conv3 = _ConvBnReLU2d(16, 8)
+        self.res = nn.Conv2d(8, 1, kernel_size=3, padding=1, bias=False)
+
+    def forward(self, img, depth_0, depth_min, depth_max):
+        """img [B,3,H,W], depth_0 [B,1,H/2,W/2], depth_min / depth_max [B] -> refined depth [B,1,H,W]."""
+        self._require_eval()
+        dev = _dev(img)
+        from .engine import Refiner
+        if self._cache is None:
+            object.__setattr__(self, "_cache", (Refiner(W.pack_refinement(self._sd("r."), "r", dev)), Buffers(dev)))
+        refiner, buf = self._cache
+        B, _, H, Wd = img.shape
+        if tuple(depth_0.shape) != (B, 1, H // 2, Wd // 2):
+            raise RuntimeError(f"Refinement: depth_0 must be [B,1,H/2,W/2] = {(B, 1, H // 2, Wd // 2)}, got {tuple(depth_0.shape)}")
+        out = refiner.run(buf, _f32c(img), _f32c(depth_0).reshape(B, H // 2, Wd // 2), _f32c(depth_min).reshape(B), _f32c(depth_max).reshape(B),
+                          None, B, H, Wd)
+        return out.unsqueeze(1).clone()
+
+
 class StageNet(_CachedModule):
     def __init__(self, num_mvs_stages=3, storage=DEFAULT_STORAGE):
         super().__init__()
@@ -380,9 +407,6 @@ class CDSMVSNet(_CachedModule):
     def __init__(self, refine=False, ndepths=(48, 32, 8), depth_interals_ratio=(4, 2, 1), share_cr=False,
                  grad_method="detach", arch_mode="fpn", cr_base_chs=(8, 8, 8), storage=DEFAULT_STORAGE):
         super().__init__()
-        if refine:
-            raise NotImplementedError("CDSMVSNet(refine=True): the Refinement network is outside the hot path "
-                                      "(SURVEY.md 8f-4); construct with refine=False")
         assert len(ndepths) == len(depth_interals_ratio)
         if len(ndepths) > 3:
             raise NotImplementedError("at most 3 stages (the reference defines scales for stage1..3 only)")
@@ -399,11 +423,15 @@ class CDSMVSNet(_CachedModule):
         self.cost_regularization = nn.ModuleList([CostRegNet(in_channels=self.feature.out_channels[i],
                                                              base_channels=self.cr_base_chs[i], storage=storage)
                                                   for i in range(self.num_stage)])
+        if refine:
+            self.refine_network = Refinement()
 
     def engine(self, dev) -> CascadeEngine:
         if self._cache is None:
             mw = W.pack_model(self.state_dict(), self.num_stage, dev)
-            object.__setattr__(self, "_cache", CascadeEngine(mw, self.ndepths, self.depth_interals_ratio, self.storage, dev))
+            rw = W.pack_refinement({k: v.detach() for k, v in self.state_dict().items()}, "refine_network", dev) if self.refine else None
+            object.__setattr__(self, "_cache", CascadeEngine(mw, self.ndepths, self.depth_interals_ratio, self.storage, dev,
+                                                             refine_weights=rw))
         return self._cache
 
     def forward(self, imgs, proj_matrices, depth_values, gt_depths=None, temperature=0.001):
@@ -428,7 +456,7 @@ def patch(models_model=None, models_module=None):
     if models_model is not None:
         for name, obj in (("homo_warping_3D", homo_warping_3D), ("depth_regression", depth_regression),
                           ("conf_regression", conf_regression), ("CostRegNet", CostRegNet), ("StageNet", StageNet),
-                          ("FeatureNet", FeatureNet), ("CDSMVSNet", CDSMVSNet)):
+                          ("FeatureNet", FeatureNet), ("Refinement", Refinement), ("CDSMVSNet", CDSMVSNet)):
             setattr(models_model, name, obj)
     if models_module is not None:
         for name, obj in (("DynamicConv", DynamicConv), ("depth_regression", depth_regression),

@@ -31,6 +31,9 @@ CONFIGS = {
     "cfg4": dict(W=640, H=512, N=3, ndepths=(48, 32, 8), ratios=(4.0, 1.5, 0.75), B=4, Dtot=192, interval=2.65),
     "cfg5": dict(W=1600, H=1184, N=5, ndepths=(128, 32, 8), ratios=(4.0, 1.5, 0.75), B=1, Dtot=512,
                  interval=2.65 * 192 / 512),
+    # the reference's DTU protocol (scripts/dtu_eval.sh: 1536x1152, refine=True): cascade at 768x576 + Refinement network
+    "dtu_refine": dict(W=1536, H=1152, N=5, ndepths=(48, 32, 8), ratios=(4.0, 1.5, 0.75), B=1, Dtot=192, interval=2.65,
+                       refine=True),
 }
 DEPTH_MIN = 425.0
 
@@ -124,7 +127,12 @@ def make_sample(cfg: str | dict = "cfg1", family: str = "noise", seed: int = 0, 
     H, W, N, B = c["H"], c["W"], c["N"], c["B"]
     K, extr = make_cameras(N, H, W)
     n_stages = 3
-    proj = pack_proj_matrices(K, extr, B, n_stages)
+    # refine=True (the reference's DTU protocol, dtu_eval.sh): the cascade works at half the image resolution on pixels (2i, 2j),
+    # so the cameras handed to the model are the full-resolution ones with the first two rows of K halved
+    Kc = K.copy()
+    if c.get("refine"):
+        Kc[:2, :] *= 0.5
+    proj = pack_proj_matrices(Kc, extr, B, n_stages)
     dv = (DEPTH_MIN + c["interval"] * torch.arange(c["Dtot"], dtype=torch.float32)).unsqueeze(0).repeat(B, 1)
     gen = torch.Generator().manual_seed(seed)
     gt = None

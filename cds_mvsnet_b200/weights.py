@@ -425,6 +425,23 @@ class ModelWeights:
     vis_tc: list = field(default_factory=list)   # per stage (fp16 operand image, fp32 biases) for csrc/visnet_tc.cu
 
 
+def pack_refinement(sd, prefix, device) -> dict:
+    """Folded fp32 weights of the Refinement network (models/module.py:318-335) for csrc/refine.cu: per ConvBnReLU
+    (w [Cout][Cin][3][3] * bn scale, bias = bn shift); the transposed conv keeps torch's [Cin][Cout][3][3] with the
+    following BatchNorm folded over Cout; res.weight as is."""
+    f32 = dict(dtype=torch.float32, device=device)
+    out = {}
+    for n in ("conv0", "conv1", "conv2", "conv3"):
+        scale, shift = _bn_fold(sd, f"{prefix}.{n}.bn")
+        w = sd[f"{prefix}.{n}.conv.weight"].double() * scale.reshape(-1, 1, 1, 1)
+        out[n] = (w.to(**f32).contiguous(), shift.to(**f32).contiguous())
+    scale, shift = _bn_fold(sd, f"{prefix}.bn")
+    w = sd[f"{prefix}.deconv.weight"].double() * scale.reshape(1, -1, 1, 1)                    # [Cin, Cout, 3, 3]
+    out["deconv"] = (w.to(**f32).contiguous(), shift.to(**f32).contiguous())
+    out["res"] = sd[f"{prefix}.res.weight"].double().reshape(8, 9).to(**f32).contiguous()      # [1, 8, 3, 3]
+    return out
+
+
 def pack_model(sd, n_stages: int, device, share_cr: bool = False) -> ModelWeights:
     sd = {k: v.detach() for k, v in sd.items()}
     vis = [pack_visnet(sd, f"stage_net.vis.{s}", device) for s in range(n_stages)]

@@ -243,6 +243,18 @@ int cds_vis_filter(const float* ref_depth, const float* reproj_xyd, const float*
 int cds_prob_filter(const float* prob, const float* thresholds, int n, int C, int h, int w, unsigned char* mask, float* depth_inout,
                     cudaStream_t stream);
 
+/* ---- next row: the Refinement network (models/module.py:318-370; models/model.py:209-216) ------------ */
+/* fp32 planar NCHW, BatchNorm folded by the host (weights.py pack_refinement).  Refinement.forward is the sequence
+ * cds_refine_prescale -> cds_conv2d_3x3_f32 x3 (conv0 on the image; conv1, conv2 on the depth) -> cds_deconv2d_k3s2_f32 ->
+ * cds_conv2d_3x3_f32 (conv3 over cat(deconv, conv0)) -> cds_refine_final (res conv + bilinear up2 of the normalised depth +
+ * rescale; post[b] = optional per-item multiplier, the depth interval of models/model.py:216). */
+int cds_refine_prescale(const float* depth0, const float* lo, const float* hi, int B, int h, int w, float* depth_n, cudaStream_t stream);
+int cds_conv2d_3x3_f32(const float* a, const float* b, const float* wgt, const float* bias, int B, int Ca, int Cb, int Cout, int H, int W,
+                       int relu, float* out, cudaStream_t stream);
+int cds_deconv2d_k3s2_f32(const float* in, const float* wgt, const float* bias, int B, int C, int h, int w, float* out, cudaStream_t stream);
+int cds_refine_final(const float* x, const float* res_wgt, const float* depth_n, const float* lo, const float* hi, const float* post,
+                     int B, int h, int w, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

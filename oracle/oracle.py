@@ -374,9 +374,33 @@ def stage_net(features, proj_matrices, depth_samples, sd, stage_idx, return_inte
     return out
 
 
+def _cbr2d(x, sd, p):
+    """ConvBnReLU (module.py:169-198): 3x3 conv, no bias -> BatchNorm2d (eval) -> ReLU."""
+    return F.relu(_bn_eval(F.conv2d(x, sd[p + ".conv.weight"], padding=1), sd, p + ".bn"))
+
+
+def refinement(sd, img, depth_0, depth_min, depth_max, prefix="refine_network"):
+    """Refinement.forward (module.py:337-370): img [B,3,H,W], depth_0 [B,1,H/2,W/2], depth_min/max [B] -> [B,1,H,W]."""
+    B = depth_min.shape[0]
+    lo, hi = depth_min.view(B, 1, 1, 1), depth_max.view(B, 1, 1, 1)
+    depth = (depth_0 - lo) / (hi - lo) * 10
+    conv0 = _cbr2d(img, sd, prefix + ".conv0")
+    d = _cbr2d(_cbr2d(depth, sd, prefix + ".conv1"), sd, prefix + ".conv2")
+    d = F.conv_transpose2d(d, sd[prefix + ".deconv.weight"], stride=2, padding=1, output_padding=1)
+    d = F.relu(_bn_eval(d, sd, prefix + ".bn"))
+    res = F.conv2d(_cbr2d(torch.cat((d, conv0), 1), sd, prefix + ".conv3"), sd[prefix + ".res.weight"], padding=1)
+    depth = (F.interpolate(depth, scale_factor=2, mode="bilinear", align_corners=True) + res) / 10
+    return depth * (hi - lo) + lo
+
+
 def cdsmvsnet_forward(sd, imgs, proj_matrices, depth_values, ndepths, ratios, temperature=0.01,
-                      return_intermediates=False):
-    """CDSMVSNet.forward with refine=False, grad_method='detach', share_cr=False (model.py:140-223)."""
+                      return_intermediates=False, refine=False):
+    """CDSMVSNet.forward with grad_method='detach', share_cr=False (model.py:140-223).  refine=True: the cascade works at half
+    the image resolution on nearest-subsampled images (model.py:145-147,159-160) and the Refinement network lifts the last
+    depth map back to full resolution (model.py:209-216)."""
+    full_imgs = imgs
+    if refine:
+        imgs = imgs[..., ::2, ::2]      # F.interpolate(img, (H/2, W/2)) is nearest: picks pixel (2i, 2j)
     B, N, _, H, W = imgs.shape
     dmin, dmax = depth_values[:, 0], depth_values[:, -1]
     interval = depth_values[:, 1] - depth_values[:, 0]
@@ -400,7 +424,12 @@ def cdsmvsnet_forward(sd, imgs, proj_matrices, depth_values, ndepths, ratios, te
         depth = o["depth"]
         outputs[name] = o
         outputs.update({k: v for k, v in o.items() if k != "_inter"})
-    outputs["refined_depth"] = depth
+    if refine:
+        iv = interval.view(B, 1, 1)
+        refined = refinement(sd, full_imgs[:, 0], (depth / iv).unsqueeze(1), dmin / interval, dmax / interval)
+        outputs["refined_depth"] = refined.squeeze(1) * iv
+    else:
+        outputs["refined_depth"] = depth
     if return_intermediates:
         outputs["_features"] = feats
     return outputs

@@ -121,3 +121,19 @@ def test_end_to_end(golden, pretrained_sd, tag, family):
     if family == "plane":
         # known-answer: the photo-consistent slanted plane is recovered
         assert (out["depth"] - s.gt_depth).abs().mean() < 8.0
+
+
+def test_refinement_oracle_matches_live_reference(golden, pretrained_sd):
+    """Refinement network and the refine=True cascade of the oracle against the live reference's outputs."""
+    from cds_mvsnet_b200 import synthetic
+    g = golden("refine")
+    sd = dict(pretrained_sd)
+    sd.update(golden("weights_refine_both_dtu_blended"))
+    out = O.refinement(sd, g["img"], g["depth_0"], g["depth_min"], g["depth_max"])
+    torch.testing.assert_close(out, g["refined"], rtol=1e-6, atol=1e-4)
+    W_, H_, N, B, Dtot = (int(v) for v in g["cfg"][:5])
+    cfg = dict(W=W_, H=H_, N=N, B=B, Dtot=Dtot, ndepths=tuple(int(v) for v in g["cfg"][5:]), ratios=tuple(float(r) for r in g["ratios"]),
+               interval=float(g["interval"]))
+    s = synthetic.make_sample(cfg, "noise", seed=0)
+    o = O.cdsmvsnet_forward(sd, g["e2e_imgs"], s.proj_matrices, s.depth_values, cfg["ndepths"], cfg["ratios"], 0.01, refine=True)
+    assert O.rel_l1(o["depth"], g["e2e_depth"]) < 1e-5 and O.rel_l1(o["refined_depth"], g["e2e_refined"]) < 1e-5

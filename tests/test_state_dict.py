@@ -47,4 +47,20 @@ def test_training_mode_is_refused():
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 3, 3, 64, 64), {}, torch.zeros(1, 4))
     with pytest.raises(NotImplementedError):
-        C.CDSMVSNet(refine=True)
+        C.CDSMVSNet(share_cr=True)
+
+
+def test_refine_state_dict_keys(golden, pretrained_sd):
+    """refine=True adds the reference's refine_network.* entries (models/module.py:318-335): a full checkpoint loads strictly."""
+    rsd = golden("weights_refine_both_dtu_blended")
+    m = C.CDSMVSNet(refine=True, ndepths=(48, 32, 8), depth_interals_ratio=(4.0, 1.5, 0.75))
+    sd = dict(pretrained_sd)
+    sd.update(rsd)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert len(rsd) == 31 and all(k.startswith("refine_network.") for k in rsd)
+    folded = W.pack_refinement(sd, "refine_network", "cpu")
+    w, b = folded["deconv"]
+    scale = sd["refine_network.bn.weight"] / torch.sqrt(sd["refine_network.bn.running_var"] + 1e-5)
+    assert torch.isclose(w[3, 5, 1, 2], sd["refine_network.deconv.weight"][3, 5, 1, 2] * scale[5], rtol=1e-6)
+    assert folded["res"].shape == (8, 9) and folded["conv3"][0].shape == (8, 16, 3, 3)
