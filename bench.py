@@ -315,12 +315,13 @@ def main():
     e0.record()
     prev = None
     checksum = 0.0
+    last_key = f"stage{len(cfg['ndepths'])}.depth"
     for _ in range(args.steps):
         t = pipe.submit(host["imgs"], host["proj"], host["dv"])
         if prev is not None:
-            checksum += float(pipe.result(prev)["stage3.depth"][0, 0, 0])   # the host consumes every result
+            checksum += float(pipe.result(prev)[last_key][0, 0, 0])   # the host consumes every result
         prev = t
-    checksum += float(pipe.result(prev)["stage3.depth"][0, 0, 0])
+    checksum += float(pipe.result(prev)[last_key][0, 0, 0])
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
