@@ -40,6 +40,10 @@ def _flatten(out):
         if isinstance(v, dict):
             for kk, vv in v.items():
                 flat[f"{k}.{kk}"] = vv
+    # refine=True: the full-resolution refined depth is a map of its own (refine=False aliases the last stage's depth)
+    rd = out.get("refined_depth")
+    if rd is not None and all(rd.data_ptr() != v.data_ptr() for v in flat.values()):
+        flat["refined_depth"] = rd
     return flat
 
 
