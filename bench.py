@@ -263,6 +263,7 @@ def main():
     # the roofline and of the kernel table; the ~140 extra event records per step cost ~3 %, so `value` is not taken here)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    overlap_was, engine.overlap = engine.overlap, False   # one stream: concurrent kernels would share the SMs and blur each other's durations
     with _lib.LaunchProfile() as prof:
         ev2.record()
         for _ in range(args.steps):
@@ -271,6 +272,7 @@ def main():
     barrier()
     ms_instrumented = ev2.elapsed_time(ev3)
     table = prof.summary()
+    engine.overlap = overlap_was
 
     # ---- timed region 2: end to end through the public API with HOST buffers -----------------------------------
     # (a) one call at a time: model(...) on pinned host inputs, results read back, host blocks on every item
