@@ -642,7 +642,7 @@ int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStr
     return cds_check_launch("cds_image_to_nhwc8");
 }
 
-// 1 when the tensor-core DynamicConv covers this layer (the feature extractor's shapes, W >= 128)
+// 1 when the tensor-core DynamicConv covers this layer (the feature extractor's shapes, W >= 8)
 int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* ks) {
     if (W < 8 || H < 1) return 0;
     return layer_id(Cin, Cout, num_kernels, ks) != 0;

@@ -114,12 +114,12 @@ int cds_deconv3d_k3s2(const void* in, const float* wgt, const float* bias, const
 /* Tensor-core (tcgen05 + TMEM) form of the stride-1 Conv3d block, fp16 storage only.  Same semantics as
  * cds_conv3d_k3; wgt_packed is the fp16 operand image built by the host (cds_conv3d_k3_tc_weight_halfs()
  * halfs, layout [mma][k-chunk 2][Npad/8][8 n][8 k], see csrc/conv3d_tc.cu).  cds_conv3d_k3_tc_supported()
- * tells whether a layer shape is covered (stride 1, W >= 128, channel pairs of the regulariser). */
+ * tells whether a layer shape is covered (stride 1, W >= 8, channel pairs of the regulariser). */
 int cds_conv3d_k3_tc_supported(int Cin, int Cout, int D, int H, int W, int stride);
 int cds_conv3d_k3_tc_weight_halfs(int Cin, int Cout);
 int cds_conv3d_k3_tc(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H,
                      int W, int relu, void* out, cudaStream_t stream);
-/* Tensor-core form of the Deconv3d block (same semantics as cds_deconv3d_k3s2, fp16 storage, input W >= 128).
+/* Tensor-core form of the Deconv3d block (same semantics as cds_deconv3d_k3s2, fp16 storage, input W >= 8).
  * wgt_packed: fp16 operand image (cds_deconv3d_k3s2_tc_weight_halfs() halfs, layout in csrc/conv3d_tc.cu). */
 int cds_deconv3d_k3s2_tc_supported(int Cin, int Cout, int D, int H, int W);
 int cds_deconv3d_k3s2_tc_weight_halfs(int Cin, int Cout);
@@ -175,7 +175,7 @@ int cds_dynamic_conv(const void* x, int in_mode, const int* img_index, const dou
                      int nc_mode, float* nc_abs, cudaStream_t stream);
 /* Tensor-core (tcgen05 + TMEM + TMA) DynamicConv for the feature extractor's layer shapes (8->8 with kernels
  * (3,7,11) [conv00, image padded to 8 channels by cds_image_to_nhwc8], (3,5,7), (1,3); 16->16 with (3,5), (1,3);
- * 32->32 with (1,3)), fp16 storage, W >= 128.  Same semantics and outputs as cds_dynamic_conv.
+ * 32->32 with (1,3)), fp16 storage, W >= 8.  Same semantics and outputs as cds_dynamic_conv.
  * x: [n_images,H,W,Cin] fp16; item i reads image img_index[i] (NULL: i); wgt_packed: fp16 operand image from the host
  * (cds_dynamic_conv_tc_weight_halfs() halfs, layout in csrc/dynconv_tc.cu).  kernel_sizes is a HOST array.
  * Split-precision activations (value + fp16 rounding residual as two fp16 planes, ~22 bits): split_in = 1 means x is
