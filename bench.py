@@ -162,7 +162,7 @@ def run_reference_arm(args, cfg, rank, world):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(key, cfg):
@@ -171,7 +171,29 @@ def workload_name(key, cfg):
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Everything that writes to stdout while the job runs (NCCL's version banner, library chatter) is sent to stderr; the one
+    JSON line goes to the real stdout at the end."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -408,7 +430,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
