@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
     pixel_ray(k, (float)x, (float)y, rx, ry, rz);
     const float* dp = depth + (size_t)b * D * P + (size_t)y * w + x;
 
-    // online softmax statistics: m = running max, S = sum e^(s-m), A = sum (s-m) e^(s-m)
+    // online softmax statistics: m = running max, S = sum e^(s-m), A = sum (s-m) e^(s-m).  After the channel reduction every
+    // lane of the pixel holds the similarity of every plane of the step; lane `chunk` folds only plane d0 + chunk into ITS
+    // statistics (one update per step instead of LPP), and the LPP partial statistics are merged once at the end.
     float m = -INFINITY, S = 0.f, A = 0.f;
     // the hypothesis of the NEXT step is fetched one step ahead: it streams from DRAM, and the gathers that depend on
     // it would otherwise see two memory latencies back to back
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
             project_fast(k, rx, ry, rz, dep, u, vv);
             mine = make_foot(u, vv, w, h);
         }
+        float my_s = 0.f;
 #pragma unroll
         for (int j = 0; j < LPP; ++j) {
             if (d0 + j >= D) break;   // warp-uniform
@@ -172,19 +175,35 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
             float s = s2.x + s2.y;
 #pragma unroll
             for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (j == chunk) my_s = s;
+        }
+        if (d0 + chunk < D) {
+            const float s = my_s;
             if (s > m) {
-                float delta = m - s;  // <= 0 (or -inf on the first plane)
-                float e = __expf(delta);
-                const bool first = (d0 + j) == 0;
+                const float delta = m - s;  // <= 0 (or -inf on this lane's first plane)
+                const float e = __expf(delta);
+                const bool first = S == 0.f;
                 A = first ? 0.f : e * (A + delta * S);
                 S = first ? 0.f : S * e;
                 m = s;
             }
-            float z = s - m;
-            float e = __expf(z);
+            const float z = s - m;
+            const float e = __expf(z);
             S += e;
             A += z * e;
         }
+    }
+    // merge the lanes' partial statistics: rebasing (m_i, S_i, A_i) to the common maximum M gives S_i e^(m_i - M) and
+    // (A_i + (m_i - M) S_i) e^(m_i - M); a lane that saw no plane (D < LPP) contributes nothing
+#pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), So = __shfl_xor_sync(0xffffffffu, S, o), Ao = __shfl_xor_sync(0xffffffffu, A, o);
+        const float M = fmaxf(m, mo);
+        const float ea = S > 0.f ? __expf(m - M) : 0.f, eb = So > 0.f ? __expf(mo - M) : 0.f;
+        const float Sa = S > 0.f ? S : 0.f, da = S > 0.f ? m - M : 0.f, db = So > 0.f ? mo - M : 0.f;
+        A = (A + da * Sa) * ea + (Ao + db * So) * eb;
+        S = Sa * ea + So * eb;
+        m = M;
     }
     if (live && chunk == 0) entropy[((size_t)v * B + b) * P + (size_t)y * w + x] = __logf(S) - A / S;
 }
