@@ -10,10 +10,16 @@
 // (pixel, 8-channel chunk) so each bilinear tap is one 16-byte (fp16) load and the C/8 lanes of
 // a pixel reduce the channel sum with warp shuffles.
 //
-// Both kernels are instruction-issue bound (ncu: 78 % issue-active, IPC 3.1), so the work per gather is
-// trimmed: the C/8 lanes of a pixel SHARE the projection + bilinear-footprint arithmetic (each lane does it
-// for one plane / one view and broadcasts 6 words by shuffle), interior footprints take a branch-free fast
-// path, and the blend / dot products run as packed fp32x2 FMAs (FFMA2, sm_100).
+// Both kernels are instruction-issue bound (ncu: 74-78 % issue-active, IPC 3), so the work per gather is trimmed:
+//   * the C/8 lanes of a pixel SHARE the projection + bilinear-footprint arithmetic (each lane does it for one plane /
+//     one view and broadcasts it by shuffle), interior footprints take a branch-free fast path;
+//   * a footprint always names a 2x2 block inside the image (border footprints slide and re-slot their weights), so the
+//     four taps are one 64-bit multiply-add per row plus immediates;
+//   * fp16 storage never converts a tap to fp32: pass 1 takes per-tap dot products on FHFMA (sm_100 mixed-precision FMA,
+//     fp16 x fp16 + fp32), pass 2 blends the taps in packed half and multiplies by the reference chunk on FHFMA;
+//   * fp32 storage blends and multiplies as packed fp32x2 FMAs (FFMA2).
+#include <cstdlib>
+#include <type_traits>
 #include "cds_common.cuh"
 
 namespace {
@@ -58,12 +64,12 @@ struct Pix8<float> {
     }
 };
 
-// Bilinear footprint in gather form: pixel offset of the (clamped) top-left tap, whether the right / lower
-// neighbours are distinct pixels, and the four weights (0 for taps outside the image: zero padding,
-// warping.py:100-101).
+// Bilinear footprint in gather form: pixel offset of the top-left pixel of a 2x2 block that ALWAYS lies inside the
+// image (x in [0, w-2], y in [0, h-2]) and the weights of its four pixels.  A footprint that straddles the border is
+// slid onto the nearest inside block and its weights move to the slots their pixels now occupy (0 for taps outside
+// the image: zero padding, warping.py:100-101), so the four loads sit at fixed offsets from one address.
 struct Foot {
     int o00;     // ya * w + xa
-    int step;    // bit 0: xb != xa, bit 1: yb != ya
     float w00, w01, w10, w11;
 };
 __device__ __forceinline__ Foot make_foot(float u, float v, int w, int h) {
@@ -74,14 +80,17 @@ __device__ __forceinline__ Foot make_foot(float u, float v, int w, int h) {
         float fx = u - (float)x0, fy = v - (float)y0;
         float gx = 1.f - fx, gy = 1.f - fy;
         f.o00 = y0 * w + x0;
-        f.step = 3;
         f.w00 = gx * gy; f.w01 = fx * gy; f.w10 = gx * fy; f.w11 = fx * fy;
     } else {
-        Taps t = make_taps(u, v, w, h);
-        int xa = min(max(t.x0, 0), w - 1), xb = min(max(t.x0 + 1, 0), w - 1);
-        int ya = min(max(t.y0, 0), h - 1), yb = min(max(t.y0 + 1, 0), h - 1);
+        Taps t = make_taps(u, v, w, h);   // weights of outside taps are already 0
+        const int xa = min(max(t.x0, 0), w - 2), ya = min(max(t.y0, 0), h - 2);
+        // column x0 sits in slot x0 - xa: -1 (x0 = -1: only the right tap is inside, it is slot 0 now), 0, or 1 (x0 = w-1:
+        // only the left tap is inside, it is slot 1 now); anything further away has no inside tap at all
+        if (t.x0 < xa) { t.w00 = t.w01; t.w10 = t.w11; t.w01 = 0.f; t.w11 = 0.f; }
+        else if (t.x0 > xa) { t.w01 = t.w00; t.w11 = t.w10; t.w00 = 0.f; t.w10 = 0.f; }
+        if (t.y0 < ya) { t.w00 = t.w10; t.w01 = t.w11; t.w10 = 0.f; t.w11 = 0.f; }
+        else if (t.y0 > ya) { t.w10 = t.w00; t.w11 = t.w01; t.w00 = 0.f; t.w01 = 0.f; }
         f.o00 = ya * w + xa;
-        f.step = (xb != xa ? 1 : 0) | (yb != ya ? 2 : 0);
         f.w00 = t.w00; f.w01 = t.w01; f.w10 = t.w10; f.w11 = t.w11;
     }
     return f;
@@ -90,7 +99,6 @@ __device__ __forceinline__ Foot make_foot(float u, float v, int w, int h) {
 __device__ __forceinline__ Foot shfl_foot(const Foot& f, int src) {
     Foot g;
     g.o00 = __shfl_sync(0xffffffffu, f.o00, src);
-    g.step = __shfl_sync(0xffffffffu, f.step, src);
     g.w00 = __shfl_sync(0xffffffffu, f.w00, src);
     g.w01 = __shfl_sync(0xffffffffu, f.w01, src);
     g.w10 = __shfl_sync(0xffffffffu, f.w10, src);
@@ -98,27 +106,115 @@ __device__ __forceinline__ Foot shfl_foot(const Foot& f, int src) {
     return g;
 }
 
-// bilinear blend of 8 channels at footprint f; fea points at (image, this thread's channel chunk)
+// The four tap addresses of footprint f for this thread's channel chunk: one 64-bit multiply-add for the block's first
+// row, one for its second, and compile-time immediates for the right-hand column.  `pix0` is the pixel index of the
+// image's first pixel inside `fea` (view / batch offset), `fea` already points at the thread's channel chunk.
 template <typename T, int C>
-__device__ __forceinline__ void gather8(const T* __restrict__ fea, int w, const Foot& f, float2 (&out)[4]) {
-    const T* p00 = fea + (size_t)(unsigned)(f.o00 * C);
-    const int dx = (f.step & 1) ? C : 0;
-    const int dy = (f.step & 2) ? w * C : 0;
+struct TapAddr {
+    const char* r0;
+    const char* r1;
+    static constexpr int kPix = C * (int)sizeof(T);
+    __device__ __forceinline__ TapAddr(const T* fea, unsigned pix0, int w, const Foot& f) {
+        const unsigned p = pix0 + (unsigned)f.o00;
+        r0 = reinterpret_cast<const char*>(fea) + (size_t)p * kPix;
+        r1 = reinterpret_cast<const char*>(fea) + (size_t)(p + (unsigned)w) * kPix;
+    }
+    __device__ __forceinline__ const T* t00() const { return reinterpret_cast<const T*>(r0); }
+    __device__ __forceinline__ const T* t01() const { return reinterpret_cast<const T*>(r0 + kPix); }
+    __device__ __forceinline__ const T* t10() const { return reinterpret_cast<const T*>(r1); }
+    __device__ __forceinline__ const T* t11() const { return reinterpret_cast<const T*>(r1 + kPix); }
+};
+
+// bilinear blend of 8 channels at footprint f
+template <typename T, int C>
+__device__ __forceinline__ void gather8(const T* __restrict__ fea, unsigned pix0, int w, const Foot& f, float2 (&out)[4]) {
+    const TapAddr<T, C> ta(fea, pix0, w, f);
     float2 a[4], b[4], c[4], d[4];
-    Pix8<T>::load(p00, a);
-    Pix8<T>::load(p00 + dx, b);
-    Pix8<T>::load(p00 + dy, c);
-    Pix8<T>::load(p00 + dy + dx, d);
+    Pix8<T>::load(ta.t00(), a);
+    Pix8<T>::load(ta.t01(), b);
+    Pix8<T>::load(ta.t10(), c);
+    Pix8<T>::load(ta.t11(), d);
     const float2 w00 = make_float2(f.w00, f.w00), w01 = make_float2(f.w01, f.w01);
     const float2 w10 = make_float2(f.w10, f.w10), w11 = make_float2(f.w11, f.w11);
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = ffma2(w11, d[i], ffma2(w10, c[i], ffma2(w01, b[i], fmul2(w00, a[i]))));
 }
 
+// ---- similarity of one reference pixel chunk with a footprint: sum_c ref[c] * blend[c] --------------------------
+// fp32 storage: blend, then dot.  fp16 storage: the sum is re-associated as sum_t w_t (ref . tap_t), and each tap's
+// dot product runs on the mixed-precision FMA of sm_100 (FHFMA: fp16 x fp16 + fp32 -> fp32, exact products, no
+// fp16 -> fp32 conversions, ref stays packed in 4 registers).
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float dot8_f16(const uint4& r, const uint4& t) {
+    const uint32_t* rr = &r.x;
+    const uint32_t* tt = &t.x;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc = fhfma((uint16_t)(rr[i] & 0xffffu), (uint16_t)(tt[i] & 0xffffu), acc);
+        acc = fhfma((uint16_t)(rr[i] >> 16), (uint16_t)(tt[i] >> 16), acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ __half2 as_half2(uint32_t x) { return reinterpret_cast<__half2&>(x); }
+__device__ __forceinline__ uint32_t as_u32(__half2 x) { return reinterpret_cast<uint32_t&>(x); }
+
+template <typename T, int C>
+struct RefChunk;
+template <int C>
+struct RefChunk<float, C> {
+    float2 ref[4];
+    __device__ __forceinline__ void load(const float* p) { Pix8<float>::load(p, ref); }
+    __device__ __forceinline__ float similarity(const float* fea, unsigned pix0, int w, const Foot& f) const {
+        float2 wv[4];
+        gather8<float, C>(fea, pix0, w, f, wv);
+        float2 s2 = fmul2(ref[0], wv[0]);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) s2 = ffma2(ref[i], wv[i], s2);
+        return s2.x + s2.y;
+    }
+};
+template <int C>
+struct RefChunk<__half, C> {
+    uint4 ref;
+    __device__ __forceinline__ void load(const __half* p) { ref = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ float similarity(const __half* fea, unsigned pix0, int w, const Foot& f) const {
+        const TapAddr<__half, C> ta(fea, pix0, w, f);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ta.t00()));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(ta.t01()));
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(ta.t10()));
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(ta.t11()));
+        return f.w11 * dot8_f16(ref, d) + (f.w10 * dot8_f16(ref, c) + (f.w01 * dot8_f16(ref, b) + f.w00 * dot8_f16(ref, a)));
+    }
+    // same with the weights as two half2 (w00, w01), (w10, w11): packed-half blend of the taps, then one FHFMA dot product
+    __device__ __forceinline__ float similarity_packed(const __half* fea, int w, int o00, uint32_t wa, uint32_t wb) const {
+        Foot f;
+        f.o00 = o00;
+        const TapAddr<__half, C> ta(fea, 0u, w, f);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ta.t00()));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(ta.t01()));
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(ta.t10()));
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(ta.t11()));
+        const __half2 w00 = __low2half2(as_half2(wa)), w01 = __high2half2(as_half2(wa));
+        const __half2 w10 = __low2half2(as_half2(wb)), w11 = __high2half2(as_half2(wb));
+        const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+        uint4 bl;
+        uint32_t* o = &bl.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            o[i] = as_u32(__hfma2(w11, as_half2(pd[i]), __hfma2(w10, as_half2(pc[i]), __hfma2(w01, as_half2(pb[i]), __hmul2(w00, as_half2(pa[i]))))));
+        return dot8_f16(ref, bl);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // pass 1: entropy[v, b, y, x] = H(softmax_d(sum_c ref[c] * warp_d[c]))
 // ---------------------------------------------------------------------------------------------
-template <typename T, int C>
+template <typename T, int C, bool PACKED>
 __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                       const float* __restrict__ coef, const float* __restrict__ depth,
                                                       int V, int B, int D, int h, int w, float* __restrict__ entropy) {
@@ -137,9 +233,11 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
     const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
 
     const T* rf = ref_fea + (((size_t)v * B + b) * P + (size_t)y * w + x) * C + chunk * 8;
-    const T* sf = src_fea + ((size_t)v * B + b) * P * C + chunk * 8;
-    float2 ref[4];
-    Pix8<T>::load(rf, ref);
+    // the thread's channel chunk of the source features; the (view, batch item) image starts at pixel pix0 of it
+    const T* sf = src_fea + chunk * 8;
+    const unsigned pix0 = (unsigned)((v * B + b) * P);
+    RefChunk<T, C> ref;
+    ref.load(rf);
     WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
     float rx, ry, rz;
     pixel_ray(k, (float)x, (float)y, rx, ry, rz);
@@ -161,18 +259,31 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
             float u, vv;
             project_fast(k, rx, ry, rz, dep, u, vv);
             mine = make_foot(u, vv, w, h);
+            mine.o00 += (int)pix0;   // the footprint carries the image's offset: one add per step, not per gather
+        }
+        uint32_t m_wa = 0, m_wb = 0;   // PACKED (fp16 storage): the weights travel as two half2, 3 shuffles per footprint
+        if constexpr (PACKED) {
+            m_wa = as_u32(__floats2half2_rn(mine.w00, mine.w01));
+            m_wb = as_u32(__floats2half2_rn(mine.w10, mine.w11));
         }
         float my_s = 0.f;
 #pragma unroll
         for (int j = 0; j < LPP; ++j) {
             if (d0 + j >= D) break;   // warp-uniform
-            Foot f = LPP == 1 ? mine : shfl_foot(mine, lane_base + j);
-            float2 wv[4];
-            gather8<T, C>(sf, w, f, wv);
-            float2 s2 = fmul2(ref[0], wv[0]);
-#pragma unroll
-            for (int i = 1; i < 4; ++i) s2 = ffma2(ref[i], wv[i], s2);
-            float s = s2.x + s2.y;
+            float s;
+            if constexpr (PACKED) {
+                int o00 = mine.o00;
+                uint32_t wa = m_wa, wb = m_wb;
+                if (LPP > 1) {
+                    o00 = __shfl_sync(0xffffffffu, mine.o00, lane_base + j);
+                    wa = __shfl_sync(0xffffffffu, m_wa, lane_base + j);
+                    wb = __shfl_sync(0xffffffffu, m_wb, lane_base + j);
+                }
+                s = ref.similarity_packed(sf, w, o00, wa, wb);
+            } else {
+                Foot f = LPP == 1 ? mine : shfl_foot(mine, lane_base + j);
+                s = ref.similarity(sf, 0u, w, f);
+            }
 #pragma unroll
             for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (j == chunk) my_s = s;
@@ -213,8 +324,8 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
 // Lane `chunk` of a pixel owns the projection of views chunk, chunk + LPP, ... (its rays and translations stay in
 // registers) and broadcasts each footprint to the pixel's other lanes.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int C, int VMAX>
-__global__ void __launch_bounds__(256, VMAX <= 4 ? 3 : 2) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
+template <typename T, int C, int VMAX, int MINB>
+__global__ void __launch_bounds__(256, MINB) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                         const float* __restrict__ coef, const float* __restrict__ depth,
                                                         const float* __restrict__ vis, int V, int B, int D, int h, int w,
                                                         T* __restrict__ volume) {
@@ -258,8 +369,24 @@ __global__ void __launch_bounds__(256, VMAX <= 4 ? 3 : 2) aggregate_kernel(const
     // channel-blocked volume [B][C/8][D][h][w][8]: one 8-channel slab of a row is contiguous (what conv0's TMA wants)
     T* outp = volume + (((size_t)b * LPP + chunk) * D * P + pofs) * 8;
     const T* rbase = ref_fea + ((size_t)b * P + pofs) * C + chunk * 8;
-    const T* sbase = src_fea + (size_t)b * P * C + chunk * 8;
+    const T* sbase = src_fea + chunk * 8;
     const size_t vstride = (size_t)B * P * C;
+    const unsigned BP = (unsigned)(B * P), bP = (unsigned)(b * P);
+    // Up to 4 views: the pixel's reference chunks stay in registers for the whole sweep, already scaled by
+    // vis_v / (sum vis + 1e-6), so a plane costs one FMA per channel and view after the blend.  More views: the
+    // chunks are re-read per plane (L1-resident after the first one).
+    constexpr bool kRefInRegs = VMAX <= 4;
+    float2 rv[kRefInRegs ? VMAX : 1][4];
+    if (kRefInRegs) {
+#pragma unroll
+        for (int v = 0; v < VMAX; ++v) {
+            const float sc = vw[v] * inv;
+            if (v < V) Pix8<T>::load(rbase + (size_t)v * vstride, rv[kRefInRegs ? v : 0]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                rv[kRefInRegs ? v : 0][i] = v < V ? fmul2(rv[kRefInRegs ? v : 0][i], make_float2(sc, sc)) : make_float2(0.f, 0.f);
+        }
+    }
 
     float dep_next = __ldg(dp);
     for (int d = 0; d < D; ++d) {
@@ -277,26 +404,146 @@ __global__ void __launch_bounds__(256, VMAX <= 4 ? 3 : 2) aggregate_kernel(const
                     float py = ory[q] * dep + oty[q];
                     float iz = __frcp_rn(orz[q] * dep + otz[q]);
                     mine = make_foot(px * iz, py * iz, w, h);
+                    mine.o00 += (int)(bP + (unsigned)(q * LPP + chunk) * BP);   // offset of the owned view's image
                 }
 #pragma unroll
                 for (int j = 0; j < LPP; ++j) {
                     const int v = q * LPP + j;
                     if (v < VMAX && v < V) {   // warp-uniform
                         Foot f = LPP == 1 ? mine : shfl_foot(mine, lane_base + j);
-                        float2 wv[4], ref[4];
-                        gather8<T, C>(sbase + (size_t)v * vstride, w, f, wv);
-                        Pix8<T>::load(rbase + (size_t)v * vstride, ref);   // L1-resident after the first plane
-                        const float2 vv2 = make_float2(vw[v], vw[v]);
+                        float2 wv[4];
+                        gather8<T, C>(sbase, 0u, w, f, wv);
+                        if (kRefInRegs) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[i] = ffma2(fmul2(ref[i], wv[i]), vv2, acc[i]);
+                            for (int i = 0; i < 4; ++i) acc[i] = ffma2(rv[kRefInRegs ? v : 0][i], wv[i], acc[i]);
+                        } else {
+                            float2 ref[4];
+                            Pix8<T>::load(rbase + (size_t)v * vstride, ref);   // L1-resident after the first plane
+                            const float2 vv2 = make_float2(vw[v] * inv, vw[v] * inv);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[i] = ffma2(fmul2(ref[i], wv[i]), vv2, acc[i]);
+                        }
                     }
                 }
             }
         }
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { o[2 * i] = acc[i].x * inv; o[2 * i + 1] = acc[i].y * inv; }
+        for (int i = 0; i < 4; ++i) { o[2 * i] = acc[i].x; o[2 * i + 1] = acc[i].y; }
         if (live) Vec8<T>::store(outp + (size_t)d * P * 8, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2, fp16 storage.  Same sweep, arithmetic arranged for the fp16 feature maps:
+//   * the owner lane folds vis_v / (sum vis + 1e-6) into the four bilinear weights and packs them as two half2
+//     (3 shuffles per footprint instead of 5);
+//   * the blend of the four taps runs as packed HFMA2 on the raw loaded words -- no fp16 -> fp32 conversions.  Its
+//     rounding (fp16 weights, fp16 partial sums) is of the size of the fp16 rounding the stored volume has anyway;
+//   * the product with the reference chunk and the sum over views accumulate in fp32 through FHFMA
+//     (fp16 x fp16 + fp32), with the pixel's reference chunks held packed in registers (4 per view) for the whole sweep.
+// ---------------------------------------------------------------------------------------------
+template <int C, int VMAX, int MINB>
+__global__ void __launch_bounds__(256, MINB) aggregate_f16_kernel(const __half* __restrict__ ref_fea, const __half* __restrict__ src_fea,
+                                                                  const float* __restrict__ coef, const float* __restrict__ depth,
+                                                                  const float* __restrict__ vis, int V, int B, int D, int h, int w,
+                                                                  __half* __restrict__ volume) {
+    constexpr int LPP = C / 8;
+    constexpr int OWN = (VMAX + LPP - 1) / LPP;   // views whose projection this lane may own (V <= VMAX)
+    const int P = h * w;
+    const int b = blockIdx.y;
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    const bool live = gid < P * LPP;
+    const int g = live ? gid : P * LPP - 1;
+    const int chunk = g % LPP;
+    const int pix = g / LPP;
+    const int x = pix % w, y = pix / w;
+    const size_t pofs = (size_t)pix;
+    const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
+
+    float vsum = 0.f;
+    for (int v = 0; v < V; ++v) vsum += __ldg(vis + ((size_t)v * B + b) * P + pofs);  // reference order (model.py:59)
+    const float inv = 1.f / (vsum + 1e-6f);
+    const __half* rbase = ref_fea + ((size_t)b * P + pofs) * C + chunk * 8;
+    const size_t vstride = (size_t)B * P * C;
+    // per owned view: ray, translation, weight scale vis_v / (sum vis + 1e-6)
+    float orx[OWN], ory[OWN], orz[OWN], otx[OWN], oty[OWN], otz[OWN], osc[OWN];
+#pragma unroll
+    for (int q = 0; q < OWN; ++q) {
+        int v = q * LPP + chunk;
+        if (v < V) {
+            WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
+            pixel_ray(k, (float)x, (float)y, orx[q], ory[q], orz[q]);
+            otx[q] = k.t[0]; oty[q] = k.t[1]; otz[q] = k.t[2] + 1e-6f;
+            osc[q] = __ldg(vis + ((size_t)v * B + b) * P + pofs) * inv;
+        } else {
+            orx[q] = ory[q] = orz[q] = otx[q] = oty[q] = 0.f; otz[q] = 1.f; osc[q] = 0.f;
+        }
+    }
+    // this thread's chunk of every view's reference features, packed fp16
+    uint4 rf[VMAX];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) rf[v] = v < V ? __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)v * vstride)) : make_uint4(0, 0, 0, 0);
+
+    const float* dp = depth + (size_t)b * D * P + pofs;
+    __half* outp = volume + (((size_t)b * LPP + chunk) * D * P + pofs) * 8;
+    const __half* sbase = src_fea + chunk * 8;
+    const unsigned BP = (unsigned)(B * P), bP = (unsigned)(b * P);
+
+    float dep_next = __ldg(dp);
+    for (int d = 0; d < D; ++d) {
+        const float dep = dep_next;
+        dep_next = __ldg(dp + (size_t)min(d + 1, D - 1) * P);   // one plane ahead (see entropy_kernel)
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < OWN; ++q) {
+            if (q * LPP < V) {   // warp-uniform
+                int m_o00;
+                uint32_t m_wa, m_wb;   // (w00, w01), (w10, w11) scaled by the view's visibility share
+                {
+                    float px = orx[q] * dep + otx[q];
+                    float py = ory[q] * dep + oty[q];
+                    float iz = __frcp_rn(orz[q] * dep + otz[q]);
+                    Foot mine = make_foot(px * iz, py * iz, w, h);
+                    m_o00 = mine.o00 + (int)(bP + (unsigned)(q * LPP + chunk) * BP);   // offset of the owned view's image
+                    m_wa = as_u32(__floats2half2_rn(mine.w00 * osc[q], mine.w01 * osc[q]));
+                    m_wb = as_u32(__floats2half2_rn(mine.w10 * osc[q], mine.w11 * osc[q]));
+                }
+#pragma unroll
+                for (int j = 0; j < LPP; ++j) {
+                    const int v = q * LPP + j;
+                    if (v < VMAX && v < V) {   // warp-uniform
+                        Foot f;
+                        uint32_t wa = m_wa, wb = m_wb;
+                        f.o00 = m_o00;
+                        if (LPP > 1) {
+                            f.o00 = __shfl_sync(0xffffffffu, m_o00, lane_base + j);
+                            wa = __shfl_sync(0xffffffffu, m_wa, lane_base + j);
+                            wb = __shfl_sync(0xffffffffu, m_wb, lane_base + j);
+                        }
+                        const TapAddr<__half, C> ta(sbase, 0u, w, f);
+                        const uint4 t00 = __ldg(reinterpret_cast<const uint4*>(ta.t00()));
+                        const uint4 t01 = __ldg(reinterpret_cast<const uint4*>(ta.t01()));
+                        const uint4 t10 = __ldg(reinterpret_cast<const uint4*>(ta.t10()));
+                        const uint4 t11 = __ldg(reinterpret_cast<const uint4*>(ta.t11()));
+                        const __half2 w00 = __low2half2(as_half2(wa)), w01 = __high2half2(as_half2(wa));
+                        const __half2 w10 = __low2half2(as_half2(wb)), w11 = __high2half2(as_half2(wb));
+                        const uint32_t* a = &t00.x; const uint32_t* bq = &t01.x; const uint32_t* c = &t10.x; const uint32_t* e = &t11.x;
+                        const uint32_t* r = &rf[v].x;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t s = as_u32(__hfma2(w11, as_half2(e[i]), __hfma2(w10, as_half2(c[i]),
+                                                      __hfma2(w01, as_half2(bq[i]), __hmul2(w00, as_half2(a[i]))))));
+                            acc[2 * i] = fhfma((uint16_t)(r[i] & 0xffffu), (uint16_t)(s & 0xffffu), acc[2 * i]);
+                            acc[2 * i + 1] = fhfma((uint16_t)(r[i] >> 16), (uint16_t)(s >> 16), acc[2 * i + 1]);
+                        }
+                    }
+                }
+            }
+        }
+        if (live) Vec8<__half>::store(outp + (size_t)d * P * 8, acc);
     }
 }
 
@@ -316,10 +563,18 @@ int launch_entropy(const void* ref, const void* src, const float* coef, const fl
     dim3 blocks(cds_div_up((long long)h * w * (C / 8), 256), V * B);
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
+    // fp16 storage: fp32 tap weights on per-tap FHFMA dot products.  CDS_ENTROPY_PACKED=1 opts into the packed-half blend of
+    // aggregate_f16_kernel (10 % faster, but the entropy's error grows from < 2e-4 to 5e-4, measured on B200)
+    static const bool packed = [] { const char* e = getenv("CDS_ENTROPY_PACKED"); return e && e[0] == '1'; }();
+    constexpr bool kHalf = std::is_same<T, __half>::value;
+#define CDS_ENT(c)                                                                                                          \
+    if (kHalf && packed) entropy_kernel<T, c, kHalf><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy); \
+    else entropy_kernel<T, c, false><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy);                    \
+    break;
     switch (C) {
-        case 8: entropy_kernel<T, 8><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy); break;
-        case 16: entropy_kernel<T, 16><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy); break;
-        case 32: entropy_kernel<T, 32><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy); break;
+        case 8: CDS_ENT(8)
+        case 16: CDS_ENT(16)
+        case 32: CDS_ENT(32)
         default: cds_set_error("cds_costvol_entropy: C must be 8, 16 or 32 (got %d)", C); return CDS_EUNSUPPORTED;
     }
     return cds_check_launch("cds_costvol_entropy");
@@ -332,9 +587,30 @@ int launch_aggregate(const void* ref, const void* src, const float* coef, const 
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
     T* o = (T*)volume;
-#define CDS_AGG(c)                                                                                              \
-    if (V <= 4) aggregate_kernel<T, c, 4><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);     \
-    else aggregate_kernel<T, c, kMaxViews><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);     \
+    // fp32 storage (and CDS_COSTVOL_BLEND=f32): fp32 blend.  fp16 storage: packed-half blend, see aggregate_f16_kernel.
+    static const int occ = [] { const char* e = getenv("CDS_AGG_OCC"); return e ? atoi(e) : 0; }();
+    static const bool blend32 = [] { const char* e = getenv("CDS_COSTVOL_BLEND"); return e && e[0] == 'f' && e[1] == '3'; }();
+    if constexpr (std::is_same<T, __half>::value) {
+        if (!blend32) {
+#define CDS_AGGH(c, ob)                                                                                                     \
+    if (V <= 4 && (occ ? occ : ob) == 4) aggregate_f16_kernel<c, 4, 4><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); \
+    else if (V <= 4 && (occ ? occ : ob) == 3) aggregate_f16_kernel<c, 4, 3><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); \
+    else if (V <= 4) aggregate_f16_kernel<c, 4, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);        \
+    else aggregate_f16_kernel<c, kMaxViews, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);           \
+    break;
+            switch (C) {
+                case 8: CDS_AGGH(8, 4)
+                case 16: CDS_AGGH(16, 3)
+                case 32: CDS_AGGH(32, 3)
+                default: cds_set_error("cds_costvol_aggregate: C must be 8, 16 or 32 (got %d)", C); return CDS_EUNSUPPORTED;
+            }
+            return cds_check_launch("cds_costvol_aggregate");
+        }
+    }
+#define CDS_AGG(c)                                                                                                 \
+    if (V <= 4 && occ == 2) aggregate_kernel<T, c, 4, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); \
+    else if (V <= 4) aggregate_kernel<T, c, 4, 3><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);   \
+    else aggregate_kernel<T, c, kMaxViews, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);    \
     break;
     switch (C) {
         case 8: CDS_AGG(8)
@@ -354,7 +630,7 @@ int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* c
     CDS_REQUIRE(ref_fea && src_fea && coef && depth && entropy, CDS_EARG, "cds_costvol_entropy: null pointer");
     CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
                 "cds_costvol_entropy: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
-    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B <= 65535, CDS_ESHAPE,
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B * h * w < (1ll << 31) && (long long)V * B <= 65535, CDS_ESHAPE,
                 "cds_costvol_entropy: feature map too large for 32-bit offsets");
     if (dtype == CDS_F16) return launch_entropy<__half>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     if (dtype == CDS_F32) return launch_entropy<float>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
@@ -368,7 +644,7 @@ int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float*
     CDS_REQUIRE(ref_fea && src_fea && coef && depth && vis && volume, CDS_EARG, "cds_costvol_aggregate: null pointer");
     CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
                 "cds_costvol_aggregate: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
-    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && B <= 65535, CDS_ESHAPE,
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B * h * w < (1ll << 31) && B <= 65535, CDS_ESHAPE,
                 "cds_costvol_aggregate: feature map too large for 32-bit offsets");
     if (dtype == CDS_F16) return launch_aggregate<__half>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     if (dtype == CDS_F32) return launch_aggregate<float>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
