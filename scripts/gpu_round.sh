@@ -16,7 +16,7 @@ N=${NCU_LIST_COUNT:-69}
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s $N -c $N --csv --log-file $O/${TAG}_launches.csv \
     python scripts/run_forward.py --iters 2 > $O/${TAG}_ncu_list.log 2>&1
 # --set full of the kernels named in NCU_KERNELS as "<regex>:<skip>" pairs
-for KS in ${NCU_KERNELS:-dynconv_tc_kernel:0 aggregate_kernel:1}; do
+for KS in ${NCU_KERNELS:-dynconv_tc_kernel:0 aggregate_f16_kernel:1}; do
   K=${KS%%:*}; S=${KS##*:}
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c 1 -f -o $O/${TAG}_${K}_$S \
       python scripts/run_forward.py --iters 1 > $O/${TAG}_ncu_${K}_$S.log 2>&1
