@@ -95,7 +95,7 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-LAUNCHES = 0   # C-ABI calls issued by this process (every one enqueues exactly one kernel)
+LAUNCHES = 0   # C-ABI calls issued by this process (every inference entry enqueues exactly one kernel)
 
 
 class LaunchProfile:

@@ -45,8 +45,7 @@ def _f32c(t):
 # ------------------------------------------------------------------------------------------------
 # functions
 # ------------------------------------------------------------------------------------------------
-def homo_warping_3D(src_fea, src_proj, ref_proj, depth_values):
-    """[B,C,H,W], [B,4,4], [B,4,4], [B,D] | [B,D,H,W] -> [B,C,D,H,W] (models/utils/warping.py:69-104)."""
+def _warp_forward(src_fea, src_proj, ref_proj, depth_values):
     dev = _dev(src_fea)
     B, C, H, Wd = src_fea.shape
     D = depth_values.shape[1]
@@ -59,11 +58,44 @@ def homo_warping_3D(src_fea, src_proj, ref_proj, depth_values):
     out = torch.empty(B, C, D, H, Wd, dtype=torch.float32, device=dev)
     src, dep = _f32c(src_fea), _f32c(depth_values)
     call("cds_homo_warp", ptr(src), ptr(coef), ptr(dep), int(per_pixel), B, C, D, H, Wd, ptr(out))
-    return out
+    return out, coef, dep
 
 
-def depth_regression(p, depth_values):
-    """sum_d p_d * depth_d (models/module.py:373-379); depth_values [B,D] or [B,D,H,W]."""
+class _HomoWarpFn(torch.autograd.Function):
+    """homo_warping_3D with its backward: the gradient reaches src_fea only, the grid is no_grad (warping.py:79)."""
+
+    @staticmethod
+    def forward(ctx, src_fea, src_proj, ref_proj, depth_values):
+        out, coef, dep = _warp_forward(src_fea, src_proj, ref_proj, depth_values)
+        ctx.save_for_backward(coef, dep)
+        ctx.src_shape, ctx.src_dtype = tuple(src_fea.shape), src_fea.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        coef, dep = ctx.saved_tensors
+        B, C, H, Wd = ctx.src_shape
+        D = dep.shape[1]
+        g = _f32c(grad_out)
+        if C % 4 == 0:   # vector reductions into a channels-last workspace, then one layout pass (two kernels behind one call)
+            grad_src = torch.empty(B, C, H, Wd, dtype=torch.float32, device=g.device)
+            ws = torch.zeros(B, H, Wd, C, dtype=torch.float32, device=g.device)
+        else:
+            grad_src, ws = torch.zeros(B, C, H, Wd, dtype=torch.float32, device=g.device), None
+        call("cds_homo_warp_backward", ptr(g), ptr(coef), ptr(dep), int(dep.dim() == 4), B, C, D, H, Wd, ptr(grad_src), ptr(ws))
+        return grad_src.to(ctx.src_dtype), None, None, None
+
+
+def homo_warping_3D(src_fea, src_proj, ref_proj, depth_values):
+    """[B,C,H,W], [B,4,4], [B,4,4], [B,D] | [B,D,H,W] -> [B,C,D,H,W] (models/utils/warping.py:69-104).
+
+    Differentiable in ``src_fea`` (the only gradient the reference propagates, warping.py:79)."""
+    if torch.is_grad_enabled() and src_fea.requires_grad:
+        return _HomoWarpFn.apply(src_fea, src_proj, ref_proj, depth_values)
+    return _warp_forward(src_fea, src_proj, ref_proj, depth_values)[0]
+
+
+def _regress_forward(p, depth_values):
     dev = _dev(p)
     B, D, H, Wd = p.shape
     out = torch.empty(B, H, Wd, dtype=torch.float32, device=dev)
@@ -71,7 +103,39 @@ def depth_regression(p, depth_values):
     if dv.dim() == 1:
         dv = dv.unsqueeze(0).expand(B, D).contiguous()
     call("cds_softmax_regress", ptr(pc), ptr(dv), int(dv.dim() == 4), 1, B, D, H, Wd, ptr(out), None, None)
-    return out
+    return out, pc, dv
+
+
+class _DepthRegressFn(torch.autograd.Function):
+    """depth_regression with its backward (d/dp = g * depth_d, d/d depth = g * p_d)."""
+
+    @staticmethod
+    def forward(ctx, p, depth_values):
+        out, pc, dv = _regress_forward(p, depth_values)
+        ctx.save_for_backward(pc, dv)
+        ctx.dv_shape, ctx.dtypes = tuple(depth_values.shape), (p.dtype, depth_values.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_depth):
+        pc, dv = ctx.saved_tensors
+        B, D, H, Wd = pc.shape
+        g = _f32c(grad_depth)
+        need_p, need_dv = ctx.needs_input_grad
+        grad_p = torch.empty_like(pc) if need_p else None
+        grad_dv = torch.empty_like(pc) if need_dv else None
+        call("cds_depth_regress_backward", ptr(g), ptr(pc), ptr(dv), int(dv.dim() == 4), B, D, H, Wd, ptr(grad_p), ptr(grad_dv))
+        if need_dv and len(ctx.dv_shape) != 4:   # plane depths shared by all pixels: fold the per-pixel products
+            grad_dv = grad_dv.sum((2, 3))
+            grad_dv = grad_dv.sum(0) if len(ctx.dv_shape) == 1 else grad_dv
+        return (grad_p.to(ctx.dtypes[0]) if need_p else None), (grad_dv.to(ctx.dtypes[1]) if need_dv else None)
+
+
+def depth_regression(p, depth_values):
+    """sum_d p_d * depth_d (models/module.py:373-379); depth_values [B,D] or [B,D,H,W].  Differentiable."""
+    if torch.is_grad_enabled() and (p.requires_grad or depth_values.requires_grad):
+        return _DepthRegressFn.apply(p, depth_values)
+    return _regress_forward(p, depth_values)[0]
 
 
 def conf_regression(p, n=4):

@@ -255,6 +255,29 @@ int cds_deconv2d_k3s2_f32(const float* in, const float* wgt, const float* bias, 
 int cds_refine_final(const float* x, const float* res_wgt, const float* depth_n, const float* lo, const float* hi, const float* post,
                      int B, int h, int w, float* out, cudaStream_t stream);
 
+/* ---- next row (first slice): backward passes of the op-level drop-ins and the stage loss ---------------- */
+/* Adjoint of cds_homo_warp in src_fea (the sampling grid carries no gradient, models/utils/warping.py:79): grad_out
+ * [B,C,D,h,w] fp32 is scattered with the forward's bilinear weights into grad_src [B,C,h,w] fp32 (float reductions: the
+ * order of the adds, hence the last bits, varies from run to run).  workspace == NULL: scalar reductions straight into
+ * grad_src, which the CALLER ZEROES first (any C).  workspace != NULL (C % 4 == 0): B*h*w*C floats ZEROED by the caller
+ * receive 16-byte vector reductions in channels-last order and a second kernel writes grad_src (need not be zeroed). */
+int cds_homo_warp_backward(const float* grad_out, const float* coef, const float* depth, int depth_per_pixel, int B, int C,
+                           int D, int h, int w, float* grad_src, float* workspace, cudaStream_t stream);
+/* depth_regression backward (models/module.py:373-379): grad_p[b,d] = grad_depth[b] * depth[b,d] and
+ * grad_dv[b,d] = grad_depth[b] * prob[b,d], both [B,D,h,w]; either output may be NULL (then its input may be too). */
+int cds_depth_regress_backward(const float* grad_depth, const float* prob, const float* depth, int depth_per_pixel, int B, int D,
+                               int h, int w, float* grad_p, float* grad_dv, cudaStream_t stream);
+/* One stage of final_loss (models/losses.py:14-23): ADDS to sums[0..2] (fp64, zeroed by the caller) the smooth-L1 sum of
+ * est/interval - gt/interval over mask > 0.5, the mask count, and the masked sum of norm_curv (NULL: skipped).
+ * est, gt, mask, norm_curv [B,h,w] fp32; interval [B]. */
+int cds_stage_loss_forward(const float* est, const float* gt, const float* mask, const float* interval, const float* norm_curv,
+                           int B, int h, int w, double* sums, cudaStream_t stream);
+/* Its backward: grad_est = *g_depth * smooth_l1'(.) / (interval * count), grad_curv = *g_curv / count on the mask, 0 off it
+ * (g_depth, g_curv: device scalars, the upstream gradients of the two means; sums from the forward call). */
+int cds_stage_loss_backward(const float* est, const float* gt, const float* mask, const float* interval, const double* sums,
+                            const float* g_depth, const float* g_curv, int B, int h, int w, float* grad_est, float* grad_curv,
+                            cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@ into the reference tree, TruongKhang/cds-mvsnet @ 2a84f7a):
 * DynamicConv / FeatureNet ........ models/dynamic_conv.py:81-122, models/module.py:28-71,201-267
 * fundamental matrix / epipoles ... models/dynamic_conv.py:7-47
 * cascade driver .................. models/model.py:140-223
+* backward of warp / soft-argmin .. models/utils/warping.py:79,100-101, models/module.py:373-379 (what autograd derives)
+* training loss (no feat term) .... models/losses.py:6-48
 
 The dense arithmetic the reference delegates to PyTorch 1.6 ATen/cuDNN (conv2d/conv3d/
 conv_transpose3d, softmax, instance/batch norm, linalg inverse; third-party, not vendored in
@@ -145,6 +147,45 @@ def homo_warp(src_fea, src_proj, ref_proj, depth_values):
     return bilinear_gather_zeros(src_fea, u, v).reshape(B, C, D, h, w)
 
 
+def bilinear_scatter_zeros(grad: torch.Tensor, u: torch.Tensor, v: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """Adjoint of ``bilinear_gather_zeros`` in ``fea``: grad [B,C,M] at coords (u,v) [B,M] -> [B,C,h,w].
+
+    What autograd does for the reference's grid_sample when only ``src_fea`` carries a gradient (the grid is built
+    under no_grad, warping.py:79): every sample adds weight * grad to its in-image taps, out-of-image taps are dropped.
+    """
+    B, C, M = grad.shape
+    un = u / ((w - 1) / 2) - 1
+    vn = v / ((h - 1) / 2) - 1
+    u = (un + 1) / 2 * (w - 1)
+    v = (vn + 1) / 2 * (h - 1)
+    x0 = torch.floor(u)
+    y0 = torch.floor(v)
+    fx, fy = u - x0, v - y0
+    out = torch.zeros(B, C, h * w, dtype=torch.float64)
+    for dy, dx, wgt in ((0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)), (1, 0, (1 - fx) * fy), (1, 1, fx * fy)):
+        xi, yi = x0 + dx, y0 + dy
+        ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
+        idx = (yi.clamp(0, h - 1) * w + xi.clamp(0, w - 1)).long()
+        contrib = (grad * (wgt * ok).unsqueeze(1)).double()   # fp64 accumulation: the order of the adds is not the reference's
+        out.scatter_add_(2, idx.unsqueeze(1).expand(B, C, -1), contrib)
+    return out.reshape(B, C, h, w).float()
+
+
+def homo_warp_backward(grad_out, src_proj, ref_proj, depth_values):
+    """d(loss)/d(src_fea) of homo_warping_3D given d(loss)/d(out) [B,C,D,h,w] (warping.py:79: coordinates carry no gradient)."""
+    B, C, D, h, w = grad_out.shape
+    rot, trans = warp_coefficients(src_proj, ref_proj)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)), 0)
+    ray = rot @ pix.unsqueeze(0)
+    dep = depth_values.reshape(B, 1, D, -1)
+    p = ray.unsqueeze(2) * dep + trans.reshape(B, 3, 1, 1)
+    z = p[:, 2] + 1e-6
+    u = (p[:, 0] / z).reshape(B, -1)
+    v = (p[:, 1] / z).reshape(B, -1)
+    return bilinear_scatter_zeros(grad_out.reshape(B, C, -1), u, v, h, w)
+
+
 # ----------------------------------------------------------------------------------------------
 # hypotheses (A9)
 # ----------------------------------------------------------------------------------------------
@@ -211,6 +252,17 @@ def depth_regression(p, depth_values):
     if depth_values.dim() <= 2:
         depth_values = depth_values.reshape(*depth_values.shape, 1, 1)
     return (p * depth_values).sum(1)
+
+
+def depth_regression_backward(grad_depth, p, depth_values):
+    """(d/dp, d/d depth_values) of sum_d p_d * depth_d (module.py:373-379) given d(loss)/d(depth) [B,h,w]."""
+    dv = depth_values.reshape(*depth_values.shape, 1, 1) if depth_values.dim() <= 2 else depth_values
+    g = grad_depth.unsqueeze(1)
+    grad_p = g * dv.expand_as(p)
+    grad_dv = g * p
+    if depth_values.dim() <= 2:
+        grad_dv = grad_dv.sum((2, 3)).reshape(depth_values.shape)
+    return grad_p, grad_dv
 
 
 def conf_regression(p, n: int = 4):
@@ -438,6 +490,43 @@ def cdsmvsnet_forward(sd, imgs, proj_matrices, depth_values, ndepths, ratios, te
 # ----------------------------------------------------------------------------------------------
 # helpers shared by tests / bench
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# training loss: models/losses.py:6-48 without the feat_distance term
+# ----------------------------------------------------------------------------------------------
+def stage_loss(est, gt, mask, interval, curv=None):
+    """(smooth-L1 mean of est/iv - gt/iv over mask > 0.5, masked mean of curv) -- losses.py:14-23, fp64 sums."""
+    iv = interval.reshape(-1, 1, 1)
+    on = (mask > 0.5)
+    diff = (est / iv - gt / iv)
+    a = diff.abs()
+    per = torch.where(a < 1, 0.5 * diff * diff, a - 0.5)
+    n = on.double().sum()
+    depth_loss = ((per.double() * on).sum() / n).float()
+    curv_mean = None if curv is None else ((curv.reshape(est.shape).double() * on).sum() / n).float()
+    return depth_loss, curv_mean
+
+
+def stage_loss_backward(est, gt, mask, interval, g_depth=1.0, g_curv=1.0):
+    """(d/d est, d/d curv) of the two means above."""
+    iv = interval.reshape(-1, 1, 1)
+    on = (mask > 0.5)
+    diff = (est / iv - gt / iv)
+    n = on.float().sum()
+    slope = torch.where(diff.abs() < 1, diff, torch.sign(diff))
+    return g_depth * slope / iv / n * on, g_curv * on.float() / n
+
+
+def final_loss(inputs, depth_gt_ms, mask_ms, dlossw=None, depth_interval=None):
+    total, depth_loss = torch.zeros(()), None
+    for i, k in enumerate(("stage1", "stage2", "stage3")):
+        depth_loss, curv = stage_loss(inputs[k]["depth"], depth_gt_ms[k], mask_ms[k], depth_interval, inputs[k]["norm_curv"])
+        total = total + (1.0 if dlossw is None else dlossw[i]) * (depth_loss + 0.1 * curv)
+    if "refined_depth" in inputs:
+        depth_loss, _ = stage_loss(inputs["refined_depth"], depth_gt_ms["stage4"], mask_ms["stage4"], depth_interval)
+        total = total + 2 * depth_loss
+    return total, depth_loss
+
+
 def rel_l1(a: torch.Tensor, b: torch.Tensor) -> float:
     """mean |a-b| / mean |b| -- the parity metric north_star quotes (1e-3 on depth)."""
     return float((a.double() - b.double()).abs().mean() / b.double().abs().mean().clamp_min(1e-30))

@@ -1,0 +1,158 @@
+"""Training slice: the backward kernels of the op-level drop-ins and the stage loss, called through
+autograd over the C ABI, against the gradients of the live reference (train_ops.npz), against the CPU oracle on seeded
+inputs, and at full size through the adjoint identity.
+
+Tolerances: fp32 arithmetic; the scatter's float reductions arrive in a run-dependent order, so the bound is the fp32
+re-association floor of a sum of <= a few hundred terms (a few 1e-6 relative to the largest gradient), plus the same
+~1e-4 px coordinate noise as the forward test (fp64 coefficient inverse here, fp32 torch.inverse in the reference)."""
+import pytest
+import torch
+
+import cds_mvsnet_b200 as C
+from cds_mvsnet_b200 import losses, synthetic
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def close(a, b, atol, rtol=1e-5):
+    torch.testing.assert_close(a.float().cpu(), b.float().cpu(), atol=atol, rtol=rtol)
+
+
+# ------------------------------------------------------------------------------------------ A1 backward
+def test_homo_warp_backward_golden(golden):
+    g = golden("train_ops")
+    for tag in ("planes", "pix"):
+        fea = cu(g["warp_src_fea"]).requires_grad_(True)
+        out = C.homo_warping_3D(fea, cu(g["warp_src_proj"]), cu(g["warp_ref_proj"]), cu(g[f"warp_depth_{tag}"]))
+        assert out.requires_grad
+        out.backward(cu(g["warp_grad_out"]))
+        # gradient magnitudes reach ~30 (sums of up to ~50 unit-normal terms); coordinate noise moves a weight by ~1e-4
+        close(fea.grad, g[f"warp_grad_src_{tag}"], 3e-3, 1e-4)
+        assert O.rel_l1(fea.grad.cpu(), g[f"warp_grad_src_{tag}"]) < 2e-4
+
+
+@pytest.mark.parametrize("Cc", [5, 8])   # 5: scalar reductions into NCHW; 8: vector reductions into the channels-last workspace
+def test_homo_warp_backward_oracle_random(Cc):
+    torch.manual_seed(3)
+    s = synthetic.make_sample(dict(W=64, H=64, N=2, ndepths=(8,), ratios=(1.0,), B=3, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage1"]
+    refP, srcP = O.compose_projection(pm[:, 0]), O.compose_projection(pm[:, 1])
+    dv = 425 + 500 * torch.rand(3, 7, 16, 16)
+    g_out = torch.randn(3, Cc, 7, 16, 16)
+    fea = torch.randn(3, Cc, 16, 16, device=DEV, requires_grad=True)
+    C.homo_warping_3D(fea, cu(srcP), cu(refP), cu(dv)).backward(cu(g_out))
+    want = O.homo_warp_backward(g_out, srcP, refP, dv)
+    assert O.rel_l1(fea.grad.cpu(), want) < 1e-4
+    close(fea.grad, want, 1e-3, 1e-4)
+    # no gradient reaches the cameras or the hypotheses (the reference builds the grid under no_grad, warping.py:79)
+    fea2 = fea.detach().clone().requires_grad_(True)
+    dvg, sp = cu(dv).requires_grad_(True), cu(srcP).requires_grad_(True)
+    C.homo_warping_3D(fea2, sp, cu(refP), dvg).sum().backward()
+    assert dvg.grad is None and sp.grad is None and fea2.grad is not None
+    # inference calls stay on the plain path
+    with torch.no_grad():
+        assert not C.homo_warping_3D(fea, cu(srcP), cu(refP), cu(dv)).requires_grad
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32, 256, 320), (1, 16, 32, 592, 800)])
+def test_homo_warp_adjoint_full_size(shape):
+    """<warp(x), g> = <x, warp^T(g)> at the stage-2 training shape and at cfg2's stage-2 shape (1600x1184 / 2, D = 32)."""
+    B, Cc, D, h, w = shape
+    torch.manual_seed(11)
+    s = synthetic.make_sample(dict(W=2 * w, H=2 * h, N=2, ndepths=(48, 32, 8), ratios=(4.0, 1.5, 0.75), B=B, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage2"]
+    refP, srcP = cu(O.compose_projection(pm[:, 0])), cu(O.compose_projection(pm[:, 1]))
+    dv = 500 + 300 * torch.rand(B, D, h, w, device=DEV)
+    x = torch.randn(B, Cc, h, w, device=DEV, requires_grad=True)
+    g = torch.randn(B, Cc, D, h, w, device=DEV)
+    out = C.homo_warping_3D(x, srcP, refP, dv)
+    lhs = (out.detach().double() * g.double()).sum()
+    out.backward(g)
+    rhs = (x.detach().double() * x.grad.double()).sum()
+    assert (out.detach() != 0).float().mean() > 0.1          # the views overlap: the identity is not trivially 0 = 0
+    assert abs(lhs - rhs) <= 2e-6 * (out.detach().double() * g.double()).abs().sum()
+    # linearity of the adjoint: warp^T(2g) = 2 warp^T(g) up to the reduction order
+    x2 = x.detach().clone().requires_grad_(True)
+    C.homo_warping_3D(x2, srcP, refP, dv).backward(2 * g)
+    assert O.rel_l1(x2.grad, 2 * x.grad) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ A5 backward
+def test_depth_regression_backward_golden(golden):
+    g = golden("train_ops")
+    for tag in ("planes", "pix"):
+        p = cu(g["regress_p"]).requires_grad_(True)
+        dv = cu(g[f"warp_depth_{tag}"]).requires_grad_(True)
+        C.depth_regression(p, dv).backward(cu(g["regress_grad_depth"]))
+        close(p.grad, g[f"regress_grad_p_{tag}"], 0.0, 0.0)              # one product per element: exact
+        close(dv.grad, g[f"regress_grad_dv_{tag}"], 2e-4 if tag == "planes" else 0.0, 1e-5)   # planes: a sum over h*w pixels
+    # hypotheses without a gradient (the cascade's case, models/model.py:177-178 detaches them)
+    p = cu(g["regress_p"]).requires_grad_(True)
+    C.depth_regression(p, cu(g["warp_depth_pix"])).backward(cu(g["regress_grad_depth"]))
+    close(p.grad, g["regress_grad_p_pix"], 0.0, 0.0)
+
+
+def test_softargmin_chain_matches_torch_autograd():
+    """softmax (torch) -> depth_regression (CUDA backward) against the same chain differentiated by torch alone."""
+    torch.manual_seed(5)
+    logits = torch.randn(2, 8, 24, 40, device=DEV)
+    dv = 425 + 500 * torch.rand(2, 8, 24, 40, device=DEV)
+    gd = torch.randn(2, 24, 40, device=DEV)
+    a = logits.clone().requires_grad_(True)
+    C.depth_regression(torch.softmax(a, 1), dv).backward(gd)
+    b = logits.clone().requires_grad_(True)
+    (torch.softmax(b, 1) * dv).sum(1).backward(gd)
+    close(a.grad, b.grad, 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------ loss
+def loss_case(g, requires_grad=True):
+    mk = (lambda t: cu(t).requires_grad_(True)) if requires_grad else cu
+    inputs = {f"stage{i}": {"depth": mk(g[f"loss_in_stage{i}.depth"]), "norm_curv": mk(g[f"loss_in_stage{i}.norm_curv"])} for i in (1, 2, 3)}
+    inputs["refined_depth"] = mk(g["loss_in_refined_depth"])
+    gts = {f"stage{i}": cu(g[f"loss_gt_stage{i}"]) for i in (1, 2, 3, 4)}
+    masks = {f"stage{i}": cu(g[f"loss_mask_stage{i}"]) for i in (1, 2, 3, 4)}
+    return inputs, gts, masks
+
+
+def test_final_loss_golden(golden):
+    g = golden("train_ops")
+    inputs, gts, masks = loss_case(g)
+    total, dl = losses.final_loss(inputs, gts, masks, dlossw=g["loss_dlossw"].tolist(), depth_interval=cu(g["loss_interval"]))
+    close(total, g["loss_total"], 1e-6, 2e-6)
+    close(dl, g["loss_depth"], 1e-6, 2e-6)
+    total.backward()
+    for i in (1, 2, 3):
+        close(inputs[f"stage{i}"]["depth"].grad, g[f"loss_grad_stage{i}.depth"], 1e-9, 1e-5)
+        close(inputs[f"stage{i}"]["norm_curv"].grad, g[f"loss_grad_stage{i}.norm_curv"], 1e-9, 1e-5)
+    close(inputs["refined_depth"].grad, g["loss_grad_refined_depth"], 1e-9, 1e-5)
+
+
+def test_final_loss_edges(golden):
+    g = golden("train_ops")
+    inputs, gts, masks = loss_case(g, requires_grad=False)
+    # no weights, no refined depth: the reference's `else` branch (losses.py:39-40)
+    del inputs["refined_depth"]
+    total, _ = losses.final_loss(inputs, gts, masks, depth_interval=cu(g["loss_interval"]))
+    cpu_in = {k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in inputs.items()}
+    want, _ = O.final_loss(cpu_in, {k: v.cpu() for k, v in gts.items()}, {k: v.cpu() for k, v in masks.items()},
+                           depth_interval=g["loss_interval"])
+    close(total, want, 1e-6, 2e-6)
+    # an empty mask gives NaN like the reference's mean over an empty selection
+    masks["stage2"] = torch.zeros_like(masks["stage2"])
+    total, _ = losses.final_loss(inputs, gts, masks, depth_interval=cu(g["loss_interval"]))
+    assert torch.isnan(total)
+    # the training-mode term is not built: loud, not silent
+    inputs["stage1"]["feat_distance"] = torch.zeros(1, device=DEV)
+    with pytest.raises(NotImplementedError):
+        losses.final_loss(inputs, gts, masks, depth_interval=cu(g["loss_interval"]))
+    # CPU tensors are refused
+    with pytest.raises(RuntimeError):
+        losses.final_loss({k: {kk: vv.cpu() for kk, vv in v.items() if kk != "feat_distance"} for k, v in inputs.items()},
+                          {k: v.cpu() for k, v in gts.items()}, {k: v.cpu() for k, v in masks.items()}, depth_interval=g["loss_interval"])

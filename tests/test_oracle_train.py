@@ -1,0 +1,57 @@
+"""Training slice: the oracle's backward / loss restatements against the gradients of the LIVE reference
+(tests/golden/make_golden_train.py -> train_ops.npz).  CPU only."""
+import torch
+
+from oracle import oracle as O
+
+torch.set_grad_enabled(False)
+
+
+def close(a, b, atol, rtol=1e-5):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    torch.testing.assert_close(a, b, atol=atol, rtol=rtol)
+
+
+def test_warp_backward(golden):
+    g = golden("train_ops")
+    for tag in ("planes", "pix"):
+        got = O.homo_warp_backward(g["warp_grad_out"], g["warp_src_proj"], g["warp_ref_proj"], g[f"warp_depth_{tag}"])
+        close(got, g[f"warp_grad_src_{tag}"], 4e-6)
+    # the adjoint identity <warp(x), g> = <x, warp^T(g)> ties the backward restatement to the forward one
+    x = g["warp_src_fea"]
+    fwd = O.homo_warp(x, g["warp_src_proj"], g["warp_ref_proj"], g["warp_depth_pix"])
+    lhs = (fwd.double() * g["warp_grad_out"].double()).sum()
+    rhs = (x.double() * g["warp_grad_src_pix"].double()).sum()
+    assert abs(lhs - rhs) <= 1e-6 * abs(lhs)
+
+
+def test_depth_regression_backward(golden):
+    g = golden("train_ops")
+    for tag in ("planes", "pix"):
+        gp, gdv = O.depth_regression_backward(g["regress_grad_depth"], g["regress_p"], g[f"warp_depth_{tag}"])
+        close(gp, g[f"regress_grad_p_{tag}"], 0.0, 0.0)
+        close(gdv, g[f"regress_grad_dv_{tag}"], 1e-5)
+
+
+def loss_case(g):
+    inputs = {f"stage{i}": {"depth": g[f"loss_in_stage{i}.depth"], "norm_curv": g[f"loss_in_stage{i}.norm_curv"]} for i in (1, 2, 3)}
+    inputs["refined_depth"] = g["loss_in_refined_depth"]
+    gts = {f"stage{i}": g[f"loss_gt_stage{i}"] for i in (1, 2, 3, 4)}
+    masks = {f"stage{i}": g[f"loss_mask_stage{i}"] for i in (1, 2, 3, 4)}
+    return inputs, gts, masks
+
+
+def test_final_loss(golden):
+    g = golden("train_ops")
+    inputs, gts, masks = loss_case(g)
+    w = g["loss_dlossw"].tolist()
+    total, dl = O.final_loss(inputs, gts, masks, dlossw=w, depth_interval=g["loss_interval"])
+    close(total, g["loss_total"], 1e-6)
+    close(dl, g["loss_depth"], 1e-6)
+    for i in (1, 2, 3):
+        k = f"stage{i}"
+        ge, gc = O.stage_loss_backward(inputs[k]["depth"], gts[k], masks[k], g["loss_interval"], w[i - 1], 0.1 * w[i - 1])
+        close(ge, g[f"loss_grad_{k}.depth"], 1e-9, 1e-5)
+        close(gc.unsqueeze(1), g[f"loss_grad_{k}.norm_curv"], 1e-9, 1e-5)
+    ge, _ = O.stage_loss_backward(inputs["refined_depth"], gts["stage4"], masks["stage4"], g["loss_interval"], 2.0, 0.0)
+    close(ge, g["loss_grad_refined_depth"], 1e-9, 1e-5)
