@@ -461,6 +461,119 @@ __global__ void __launch_bounds__(128) conv1x1_cat_kernel(const T* __restrict__ 
     if (out_stats) accumulate_stats2<COUT>(st, out_stats + (size_t)n * COUT * 2, s_red);
 }
 
+// Same op, one thread per 2x2 block of output pixels: the four pixels share their half-resolution A pixel, so its
+// CA x COUT product is formed once and seeds their accumulators; every weight row fetched from shared memory feeds the
+// four pixels (a quarter of the LDS traffic that bounded the one-pixel form); the multiply-adds are packed fp32x2 (FFMA2).
+// fp32 arithmetic on the stored activations: no operand rounding beyond the storage type's own.
+__device__ __forceinline__ float2 ffma2x(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+    return d;
+}
+
+constexpr int kQuadChunks = 4;   // 2x2 blocks per thread
+
+template <typename T, int CA, int CB, int COUT>
+__global__ void __launch_bounds__(128) conv1x1_cat_quad_kernel(const T* __restrict__ A, const double* __restrict__ a_stats, int a_act,
+                                                               const T* __restrict__ Bp, const double* __restrict__ b_stats, int b_act,
+                                                               const float* __restrict__ wgt /*[CA+CB][COUT]*/, int H, int W,
+                                                               T* __restrict__ out, double* __restrict__ out_stats) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int CIN = CA + CB, N2 = COUT / 2;
+    float* s_w = sm;                   // [CIN][COUT]
+    float* s_norm = s_w + CIN * COUT;  // [CIN][2]
+    float* s_red = s_norm + CIN * 2;   // [4][COUT][2]
+    const int n = blockIdx.y;
+    const int Ha = H / 2, Wa = W / 2;
+    for (int i = threadIdx.x; i < CIN * COUT / 4; i += blockDim.x)
+        reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wgt) + i);
+    for (int c = threadIdx.x; c < CIN; c += blockDim.x) {
+        s_norm[2 * c] = 0.f;
+        s_norm[2 * c + 1] = 1.f;
+        if (c < CA && a_stats) norm_coeffs(a_stats, n, CA, c, (double)Ha * Wa, s_norm[2 * c], s_norm[2 * c + 1]);
+        if (c >= CA && b_stats) norm_coeffs(b_stats, n, CB, c - CA, (double)H * W, s_norm[2 * c], s_norm[2 * c + 1]);
+    }
+    __syncthreads();
+    float st[2][COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { st[0][c] = 0.f; st[1][c] = 0.f; }
+#pragma unroll 1
+    for (int chunk = 0; chunk < kQuadChunks; ++chunk) {
+        const long long q = ((long long)blockIdx.x * kQuadChunks + chunk) * blockDim.x + threadIdx.x;
+        if (q >= (long long)Ha * Wa) continue;
+        const int bx = (int)(q % Wa), by = (int)(q / Wa);
+        float2 acc[4][N2];
+        {   // the shared half-resolution pixel
+            float2 accA[N2];
+#pragma unroll
+            for (int k = 0; k < N2; ++k) accA[k] = make_float2(0.f, 0.f);
+            const T* pa = A + (((size_t)n * Ha + by) * Wa + bx) * CA;
+#pragma unroll
+            for (int c8 = 0; c8 < CA / 8; ++c8) {
+                float v[8];
+                Vec8<T>::load(pa + c8 * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c8 * 8 + j;
+                    const float t = apply_act((v[j] - s_norm[2 * c]) * s_norm[2 * c + 1], a_act);
+                    const float2* w2 = reinterpret_cast<const float2*>(s_w + c * COUT);
+                    const float2 tt = make_float2(t, t);
+#pragma unroll
+                    for (int k = 0; k < N2; ++k) accA[k] = ffma2x(tt, w2[k], accA[k]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int k = 0; k < N2; ++k) acc[p][k] = accA[k];
+        }
+        const T* pb = Bp + (((size_t)n * H + 2 * by) * W + 2 * bx) * CB;
+#pragma unroll
+        for (int c8 = 0; c8 < CB / 8; ++c8) {
+            float v[4][8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) Vec8<T>::load(pb + ((size_t)(p >> 1) * W + (p & 1)) * CB + c8 * 8, v[p]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = CA + c8 * 8 + j;
+                const float mean = s_norm[2 * c], rstd = s_norm[2 * c + 1];
+                const float2* w2 = reinterpret_cast<const float2*>(s_w + c * COUT);
+                float2 tt[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float t = apply_act((v[p][j] - mean) * rstd, b_act);
+                    tt[p] = make_float2(t, t);
+                }
+#pragma unroll
+                for (int k = 0; k < N2; ++k) {
+                    const float2 w = w2[k];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[p][k] = ffma2x(tt[p], w, acc[p][k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            T* op = out + (((size_t)n * H + 2 * by + (p >> 1)) * W + 2 * bx + (p & 1)) * COUT;
+#pragma unroll
+            for (int c8 = 0; c8 < COUT / 8; ++c8) {
+                float yv[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { yv[2 * j] = acc[p][c8 * 4 + j].x; yv[2 * j + 1] = acc[p][c8 * 4 + j].y; }
+                Vec8<T>::store(op + c8 * 8, yv);
+            }
+#pragma unroll
+            for (int k = 0; k < N2; ++k) {
+                st[0][2 * k] += acc[p][k].x; st[1][2 * k] += acc[p][k].x * acc[p][k].x;
+                st[0][2 * k + 1] += acc[p][k].y; st[1][2 * k + 1] += acc[p][k].y * acc[p][k].y;
+            }
+        }
+    }
+    if (out_stats) accumulate_stats2<COUT>(st, out_stats + (size_t)n * COUT * 2, s_red);
+}
+
 // InstanceNorm + activation materialised (the three stage features: InstanceNorm2d -> Tanh, module.py:223,230,232)
 template <typename T>
 __global__ void __launch_bounds__(256) instnorm_act_kernel(const T* __restrict__ raw, const double* __restrict__ stats, int act,
@@ -593,12 +706,12 @@ int cds_conv2d_1x1_cat(const void* a, const double* a_stats, int a_act, const vo
                        double* out_stats, cudaStream_t stream) {
     CDS_REQUIRE(a && b && wgt && out, CDS_EARG, "cds_conv2d_1x1_cat: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, CDS_ESHAPE, "cds_conv2d_1x1_cat: bad shape");
-    dim3 grid(cds_div_up((long long)H * W, 128 * kChunks), n);
+    dim3 grid(cds_div_up((long long)(H / 2) * (W / 2), 128 * kQuadChunks), n);
 #define CDS_GO(T, ca, cb, co)                                                                                                  \
     {                                                                                                                           \
         size_t smem = sizeof(float) * ((ca + cb) * co + (ca + cb) * 2 + 4 * co * 2);                                            \
-        conv1x1_cat_kernel<T, ca, cb, co><<<grid, 128, smem, stream>>>((const T*)a, a_stats, a_act, (const T*)b, b_stats, b_act, \
-                                                                       wgt, H, W, (T*)out, out_stats);                         \
+        conv1x1_cat_quad_kernel<T, ca, cb, co><<<grid, 128, smem, stream>>>((const T*)a, a_stats, a_act, (const T*)b, b_stats, \
+                                                                            b_act, wgt, H, W, (T*)out, out_stats);             \
         return cds_check_launch("cds_conv2d_1x1_cat");                                                                         \
     }
     if (dtype == CDS_F16) {

@@ -69,6 +69,7 @@ class FeatureExtractor:
         # end-to-end gain on the worst-case input is within sample noise)
         self.split_precision = os.environ.get("CDS_SPLIT", "0") == "1"
         self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
+        self.tc_inner = os.environ.get("CDS_TC_INNER", "1") != "0"   # inner1/inner2 (1x1 over cat) on the tensor cores vs the 2x2-block CUDA-core form
         self._buf = None
         self.pairs = None   # (V, B) when the batch is the cascade's (side, v, b) pair batch
         self.share_ref = os.environ.get("CDS_SHARE_REF", "1") != "0"
@@ -124,7 +125,7 @@ class FeatureExtractor:
         """1x1 conv over cat(nearest-up2(a), b) of FeatureNet.inner1/2."""
         e = _esize(self.storage)
         _lib.set_tag("feat." + name, (2.0 * (ca + cb) * cout * n * H * W, float(n * ((H // 2) * (W // 2) * ca + H * W * (cb + cout)) * e)))
-        if (self.use_tc2d and self.storage == torch.float16 and name in self.fw.tc
+        if (self.use_tc2d and self.tc_inner and self.storage == torch.float16 and name in self.fw.tc
                 and _lib.LIB.load().cds_conv2d_1x1_cat_tc_supported(ca, cb, cout)):
             call("cds_conv2d_1x1_cat_tc", ptr(a), ptr(a_stats), a_act, ptr(b), ptr(b_stats), ACT_LRELU, ptr(self.fw.tc[name]),
                  n, ca, cb, cout, H, W, ptr(out), ptr(out_stats))
