@@ -16,6 +16,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    """Other test modules switch autograd off process-wide at import; these tests need it."""
+    with torch.enable_grad():
+        yield
+
+
 def cu(t):
     return t.to(DEV)
 
@@ -156,3 +163,35 @@ def test_final_loss_edges(golden):
     with pytest.raises(RuntimeError):
         losses.final_loss({k: {kk: vv.cpu() for kk, vv in v.items() if kk != "feat_distance"} for k, v in inputs.items()},
                           {k: v.cpu() for k, v in gts.items()}, {k: v.cpu() for k, v in masks.items()}, depth_interval=g["loss_interval"])
+
+
+def test_training_chain_vs_cpu_autograd():
+    """One source view of the reference's training graph (models/model.py:44-49,85-91 + losses.py:14-23): warp -> similarity ->
+    softmax -> soft-argmin -> masked smooth-L1.  On the GPU the warp, the regression and the loss are the CUDA kernels (forward and
+    backward) and the glue is torch; on the CPU the whole graph is the oracle differentiated by torch.  Gradients w.r.t. both
+    feature maps must agree."""
+    torch.manual_seed(9)
+    B, Cc, D, h, w = 2, 8, 6, 24, 32
+    s = synthetic.make_sample(dict(W=4 * w, H=4 * h, N=2, ndepths=(8,), ratios=(1.0,), B=B, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage1"]
+    refP, srcP = O.compose_projection(pm[:, 0]), O.compose_projection(pm[:, 1])
+    dv = (torch.linspace(450, 900, D).reshape(1, D, 1, 1) + 20 * torch.rand(B, D, h, w)).contiguous()
+    ref0, src0 = torch.tanh(torch.randn(B, Cc, h, w)), torch.tanh(torch.randn(B, Cc, h, w))
+    gt = 450 + 450 * torch.rand(B, h, w)
+    mask = (torch.rand(B, h, w) > 0.3).float()
+    iv = torch.tensor([2.65, 2.5])
+
+    def graph(ref, src, warp, regress, loss, mv):
+        sim = (ref.unsqueeze(2) * warp(src, mv(srcP), mv(refP), mv(dv))).sum(1)
+        depth = regress(torch.softmax(sim, 1), mv(dv))
+        return loss(depth, mv(gt), mv(mask), mv(iv))
+
+    rc, sc = ref0.clone().requires_grad_(True), src0.clone().requires_grad_(True)
+    lc = graph(rc, sc, O.homo_warp, O.depth_regression, lambda d, g, m, i: O.stage_loss(d, g, m, i)[0], lambda t: t)
+    lc.backward()
+    rg, sg = cu(ref0).requires_grad_(True), cu(src0).requires_grad_(True)
+    lg = graph(rg, sg, C.homo_warping_3D, C.depth_regression, lambda d, g, m, i: losses._StageLossFn.apply(d, None, g, m, i)[0], cu)
+    lg.backward()
+    close(lg, lc.detach(), 1e-5, 1e-5)
+    assert O.rel_l1(rg.grad.cpu(), rc.grad) < 2e-4
+    assert O.rel_l1(sg.grad.cpu(), sc.grad) < 2e-4
