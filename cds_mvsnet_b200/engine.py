@@ -69,7 +69,9 @@ class FeatureExtractor:
         # end-to-end gain on the worst-case input is within sample noise)
         self.split_precision = os.environ.get("CDS_SPLIT", "0") == "1"
         self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
-        self.tc_inner = os.environ.get("CDS_TC_INNER", "1") != "0"   # inner1/inner2 (1x1 over cat) on the tensor cores vs the 2x2-block CUDA-core form
+        # inner1/inner2 (1x1 conv over the concatenation): the 2x2-block CUDA-core form (fp32 math, 0.154 / 0.133 ms at cfg2) beats the
+        # gather-form tensor-core kernel (0.289 / 0.156 ms) on this 24- / 48-deep contraction; CDS_TC_INNER=1 selects the latter
+        self.tc_inner = os.environ.get("CDS_TC_INNER", "0") != "0"
         self._buf = None
         self.pairs = None   # (V, B) when the batch is the cascade's (side, v, b) pair batch
         self.share_ref = os.environ.get("CDS_SHARE_REF", "1") != "0"
