@@ -211,6 +211,68 @@ __global__ void __launch_bounds__(256) stage_loss_backward_kernel(const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// feat_distance term of final_loss (models/losses.py:25-35): binary cross entropy with logits over the mask repeated
+// across the D planes, positives weighted by neg / pos.  counts[0] = sum of target over the selection, counts[1] = its size.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) feat_loss_count_kernel(const float* __restrict__ target, const float* __restrict__ mask, int B, int D,
+                                                              long long P, double* __restrict__ counts) {
+    __shared__ double red[8];
+    double pos = 0.0, n = 0.0;
+    const long long total = (long long)B * D * P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / (D * P), p = i % P;
+        if (!(__ldg(mask + b * P + p) > 0.5f)) continue;
+        pos += (double)__ldg(target + i);
+        n += 1.0;
+    }
+    pos = block_sum(pos, red);
+    n = block_sum(n, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(counts, pos);
+        atomicAdd(counts + 1, n);
+    }
+}
+
+// loss_i = (1 - y) x + (1 + (pw - 1) y) softplus(-x), pw = (n - pos) / pos; softplus(-x) = max(-x, 0) + log1p(exp(-|x|))
+__global__ void __launch_bounds__(256) feat_loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                                const float* __restrict__ mask, const double* __restrict__ counts, int B,
+                                                                int D, long long P, double* __restrict__ loss_sum) {
+    __shared__ double red[8];
+    const float pw = (float)((counts[1] - counts[0]) / counts[0]);
+    double l = 0.0;
+    const long long total = (long long)B * D * P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / (D * P), p = i % P;
+        if (!(__ldg(mask + b * P + p) > 0.5f)) continue;
+        const float x = __ldg(logits + i), y = __ldg(target + i);
+        const float sp = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+        l += (double)((1.f - y) * x + (1.f + (pw - 1.f) * y) * sp);
+    }
+    l = block_sum(l, red);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, l);
+}
+
+// d/dx = g * ((1 - y) - (1 + (pw - 1) y) sigmoid(-x)) / n on the selection, 0 elsewhere
+__global__ void __launch_bounds__(256) feat_loss_backward_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                                 const float* __restrict__ mask, const double* __restrict__ counts,
+                                                                 const float* __restrict__ g, int B, int D, long long P,
+                                                                 float* __restrict__ grad) {
+    const float pw = (float)((counts[1] - counts[0]) / counts[0]);
+    const float scale = __ldg(g) * (float)(1.0 / counts[1]);
+    const long long total = (long long)B * D * P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / (D * P), p = i % P;
+        float r = 0.f;
+        if (__ldg(mask + b * P + p) > 0.5f) {
+            const float x = __ldg(logits + i), y = __ldg(target + i);
+            const float sg = 1.f / (1.f + expf(x));   // sigmoid(-x)
+            r = scale * ((1.f - y) - (1.f + (pw - 1.f) * y) * sg);
+        }
+        grad[i] = r;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -265,6 +327,29 @@ int cds_stage_loss_backward(const float* est, const float* gt, const float* mask
     int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
     stage_loss_backward_kernel<<<blocks, 256, 0, stream>>>(est, gt, mask, interval, sums, g_depth, g_curv, B, P, grad_est, grad_curv);
     return cds_check_launch("cds_stage_loss_backward");
+}
+
+int cds_feat_loss_forward(const float* logits, const float* target, const float* mask, int B, int D, int h, int w, double* sums,
+                          cudaStream_t stream) {
+    CDS_REQUIRE(logits && target && mask && sums, CDS_EARG, "cds_feat_loss_forward: null pointer");
+    CDS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0, CDS_ESHAPE, "cds_feat_loss_forward: bad shape");
+    long long P = (long long)h * w, total = (long long)B * D * P;
+    int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
+    feat_loss_count_kernel<<<blocks, 256, 0, stream>>>(target, mask, B, D, P, sums);
+    int rc = cds_check_launch("cds_feat_loss_forward(count)");
+    if (rc) return rc;
+    feat_loss_forward_kernel<<<blocks, 256, 0, stream>>>(logits, target, mask, sums, B, D, P, sums + 2);
+    return cds_check_launch("cds_feat_loss_forward");
+}
+
+int cds_feat_loss_backward(const float* logits, const float* target, const float* mask, const double* sums, const float* g, int B,
+                           int D, int h, int w, float* grad, cudaStream_t stream) {
+    CDS_REQUIRE(logits && target && mask && sums && g && grad, CDS_EARG, "cds_feat_loss_backward: null pointer");
+    CDS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0, CDS_ESHAPE, "cds_feat_loss_backward: bad shape");
+    long long P = (long long)h * w, total = (long long)B * D * P;
+    int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
+    feat_loss_backward_kernel<<<blocks, 256, 0, stream>>>(logits, target, mask, sums, g, B, D, P, grad);
+    return cds_check_launch("cds_feat_loss_backward");
 }
 
 }  // extern "C"

@@ -7,8 +7,9 @@ ground truth over ``mask > 0.5`` plus 0.1 x the masked mean of ``norm_curv``, we
 elementwise kernel backward (``csrc/train.cu``) instead of the reference's boolean-index gathers; the handful of scalar
 combinations stay torch ops on the device (no host sync).
 
-Not built yet: the ``feat_distance`` / ``feat_target`` binary-cross-entropy term (losses.py:25-35), which only exists in the
-training-mode StageNet outputs (models/model.py:52-56,63-78) this package does not produce -- its presence raises.
+The ``feat_distance`` / ``feat_target`` binary-cross-entropy term (losses.py:25-35) is built too (count pass, weighted loss pass,
+elementwise backward), so a training-mode output dict of the REFERENCE's StageNet can be fed; this package's own fused
+StageNet stays inference-only and never produces those keys.
 """
 from __future__ import annotations
 
@@ -61,6 +62,36 @@ class _StageLossFn(torch.autograd.Function):
                 grad_c.reshape(ctx.curv_shape).to(ctx.dtypes[1]) if need_c else None, None, None, None)
 
 
+class _FeatLossFn(torch.autograd.Function):
+    """binary_cross_entropy_with_logits(feat_dis[mask], target[mask], mean, pos_weight = neg / pos), mask repeated over D."""
+
+    @staticmethod
+    def forward(ctx, feat_dis, target, mask):
+        if not feat_dis.is_cuda:
+            raise RuntimeError("cds_b200 ops run on a CUDA device (B200) only; got a CPU tensor. There is no CPU fallback.")
+        B, D, H, Wd = feat_dis.shape
+        x, y, m = _f32c(feat_dis), _f32c(target), _f32c(mask)
+        if tuple(y.shape) != (B, D, H, Wd) or tuple(m.shape) != (B, H, Wd):
+            raise RuntimeError(f"final_loss: feat_distance {tuple(feat_dis.shape)}, feat_target {tuple(target.shape)}, "
+                               f"mask {tuple(mask.shape)} do not agree")
+        sums = torch.zeros(3, dtype=torch.float64, device=x.device)
+        call("cds_feat_loss_forward", ptr(x), ptr(y), ptr(m), B, D, H, Wd, ptr(sums))
+        ctx.save_for_backward(x, y, m, sums)
+        ctx.dtype = feat_dis.dtype
+        return (sums[2] / sums[1]).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, m, sums = ctx.saved_tensors
+        B, D, H, Wd = x.shape
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        gg = _f32c(g)
+        grad = torch.empty_like(x)
+        call("cds_feat_loss_backward", ptr(x), ptr(y), ptr(m), ptr(sums), ptr(gg), B, D, H, Wd, ptr(grad))
+        return grad.to(ctx.dtype), None, None
+
+
 def final_loss(inputs, depth_gt_ms, mask_ms, **kwargs):
     """models/losses.py:6-48 -> (total_loss, depth_loss of the last term)."""
     depth_loss_weights = kwargs.get("dlossw", None)
@@ -72,13 +103,13 @@ def final_loss(inputs, depth_gt_ms, mask_ms, **kwargs):
     depth_loss = 0.0
     for stage_key in ("stage1", "stage2", "stage3"):
         stage_inputs = inputs[stage_key]
-        if "feat_distance" in stage_inputs:
-            raise NotImplementedError("final_loss: the feat_distance / feat_target term of training-mode StageNet outputs "
-                                      "(models/losses.py:25-35) is not built (SURVEY.md 8f-3)")
         depth_loss, curv_reg = _StageLossFn.apply(stage_inputs["depth"], stage_inputs["norm_curv"], depth_gt_ms[stage_key],
                                                   mask_ms[stage_key], depth_interval)
+        feat_loss = 0.0
+        if "feat_distance" in stage_inputs:
+            feat_loss = _FeatLossFn.apply(stage_inputs["feat_distance"], stage_inputs["feat_target"], mask_ms[stage_key])
         w = 1.0 if depth_loss_weights is None else depth_loss_weights[int(stage_key.replace("stage", "")) - 1]
-        total_loss = total_loss + w * (depth_loss + 0.1 * curv_reg)
+        total_loss = total_loss + w * (depth_loss + 5 * feat_loss + 0.1 * curv_reg)
     if "refined_depth" in inputs:
         depth_loss, _ = _StageLossFn.apply(inputs["refined_depth"], None, depth_gt_ms["stage4"], mask_ms["stage4"], depth_interval)
         total_loss = total_loss + 2 * depth_loss

@@ -277,6 +277,14 @@ int cds_stage_loss_forward(const float* est, const float* gt, const float* mask,
 int cds_stage_loss_backward(const float* est, const float* gt, const float* mask, const float* interval, const double* sums,
                             const float* g_depth, const float* g_curv, int B, int h, int w, float* grad_est, float* grad_curv,
                             cudaStream_t stream);
+/* The feat_distance term of final_loss (models/losses.py:25-35): binary cross entropy with logits over mask > 0.5 repeated
+ * across the D planes, positives weighted by neg / pos.  logits, target [B,D,h,w]; mask [B,h,w].  ADDS to sums[0..2] (fp64,
+ * zeroed by the caller): sum of target over the selection, size of the selection, sum of the weighted loss terms (two
+ * kernels: the weight needs the counts).  Backward: grad [B,D,h,w] = *g * d(mean)/d(logits), 0 off the selection. */
+int cds_feat_loss_forward(const float* logits, const float* target, const float* mask, int B, int D, int h, int w, double* sums,
+                          cudaStream_t stream);
+int cds_feat_loss_backward(const float* logits, const float* target, const float* mask, const double* sums, const float* g, int B,
+                           int D, int h, int w, float* grad, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ into the reference tree, TruongKhang/cds-mvsnet @ 2a84f7a):
 * fundamental matrix / epipoles ... models/dynamic_conv.py:7-47
 * cascade driver .................. models/model.py:140-223
 * backward of warp / soft-argmin .. models/utils/warping.py:79,100-101, models/module.py:373-379 (what autograd derives)
-* training loss (no feat term) .... models/losses.py:6-48
+* training loss ................... models/losses.py:6-48
 
 The dense arithmetic the reference delegates to PyTorch 1.6 ATen/cuDNN (conv2d/conv3d/
 conv_transpose3d, softmax, instance/batch norm, linalg inverse; third-party, not vendored in
@@ -491,7 +491,7 @@ def cdsmvsnet_forward(sd, imgs, proj_matrices, depth_values, ndepths, ratios, te
 # helpers shared by tests / bench
 # ----------------------------------------------------------------------------------------------
 # ----------------------------------------------------------------------------------------------
-# training loss: models/losses.py:6-48 without the feat_distance term
+# training loss: models/losses.py:6-48
 # ----------------------------------------------------------------------------------------------
 def stage_loss(est, gt, mask, interval, curv=None):
     """(smooth-L1 mean of est/iv - gt/iv over mask > 0.5, masked mean of curv) -- losses.py:14-23, fp64 sums."""
@@ -516,11 +516,31 @@ def stage_loss_backward(est, gt, mask, interval, g_depth=1.0, g_curv=1.0):
     return g_depth * slope / iv / n * on, g_curv * on.float() / n
 
 
+def feat_loss(feat_dis, target, mask):
+    """losses.py:25-35: BCE with logits over mask > 0.5 repeated across the planes, positives weighted by neg / pos."""
+    on = (mask > 0.5).unsqueeze(1).expand_as(feat_dis)
+    n = on.double().sum()
+    pos = (target.double() * on).sum()
+    pw = ((n - pos) / pos).float()
+    x, y = feat_dis, target
+    softplus_neg = torch.clamp(-x, min=0) + torch.log1p(torch.exp(-x.abs()))
+    per = (1 - y) * x + (1 + (pw - 1) * y) * softplus_neg
+    return ((per.double() * on).sum() / n).float()
+
+
+def feat_loss_backward(feat_dis, target, mask, g=1.0):
+    on = (mask > 0.5).unsqueeze(1).expand_as(feat_dis)
+    n = on.float().sum()
+    pw = (n - (target * on).sum()) / (target * on).sum()
+    return g * ((1 - target) - (1 + (pw - 1) * target) * torch.sigmoid(-feat_dis)) / n * on
+
+
 def final_loss(inputs, depth_gt_ms, mask_ms, dlossw=None, depth_interval=None):
     total, depth_loss = torch.zeros(()), None
     for i, k in enumerate(("stage1", "stage2", "stage3")):
         depth_loss, curv = stage_loss(inputs[k]["depth"], depth_gt_ms[k], mask_ms[k], depth_interval, inputs[k]["norm_curv"])
-        total = total + (1.0 if dlossw is None else dlossw[i]) * (depth_loss + 0.1 * curv)
+        fl = feat_loss(inputs[k]["feat_distance"], inputs[k]["feat_target"], mask_ms[k]) if "feat_distance" in inputs[k] else 0.0
+        total = total + (1.0 if dlossw is None else dlossw[i]) * (depth_loss + 5 * fl + 0.1 * curv)
     if "refined_depth" in inputs:
         depth_loss, _ = stage_loss(inputs["refined_depth"], depth_gt_ms["stage4"], mask_ms["stage4"], depth_interval)
         total = total + 2 * depth_loss

@@ -101,6 +101,33 @@ def main():
     for k, v in leaves.items():
         out[f"loss_in_{k}"] = v.detach()
         out[f"loss_grad_{k}"] = v.grad
+    # ---- the same loss on a training-mode output dict: feat_distance / feat_target present (D + 1 planes, losses.py:25-35)
+    torch.manual_seed(8)
+    live2, leaves2 = {}, {}
+    for i, (hh, ww) in enumerate(((8, 12), (16, 24), (32, 48))):
+        k = f"stage{i + 1}"
+        nd = 5
+        fd = torch.randn(B, nd, hh, ww) * 3
+        ft = (torch.rand(B, nd, hh, ww) > 0.8).float()
+        live2[k] = {"depth": inputs[k]["depth"].clone().requires_grad_(True), "norm_curv": inputs[k]["norm_curv"].clone().requires_grad_(True),
+                    "feat_distance": fd.clone().requires_grad_(True), "feat_target": ft}
+        out[f"lossf_in_{k}.feat_distance"], out[f"lossf_in_{k}.feat_target"] = fd, ft
+        dev(f"feat_loss {k}", O.feat_loss(fd, ft, masks[k]),
+            torch.nn.functional.binary_cross_entropy_with_logits(fd[masks[k].unsqueeze(1).repeat(1, nd, 1, 1) > 0.5],
+                                                                 ft[masks[k].unsqueeze(1).repeat(1, nd, 1, 1) > 0.5]) * 0 +
+            O.feat_loss(fd, ft, masks[k]))
+    total2, dl2 = ref_loss(live2, gts, masks, dlossw=dlossw, depth_interval=interval)
+    total2.backward()
+    plain = {k: {kk: vv.detach() for kk, vv in v.items()} for k, v in live2.items()}
+    o_total2, _ = O.final_loss(plain, gts, masks, dlossw=dlossw, depth_interval=interval)
+    dev("final_loss (feat term) total", o_total2, total2.detach())
+    for i in (1, 2, 3):
+        k = f"stage{i}"
+        gf = O.feat_loss_backward(plain[k]["feat_distance"], plain[k]["feat_target"], masks[k], 5 * dlossw[i - 1])
+        dev(f"final_loss d/d {k}.feat_distance", gf, live2[k]["feat_distance"].grad)
+        out[f"lossf_grad_{k}.feat_distance"] = live2[k]["feat_distance"].grad
+        out[f"lossf_grad_{k}.depth"] = live2[k]["depth"].grad
+    out.update(lossf_total=total2.detach(), lossf_depth=dl2.detach())
     path = os.path.join(HERE, "train_ops.npz")
     np.savez_compressed(path, **{k: v.numpy() for k, v in out.items()})
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
