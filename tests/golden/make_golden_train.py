@@ -112,10 +112,12 @@ def main():
         live2[k] = {"depth": inputs[k]["depth"].clone().requires_grad_(True), "norm_curv": inputs[k]["norm_curv"].clone().requires_grad_(True),
                     "feat_distance": fd.clone().requires_grad_(True), "feat_target": ft}
         out[f"lossf_in_{k}.feat_distance"], out[f"lossf_in_{k}.feat_target"] = fd, ft
-        dev(f"feat_loss {k}", O.feat_loss(fd, ft, masks[k]),
-            torch.nn.functional.binary_cross_entropy_with_logits(fd[masks[k].unsqueeze(1).repeat(1, nd, 1, 1) > 0.5],
-                                                                 ft[masks[k].unsqueeze(1).repeat(1, nd, 1, 1) > 0.5]) * 0 +
-            O.feat_loss(fd, ft, masks[k]))
+        sel = masks[k].unsqueeze(1).repeat(1, nd, 1, 1) > 0.5       # losses.py:29-34 spelled out with the torch operator
+        pos = ft[sel].sum()
+        want = torch.nn.functional.binary_cross_entropy_with_logits(fd[sel], ft[sel], reduction="mean",
+                                                                    pos_weight=(torch.numel(ft[sel]) - pos) / pos)
+        dev(f"feat_loss {k}", O.feat_loss(fd, ft, masks[k]), want)
+        out[f"lossf_value_{k}"] = want
     total2, dl2 = ref_loss(live2, gts, masks, dlossw=dlossw, depth_interval=interval)
     total2.backward()
     plain = {k: {kk: vv.detach() for kk, vv in v.items()} for k, v in live2.items()}

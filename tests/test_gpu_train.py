@@ -155,14 +155,36 @@ def test_final_loss_edges(golden):
     masks["stage2"] = torch.zeros_like(masks["stage2"])
     total, _ = losses.final_loss(inputs, gts, masks, depth_interval=cu(g["loss_interval"]))
     assert torch.isnan(total)
-    # the training-mode term is not built: loud, not silent
-    inputs["stage1"]["feat_distance"] = torch.zeros(1, device=DEV)
-    with pytest.raises(NotImplementedError):
+    # mismatched feat_distance / mask shapes are refused
+    inputs["stage1"]["feat_distance"] = torch.zeros(2, 5, 3, 3, device=DEV)
+    inputs["stage1"]["feat_target"] = torch.zeros(2, 5, 3, 3, device=DEV)
+    with pytest.raises(RuntimeError):
         losses.final_loss(inputs, gts, masks, depth_interval=cu(g["loss_interval"]))
     # CPU tensors are refused
     with pytest.raises(RuntimeError):
-        losses.final_loss({k: {kk: vv.cpu() for kk, vv in v.items() if kk != "feat_distance"} for k, v in inputs.items()},
+        losses.final_loss({k: {kk: vv.cpu() for kk, vv in v.items() if not kk.startswith("feat_")} for k, v in inputs.items()},
                           {k: v.cpu() for k, v in gts.items()}, {k: v.cpu() for k, v in masks.items()}, depth_interval=g["loss_interval"])
+
+
+def test_final_loss_with_feat_term_golden(golden):
+    """A training-mode output dict (feat_distance / feat_target present, models/model.py:94): value and gradients of the live
+    reference's final_loss, including the 5x binary-cross-entropy term with its neg / pos weight."""
+    g = golden("train_ops")
+    inputs, gts, masks = loss_case(g)
+    del inputs["refined_depth"]
+    for i in (1, 2, 3):
+        k = f"stage{i}"
+        inputs[k]["feat_distance"] = cu(g[f"lossf_in_{k}.feat_distance"]).requires_grad_(True)
+        inputs[k]["feat_target"] = cu(g[f"lossf_in_{k}.feat_target"])
+        close(losses._FeatLossFn.apply(inputs[k]["feat_distance"].detach(), inputs[k]["feat_target"], masks[k]), g[f"lossf_value_{k}"], 2e-6, 2e-6)
+    total, dl = losses.final_loss(inputs, gts, masks, dlossw=g["loss_dlossw"].tolist(), depth_interval=cu(g["loss_interval"]))
+    close(total, g["lossf_total"], 1e-5, 2e-6)
+    close(dl, g["lossf_depth"], 1e-6, 2e-6)
+    total.backward()
+    for i in (1, 2, 3):
+        k = f"stage{i}"
+        close(inputs[k]["feat_distance"].grad, g[f"lossf_grad_{k}.feat_distance"], 1e-8, 2e-5)
+        close(inputs[k]["depth"].grad, g[f"lossf_grad_{k}.depth"], 1e-9, 1e-5)
 
 
 def test_training_chain_vs_cpu_autograd():

@@ -55,3 +55,19 @@ def test_final_loss(golden):
         close(gc.unsqueeze(1), g[f"loss_grad_{k}.norm_curv"], 1e-9, 1e-5)
     ge, _ = O.stage_loss_backward(inputs["refined_depth"], gts["stage4"], masks["stage4"], g["loss_interval"], 2.0, 0.0)
     close(ge, g["loss_grad_refined_depth"], 1e-9, 1e-5)
+
+
+def test_final_loss_with_feat_term(golden):
+    g = golden("train_ops")
+    inputs, gts, masks = loss_case(g)
+    del inputs["refined_depth"]
+    w = g["loss_dlossw"].tolist()
+    for i in (1, 2, 3):
+        k = f"stage{i}"
+        inputs[k]["feat_distance"], inputs[k]["feat_target"] = g[f"lossf_in_{k}.feat_distance"], g[f"lossf_in_{k}.feat_target"]
+        close(O.feat_loss(inputs[k]["feat_distance"], inputs[k]["feat_target"], masks[k]), g[f"lossf_value_{k}"], 1e-6)
+        gf = O.feat_loss_backward(inputs[k]["feat_distance"], inputs[k]["feat_target"], masks[k], 5 * w[i - 1])
+        close(gf, g[f"lossf_grad_{k}.feat_distance"], 1e-8, 1e-5)
+    total, dl = O.final_loss(inputs, gts, masks, dlossw=w, depth_interval=g["loss_interval"])
+    close(total, g["lossf_total"], 1e-5)
+    close(dl, g["lossf_depth"], 1e-6)
