@@ -299,7 +299,6 @@ def main():
     # ---- timed region 2: end to end through the public API with HOST buffers -----------------------------------
     # (a) one call at a time: model(...) on pinned host inputs, results read back, host blocks on every item
     out_host = None
-    from cds_mvsnet_b200.streaming import _flatten
 
     def step_e2e():
         nonlocal out_host
@@ -307,7 +306,9 @@ def main():
         dv = host["dv"].to(dev, non_blocking=True)
         proj = {k: v.to(dev, non_blocking=True) for k, v in host["proj"].items()}
         out = model(imgs, proj, dv, temperature=TEMPERATURE)
-        flat = _flatten(out)   # every per-stage map (+ the full-resolution refined depth of refine=True models), like the streamed leg
+        flat = {f"{k}.{kk}": vv for k, v in out.items() if isinstance(v, dict) for kk, vv in v.items()}
+        if getattr(model, "refine", False):   # refine=True: the full-resolution refined depth is a map of its own (the streamed leg returns it too)
+            flat["refined_depth"] = out["refined_depth"]
         if out_host is None:
             out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in flat.items()}
         for k, v in flat.items():
