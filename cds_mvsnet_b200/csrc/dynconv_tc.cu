@@ -32,6 +32,11 @@
 
 namespace {
 
+// resident CTAs per SM asked of the compiler for the k=(1,3) layers with <= 16 channels (out3, out2): their epilogue is
+// latency-bound (ncu: 57 % issue-active at 28 % warp occupancy), their TMEM footprint (128 columns) allows four
+#ifndef CDS_K13_CTAS
+#define CDS_K13_CTAS 4
+#endif
 constexpr int TX = 128;
 constexpr int ROW_BYTES = TX * 16;
 constexpr float kInEps = 1e-5f;
@@ -153,7 +158,7 @@ __device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uin
 // runs the MMAs of a reference tile ONCE and its epilogue up to GRP times, once per pair: 5 instead of 8 images' worth of
 // tensor work at N = 5.
 template <class C, int TY, bool SPLIT, int GRP = 1>
-__global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 2 : 3) : 2))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+__global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 2 : (C::KMAX == 3 ? CDS_K13_CTAS : 3)) : 2))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
     static_assert(GRP == 1 || (C::COUT == 8 && !SPLIT), "shared-image groups are implemented for the 8-channel image layer");
     constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO, C8 = C::C8, CIN = C::CIN, COUT = C::COUT, NPAD = C::NPAD;
     constexpr int ROWS = TY + 2 * HALO;
