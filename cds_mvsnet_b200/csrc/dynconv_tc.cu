@@ -37,6 +37,9 @@ namespace {
 #ifndef CDS_K13_CTAS
 #define CDS_K13_CTAS 4
 #endif
+#ifndef CDS_K357_CTAS
+#define CDS_K357_CTAS 4   // conv01
+#endif
 constexpr int TX = 128;
 constexpr int ROW_BYTES = TX * 16;
 constexpr float kInEps = 1e-5f;
@@ -158,7 +161,7 @@ __device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uin
 // runs the MMAs of a reference tile ONCE and its epilogue up to GRP times, once per pair: 5 instead of 8 images' worth of
 // tensor work at N = 5.
 template <class C, int TY, bool SPLIT, int GRP = 1>
-__global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 2 : (C::KMAX == 3 ? CDS_K13_CTAS : 3)) : 2))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+__global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 2 : (C::KMAX == 3 ? CDS_K13_CTAS : (C::NK == 3 && C::KMAX == 7 ? CDS_K357_CTAS : 3))) : 2))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
     static_assert(GRP == 1 || (C::COUT == 8 && !SPLIT), "shared-image groups are implemented for the 8-channel image layer");
     constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO, C8 = C::C8, CIN = C::CIN, COUT = C::COUT, NPAD = C::NPAD;
     constexpr int ROWS = TY + 2 * HALO;
