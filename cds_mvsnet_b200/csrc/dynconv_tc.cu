@@ -716,7 +716,7 @@ static int dynamic_conv_tc_impl(const void* x, int n_images, const int* img_inde
     const int lid = layer_id(Cin, Cout, num_kernels, kernel_sizes);
     if (pair_v > 0) {
         CDS_REQUIRE(lid == 1 && !in_stats, CDS_EUNSUPPORTED, "cds_dynamic_conv_tc_pairs: implemented for the image layer (3,7,11)");
-        return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8, false, 4>(x, n_images, p, n, stream);
+        return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 16, false, 4>(x, n_images, p, n, stream);
     }
     if (split_in) {
         CDS_REQUIRE(lid == 4 && in_stats, CDS_EUNSUPPORTED,
