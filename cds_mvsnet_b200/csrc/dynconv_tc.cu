@@ -38,7 +38,7 @@ namespace {
 #define CDS_K13_CTAS 4
 #endif
 #ifndef CDS_K357_CTAS
-#define CDS_K357_CTAS 4   // conv01
+#define CDS_K357_CTAS 3   // conv01
 #endif
 constexpr int TX = 128;
 constexpr int ROW_BYTES = TX * 16;
@@ -725,7 +725,7 @@ static int dynamic_conv_tc_impl(const void* x, int n_images, const int* img_inde
     }
     switch (lid) {
         case 1: return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8>(x, n_images, p, n, stream);
-        case 2: return launch_dyn_tc<Cfg<3, 5, 7, 8, 8>, 8>(x, n_images, p, n, stream);
+        case 2: return launch_dyn_tc<Cfg<3, 5, 7, 8, 8>, 16>(x, n_images, p, n, stream);
         case 3: return launch_dyn_tc<Cfg<1, 3, 0, 8, 8>, 16>(x, n_images, p, n, stream);
         case 4: return launch_dyn_tc<Cfg<3, 5, 0, 16, 16>, 8>(x, n_images, p, n, stream);
         case 5: return launch_dyn_tc<Cfg<1, 3, 0, 16, 16>, 8>(x, n_images, p, n, stream);
