@@ -4,6 +4,10 @@ Every (scene, reference view) depth map is an independent unit (reference: test.
 batch; datasets/general_eval.py:55 builds one work item per reference view), so the path shards by work list and
 the only collectives are at the edges: a MAX-reduce of the timed interval and, when a consumer needs neighbouring
 views' maps (the geometric filter, test.py:326-352), an all_gather of the per-rank results.
+
+Training has exactly one exchange step: the gradients of the replicated 3.9 MB of weights are
+averaged over the ranks once per step.  ``all_reduce_gradients`` does that as ONE flat all-reduce (NCCL on GPUs: a single
+launch-latency-bound collective over NVLink, not one per parameter tensor).
 """
 from __future__ import annotations
 
@@ -44,3 +48,33 @@ def gather_maps(local: torch.Tensor, n_items: int) -> torch.Tensor:
         idx = shard_worklist(n_items, r, world)
         out[idx] = bucket[r][: len(idx)]
     return out
+
+
+def all_reduce_gradients(params, average: bool = True) -> int:
+    """Average (or sum) the ``.grad`` of ``params`` over all ranks through one flat buffer; returns the element count.
+
+    Parameters without a gradient on this rank contribute zeros (every rank must pass the same parameter list, as a
+    data-parallel replica set does).  A no-op outside a process group."""
+    params = [p for p in params if p.requires_grad]
+    n = sum(p.numel() for p in params)
+    if n == 0 or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return n
+    ref = next((p.grad for p in params if p.grad is not None), params[0])
+    flat = torch.zeros(n, dtype=torch.float32, device=ref.device)
+    off = 0
+    for p in params:
+        if p.grad is not None:
+            flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        off += p.numel()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat /= dist.get_world_size()
+    off = 0
+    for p in params:
+        g = flat[off:off + p.numel()].reshape(p.shape).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += p.numel()
+    return n
