@@ -34,6 +34,31 @@ def test_argument_checks_do_not_need_a_gpu():
     assert dll.cds_homo_warp(None, None, None, 0, 1, 8, 4, 8, 8, None, None) == -1
     assert b"null pointer" in dll.cds_last_error_string()
     assert dll.cds_conv3d_k3(None, None, None, 1, 8, 8, 8, 8, 8, 1, 1, 1, None, None) == -1
+    # training-slice entries: null pointers, bad shapes, the C % 4 rule of the workspace form
+    assert dll.cds_homo_warp_backward(None, None, None, 0, 1, 8, 4, 8, 8, None, None, None) == -1
+    assert dll.cds_homo_warp_backward(1, 1, 1, 0, 1, 8, 4, 1, 8, 1, None, None) == -2
+    assert dll.cds_homo_warp_backward(1, 1, 1, 0, 1, 5, 4, 8, 8, 1, 1, None) == -3
+    assert b"C % 4" in dll.cds_last_error_string()
+    assert dll.cds_depth_regress_backward(1, None, None, 0, 1, 4, 8, 8, None, None, None) == -1
+    assert dll.cds_stage_loss_forward(None, None, None, None, None, 1, 8, 8, None, None) == -1
+    assert dll.cds_stage_loss_backward(1, 1, 1, 1, 1, None, None, 1, 8, 8, 1, None, None) == -1
+    assert dll.cds_feat_loss_forward(1, 1, 1, 0, 4, 8, 8, 1, None) == -2
+
+
+def test_training_ops_refuse_cpu_tensors():
+    import torch
+
+    import cds_mvsnet_b200 as C
+    from cds_mvsnet_b200 import losses
+    x = torch.zeros(1, 8, 4, 4, requires_grad=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        C.homo_warping_3D(x, torch.eye(4)[None], torch.eye(4)[None], torch.ones(1, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        C.depth_regression(torch.zeros(1, 2, 4, 4, requires_grad=True), torch.ones(1, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.final_loss({f"stage{i}": {"depth": torch.zeros(1, 4, 4), "norm_curv": torch.zeros(1, 1, 4, 4)} for i in (1, 2, 3)},
+                          {f"stage{i}": torch.zeros(1, 4, 4) for i in (1, 2, 3)}, {f"stage{i}": torch.ones(1, 4, 4) for i in (1, 2, 3)},
+                          depth_interval=torch.ones(1))
 
 
 def test_product_path_has_no_cpu_fallback():
