@@ -58,17 +58,32 @@ __global__ void __launch_bounds__(256) homo_warp_backward_kernel(const float* __
 // Channels-last form for C % 4 == 0: the reductions go to a zeroed [B,h,w,C] fp32 workspace as 16-byte vector
 // reductions (red.global.add.v4.f32, sm_90+) -- a quarter of the reduction instructions and one L2 sector per tap and
 // channel quad instead of four -- and nhwc_to_nchw_kernel then lays the result out as the reference's [B,C,h,w].
+// Neighbouring lanes (consecutive x) usually land on overlapping footprints: lane i's right-hand column is lane i+1's
+// left-hand column whenever the views' scales are close.  Such a lane hands its right-hand column to its neighbour by
+// shuffle and the neighbour reduces the sum, which halves the reductions that reach L2 (the bound of this kernel).
+__device__ __forceinline__ float4 scale4(float w, float4 g) { return make_float4(w * g.x, w * g.y, w * g.z, w * g.w); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 shfl_up4(float4 v) {
+    return make_float4(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1), __shfl_up_sync(0xffffffffu, v.z, 1),
+                       __shfl_up_sync(0xffffffffu, v.w, 1));
+}
+
 __global__ void __launch_bounds__(256) homo_warp_backward_nhwc_kernel(const float* __restrict__ grad_out, const float* __restrict__ coef,
                                                                       const float* __restrict__ depth, int per_pixel, int B, int C,
                                                                       int D, int h, int w, float* __restrict__ ws) {
     const long long P = (long long)h * w;
     const long long total = (long long)B * D * P;
     const float half_w = (float)((double)(w - 1) / 2.0), half_h = (float)((double)(h - 1) / 2.0);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % w);
-        const int y = (int)((i / w) % h);
-        const int d = (int)((i / P) % D);
-        const int b = (int)(i / (P * D));
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: every lane takes part in the shuffles of every iteration
+    for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < total;
+        const long long ii = live ? i : total - 1;
+        const int x = (int)(ii % w);
+        const int y = (int)((ii / w) % h);
+        const int d = (int)((ii / P) % D);
+        const int b = (int)(ii / (P * D));
         const WarpCoef k = load_coef(coef + b * 12);
         const float dep = per_pixel ? __ldg(depth + ((size_t)b * D + d) * P + (size_t)y * w + x) : __ldg(depth + b * D + d);
         float rx, ry, rz, u, v;
@@ -76,15 +91,24 @@ __global__ void __launch_bounds__(256) homo_warp_backward_nhwc_kernel(const floa
         project(k, rx, ry, rz, dep, u, v);
         u = ((u / half_w - 1.f) + 1.f) / 2.f * (float)(w - 1);
         v = ((v / half_h - 1.f) + 1.f) / 2.f * (float)(h - 1);
-        const Taps t = make_taps(u, v, w, h);
-        if (t.w00 == 0.f && t.w01 == 0.f && t.w10 == 0.f && t.w11 == 0.f) continue;
+        Taps t = make_taps(u, v, w, h);
+        if (!live) t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
         const int xa = min(max(t.x0, 0), w - 1), xb = min(max(t.x0 + 1, 0), w - 1);
         const int ya = min(max(t.y0, 0), h - 1), yb = min(max(t.y0 + 1, 0), h - 1);
-        float* wb = ws + (size_t)b * P * C;
-        float4* q00 = reinterpret_cast<float4*>(wb + ((size_t)ya * w + xa) * C);
-        float4* q01 = reinterpret_cast<float4*>(wb + ((size_t)ya * w + xb) * C);
-        float4* q10 = reinterpret_cast<float4*>(wb + ((size_t)yb * w + xa) * C);
-        float4* q11 = reinterpret_cast<float4*>(wb + ((size_t)yb * w + xb) * C);
+        // pixel indices of the four taps inside the whole workspace (batch included, so equal index == equal address)
+        const long long pb = (long long)b * P;
+        const long long o00 = pb + (long long)ya * w + xa, o01 = pb + (long long)ya * w + xb;
+        const long long o10 = pb + (long long)yb * w + xa, o11 = pb + (long long)yb * w + xb;
+        // does my left-hand column coincide with the previous lane's right-hand column?
+        const long long p01 = __shfl_up_sync(0xffffffffu, o01, 1), p11 = __shfl_up_sync(0xffffffffu, o11, 1);
+        const bool take_left = lane > 0 && p01 == o00 && p11 == o10;
+        const bool give_right = __shfl_down_sync(0xffffffffu, (int)take_left, 1) != 0 && lane < 31;
+        const bool any = __any_sync(0xffffffffu, t.w00 != 0.f || t.w01 != 0.f || t.w10 != 0.f || t.w11 != 0.f);
+        if (!any) continue;   // warp-uniform
+        float4* q00 = reinterpret_cast<float4*>(ws + (size_t)o00 * C);
+        float4* q01 = reinterpret_cast<float4*>(ws + (size_t)o01 * C);
+        float4* q10 = reinterpret_cast<float4*>(ws + (size_t)o10 * C);
+        float4* q11 = reinterpret_cast<float4*>(ws + (size_t)o11 * C);
         const float* gb = grad_out + ((size_t)b * C * D + d) * P + (size_t)y * w + x;
         const size_t cs = (size_t)D * P;
         float4 g = make_float4(__ldg(gb), __ldg(gb + cs), __ldg(gb + 2 * cs), __ldg(gb + 3 * cs));
@@ -94,10 +118,21 @@ __global__ void __launch_bounds__(256) homo_warp_backward_nhwc_kernel(const floa
                 const float* gq = gb + (size_t)(c4 + 1) * 4 * cs;
                 gn = make_float4(__ldg(gq), __ldg(gq + cs), __ldg(gq + 2 * cs), __ldg(gq + 3 * cs));
             }
-            if (t.w00 != 0.f) atomicAdd(q00 + c4, make_float4(t.w00 * g.x, t.w00 * g.y, t.w00 * g.z, t.w00 * g.w));
-            if (t.w01 != 0.f) atomicAdd(q01 + c4, make_float4(t.w01 * g.x, t.w01 * g.y, t.w01 * g.z, t.w01 * g.w));
-            if (t.w10 != 0.f) atomicAdd(q10 + c4, make_float4(t.w10 * g.x, t.w10 * g.y, t.w10 * g.z, t.w10 * g.w));
-            if (t.w11 != 0.f) atomicAdd(q11 + c4, make_float4(t.w11 * g.x, t.w11 * g.y, t.w11 * g.z, t.w11 * g.w));
+            float4 v00 = scale4(t.w00, g), v10 = scale4(t.w10, g);
+            const float4 v01 = scale4(t.w01, g), v11 = scale4(t.w11, g);
+            const float4 r01 = shfl_up4(v01), r11 = shfl_up4(v11);   // the previous lane's right-hand column
+            bool left0 = t.w00 != 0.f, left1 = t.w10 != 0.f;
+            if (take_left) {
+                v00 = add4(v00, r01);
+                v10 = add4(v10, r11);
+                left0 = left1 = true;   // the neighbour's share may be non-zero where mine is zero (adding 0 is harmless)
+            }
+            if (left0) atomicAdd(q00 + c4, v00);
+            if (left1) atomicAdd(q10 + c4, v10);
+            if (!give_right) {
+                if (t.w01 != 0.f) atomicAdd(q01 + c4, v01);
+                if (t.w11 != 0.f) atomicAdd(q11 + c4, v11);
+            }
             g = gn;
         }
     }
