@@ -15,6 +15,7 @@
  *   cds_c_softmax_regress   models/model.py:90-92 ; models/module.py:373-391
  */
 #include <math.h>
+#include <stdlib.h>
 #include <stddef.h>
 
 /* y[n,co,ho,wo] = b[co] + sum_{ci,ky,kx} x[n,ci,ho*s-p+ky,wo*s-p+kx] * w[co,ci,ky,kx] */
@@ -102,6 +103,42 @@ void cds_c_bilinear_zeros(const float* fea, int C, int h, int w, const float* u,
             out[(size_t)c * M + m] = acc;
         }
     }
+}
+
+/* Adjoint of cds_c_bilinear_zeros in fea: grad[c,m] at (u[m], v[m]) is added, with the same weights, to the in-image taps of
+ * grad_fea[c,:,:] (zeroed here).  What autograd derives for grid_sample(bilinear, zeros, align_corners=True) when only the
+ * input carries a gradient (models/utils/warping.py:79,100-101).  fp64 accumulation. */
+void cds_c_bilinear_zeros_backward(const float* grad, int C, int h, int w, const float* u, const float* v, int M, float* grad_fea) {
+    double* acc = (double*)calloc((size_t)C * h * w, sizeof(double));
+    for (int m = 0; m < M; ++m) {
+        float x0f = floorf(u[m]), y0f = floorf(v[m]);
+        float fx = u[m] - x0f, fy = v[m] - y0f;
+        int x0 = (int)x0f, y0 = (int)y0f;
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                int xi = x0 + dx, yi = y0 + dy;
+                if (xi < 0 || xi >= w || yi < 0 || yi >= h) continue;
+                float wgt = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy);
+                for (int c = 0; c < C; ++c) acc[((size_t)c * h + yi) * w + xi] += (double)(wgt * grad[(size_t)c * M + m]);
+            }
+    }
+    for (size_t i = 0; i < (size_t)C * h * w; ++i) grad_fea[i] = (float)acc[i];
+    free(acc);
+}
+
+/* One stage of final_loss (models/losses.py:14-23,25-35) on flat arrays of n pixels (interval already per pixel):
+ * out[0] = smooth-L1 mean of est/iv - gt/iv over mask > 0.5, out[1] = masked mean of curv. */
+void cds_c_stage_loss(const float* est, const float* gt, const float* mask, const float* iv, const float* curv, long n, float* out) {
+    double l = 0.0, c = 0.0, cnt = 0.0;
+    for (long i = 0; i < n; ++i) {
+        if (!(mask[i] > 0.5f)) continue;
+        float d = est[i] / iv[i] - gt[i] / iv[i], a = fabsf(d);
+        l += a < 1.f ? 0.5f * d * d : a - 0.5f;
+        c += curv[i];
+        cnt += 1.0;
+    }
+    out[0] = (float)(l / cnt);
+    out[1] = (float)(c / cnt);
 }
 
 /* logits [D,P] (one batch item), depth [D,P]: softmax over D, expectation depth, 4-plane confidence window */

@@ -91,3 +91,37 @@ def test_softmax_regress(clib):
     clib.cds_c_softmax_regress(fp(la), fp(da), D, P, fp(d_out), fp(c_out))
     np.testing.assert_allclose(d_out, ref_d.numpy(), rtol=1e-5)
     assert (np.abs(c_out - ref_c.numpy()) > 1e-5).mean() < 0.05   # window index is a truncation
+
+
+def test_bilinear_backward_and_stage_loss(clib):
+    """Training slice: the plain-C scatter (adjoint of the gather) and stage loss against the torch-CPU restatements."""
+    torch.manual_seed(6)
+    C_, h, w, M = 3, 7, 9, 60
+    u = torch.rand(1, M) * (w + 3) - 2            # some samples fall outside the image
+    v = torch.rand(1, M) * (h + 3) - 2
+    g = torch.randn(1, C_, M)
+    want = O.bilinear_scatter_zeros(g, u, v, h, w)[0]
+    # the python restatement goes through the reference's normalise / un-normalise round trip; feed C the same coordinates
+    un, vn = u / ((w - 1) / 2) - 1, v / ((h - 1) / 2) - 1
+    u2, v2 = (un + 1) / 2 * (w - 1), (vn + 1) / 2 * (h - 1)
+    out = np.zeros((C_, h, w), np.float32)
+    ga, ua, va = arr(g[0]), arr(u2[0]), arr(v2[0])
+    clib.cds_c_bilinear_zeros_backward(fp(ga), C_, h, w, fp(ua), fp(va), M, fp(out))
+    np.testing.assert_allclose(out, want.numpy(), atol=2e-6)
+    # adjoint identity against the C gather
+    fea = torch.randn(C_, h, w)
+    fwd = np.zeros((C_, M), np.float32)
+    fa = arr(fea)
+    clib.cds_c_bilinear_zeros(fp(fa), C_, h, w, fp(ua), fp(va), M, fp(fwd))
+    assert abs((fwd.astype(np.float64) * ga).sum() - (fa.astype(np.float64) * out).sum()) < 1e-4
+
+    n = 500
+    gt = 425 + 500 * torch.rand(n)
+    est = gt + 4 * torch.randn(n)
+    mask, iv, curv = (torch.rand(n) > 0.3).float(), torch.full((n,), 2.65), torch.rand(n)
+    res = np.zeros(2, np.float32)
+    clib.cds_c_stage_loss.argtypes = [FP, FP, FP, FP, FP, ctypes.c_long, FP]
+    ea, gta, ma, iva, ca = arr(est), arr(gt), arr(mask), arr(iv), arr(curv)
+    clib.cds_c_stage_loss(fp(ea), fp(gta), fp(ma), fp(iva), fp(ca), n, fp(res))
+    dl, cm = O.stage_loss(est.reshape(1, 1, n), gt.reshape(1, 1, n), mask.reshape(1, 1, n), torch.tensor([2.65]), curv.reshape(1, 1, n))
+    np.testing.assert_allclose(res, [dl.item(), cm.item()], rtol=2e-6)
