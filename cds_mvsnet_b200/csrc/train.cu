@@ -6,6 +6,8 @@
 //   models/module.py:373-379            depth = sum_d p_d * depth_d  ->  d/dp = g * depth_d, d/d depth = g * p_d
 //   models/losses.py:14-23,36-37        per stage: smooth-L1 (beta 1, mean over mask > 0.5) of depth / interval, and
 //                                       the masked mean of norm_curv
+//   models/losses.py:25-35              binary cross entropy with logits of feat_distance against feat_target over the
+//                                       mask repeated across the planes, positives weighted by neg / pos
 #include "cds_common.cuh"
 
 namespace {
