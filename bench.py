@@ -392,6 +392,11 @@ def main():
     roof.update({"traffic": traffic, "kernel": f"{top['kernel']}[{top['tag']}]", "share_of_step": top["share"],
                  "ms_per_launch": top["ms_per_launch"], "peak_source": pk["src"],
                  "algorithmic": {"gflop_per_launch": top["alg_gflop"], "mb_per_launch": top["alg_mb"]}})
+    if top["kernel"].startswith("cds_dynamic_conv_tc"):
+        # what saturates first in the tap-GEMM formulation is the tensor core's shared-memory operand path, not the math pipe
+        roof["note"] = ("tap-GEMM DynamicConv: every K=16 MMA re-reads its 4 KB A slab pair and its B columns from shared memory; the "
+                        "committed ncu capture (profiles/r01_v12_ncu_conv00_pairs.txt) shows l1tex throughput 84.6 % with the tensor "
+                        "pipe 31 % active -- the kernel sits at ~5/6 of the shared-memory operand roofline (DESIGN.md section 5)")
     if args.kernel_table:
         os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
         json.dump({"workload": workload_name(args.workload, cfg), "storage": args.storage, "ms_per_step": ms_total / args.steps,
