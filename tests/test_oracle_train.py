@@ -1,5 +1,6 @@
 """Training slice: the oracle's backward / loss restatements against the gradients of the LIVE reference
 (tests/golden/make_golden_train.py -> train_ops.npz).  CPU only."""
+import pytest
 import torch
 
 from oracle import oracle as O
@@ -71,3 +72,22 @@ def test_final_loss_with_feat_term(golden):
     total, dl = O.final_loss(inputs, gts, masks, dlossw=w, depth_interval=g["loss_interval"])
     close(total, g["lossf_total"], 1e-5)
     close(dl, g["lossf_depth"], 1e-6)
+
+
+@pytest.mark.parametrize("seed,h,w,C_,M", [(0, 2, 2, 1, 40), (1, 5, 9, 3, 200), (2, 16, 7, 4, 500), (3, 3, 31, 2, 1)])
+def test_scatter_is_the_adjoint_of_the_gather(seed, h, w, C_, M):
+    """<gather(x), g> = <x, scatter(g)> on ragged shapes with samples on and beyond every border (zero padding drops them on
+    both sides alike), including the degenerate single-sample case."""
+    torch.manual_seed(seed)
+    u = torch.rand(2, M) * (w + 4) - 2.5
+    v = torch.rand(2, M) * (h + 4) - 2.5
+    u[:, 0], v[:, 0] = w - 1.0, h - 1.0            # exactly on the last pixel: only the (0,0) tap is inside
+    x, g = torch.randn(2, C_, h, w), torch.randn(2, C_, M)
+    lhs = (O.bilinear_gather_zeros(x, u, v).double() * g.double()).sum()
+    rhs = (x.double() * O.bilinear_scatter_zeros(g, u, v, h, w).double()).sum()
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
+def test_scatter_of_nothing_is_zero():
+    z = O.bilinear_scatter_zeros(torch.randn(1, 2, 3), torch.full((1, 3), -50.0), torch.full((1, 3), 1e6), 4, 5)
+    assert z.shape == (1, 2, 4, 5) and z.abs().max() == 0
