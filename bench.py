@@ -11,9 +11,15 @@ inputs, host->device and device->host copies inside the timed region.  One JSON 
 Multi-GPU: one process per GPU (torchrun), every rank runs its own replica on its own work items (depth
 maps are independent units -- SURVEY.md 8e); there is no data-path collective, ``scaling`` is "weak".
 
-``--impl reference`` times the reference's own algorithm on the host CPU cores: the reference is pure
-Python/PyTorch that cannot travel to the GPU box, so the arm runs the oracle port (oracle/oracle.py,
-pinned against the live reference by tests/golden) with all host threads on a bounded sample.
+``--impl reference`` times the reference's OWN code on the host CPU cores: the unmodified ``models.model.CDSMVSNet``
+(shipped to oracle/_ref by ``__graft_entry__.build()``, see oracle/ref_live.py) run through its public forward at the SAME
+configuration, EXACTLY K timed steps after W warm-up steps, all host threads.  If the archive is missing the oracle port
+(oracle/oracle.py, pinned against the live reference by tests/golden) is timed instead and ``kind`` says "port".
+
+The default arm also reports, in the same line: ``parity`` (our depth maps against that CPU run's output on the worst-case
+"noise" input at the full configuration), ``roofline.groups`` (HBM GB/s of the plane-sweep and regulariser kernels, TFLOP/s of
+the feature extractor) and ``reference_eager_gpu`` -- the incumbent: the same unmodified reference run eagerly on this B200
+(cuDNN/ATen, ``cudnn.benchmark=True`` as test.py:18, with TF32 off and on).
 """
 from __future__ import annotations
 
@@ -34,6 +40,7 @@ import torch  # noqa: E402
 METRIC = "depth_maps_per_sec"
 UNIT = "maps/s"
 TEMPERATURE = 0.01   # reference test.py:52
+REFERENCE_ARM_LIMIT_S = 1500.0   # wall limit of `--impl reference` (a CPU forward at cfg2 takes ~20 s on the box's 16 cores)
 
 
 def load_weights():
@@ -94,75 +101,160 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(cfg, n_threads, budget_s=25.0, steps=1, warmup=0):
-    """Depth maps / s of the oracle port on the host, measured on a bounded sample of the workload.
+def quantize_u8(imgs):
+    """8-bit images (what the reference's loader reads, datasets/general_eval.py:88-91) and their float form img / 255."""
+    u8 = (imgs * 255.0).round().clamp(0, 255).to(torch.uint8)
+    return u8, torch.from_numpy(u8.numpy().astype(np.float32) / np.float32(255.0))
 
-    The sample keeps N and the depth-plane counts and shrinks the image (cost is linear in pixels); the
-    rate is scaled back by the pixel ratio and reported for the FULL workload."""
-    from cds_mvsnet_b200 import synthetic
-    from oracle import oracle as O
-    O.FAST_GATHER = True   # gather through ATen grid_sample, as the reference itself does
-    torch.set_num_threads(n_threads)
+
+def load_state(cfg):
     sd = load_weights()
-    refine = bool(cfg.get("refine", False))
-    if refine:
+    if cfg.get("refine", False):
         zr = np.load(os.path.join(ROOT, "tests", "golden", "weights_refine_both_dtu_blended.npz"))
         sd.update({k: torch.from_numpy(zr[k]) for k in zr.files})
-    q = 64 if refine else 32
-    full_px = cfg["H"] * cfg["W"]
-    ladder = [(cfg["H"], cfg["W"])]
-    for f in (2, 4, 8):
-        h, w = max(q, (cfg["H"] // f) // q * q), max(q, (cfg["W"] // f) // q * q)
-        if (h, w) != ladder[-1]:
-            ladder.append((h, w))
+    return sd
 
-    def run(h, w):
-        c = dict(cfg, H=h, W=w, B=1)
-        s = synthetic.make_sample(c, "noise", seed=0)
-        t0 = time.perf_counter()
+
+class CpuReference:
+    """The reference's CPU forward at the FULL configuration: the live reference (kind "reference") when oracle/_ref holds it,
+    else the oracle port (kind "port").  Only bench.py's cpu_baseline / reference legs use it."""
+
+    def __init__(self, cfg, n_threads):
+        from oracle import ref_live
+        self.cfg = cfg
+        self.refine = bool(cfg.get("refine", False))
+        torch.set_num_threads(n_threads)
+        self.sd = load_state(cfg)
+        self.live = ref_live.available()
+        if self.live:
+            self.model = ref_live.build_model(self.sd, cfg["ndepths"], cfg["ratios"], refine=self.refine, device="cpu")
+            self.kind = "reference"
+            self.what = "unmodified reference models.model.CDSMVSNet.forward (oracle/_ref) on the host CPU"
+        else:
+            from oracle import oracle as O
+            O.FAST_GATHER = True   # gather through ATen grid_sample, as the reference itself does
+            self.O = O
+            self.kind = "port"
+            self.what = "oracle port (oracle/oracle.py; oracle/_ref not shipped) on the host CPU"
+
+    def __call__(self, s):
         with torch.no_grad():
-            O.cdsmvsnet_forward(sd, s.imgs, s.proj_matrices, s.depth_values, c["ndepths"], c["ratios"], TEMPERATURE, refine=refine)
-        return time.perf_counter() - t0
+            if self.live:
+                return self.model(s.imgs, s.proj_matrices, s.depth_values, temperature=TEMPERATURE)
+            return self.O.cdsmvsnet_forward(self.sd, s.imgs, s.proj_matrices, s.depth_values, self.cfg["ndepths"], self.cfg["ratios"],
+                                            TEMPERATURE, refine=self.refine)
 
-    # calibrate on the smallest rung, then take the largest rung whose predicted total fits the budget
-    h0, w0 = ladder[-1]
-    t_small = run(h0, w0)
-    per_px = t_small / (h0 * w0)
-    n_runs = steps + warmup
-    pick = ladder[-1]
-    for h, w in ladder:
-        if per_px * h * w * n_runs <= budget_s:
-            pick = (h, w)
-            break
-    times = []
-    for i in range(n_runs):
-        t = run(*pick)
-        if i >= warmup:
-            times.append(t)
-    t_step = float(np.mean(times))
-    rate = (1.0 / t_step) * (pick[0] * pick[1] / full_px)
-    sample = (f"oracle port, full cascade N={cfg['N']} D={list(cfg['ndepths'])} on a {pick[1]}x{pick[0]} image "
-              f"({pick[0] * pick[1] / full_px:.3f} of the {cfg['W']}x{cfg['H']} workload's pixels), {len(times)} run(s) of "
-              f"{t_step:.1f} s, rate scaled by the pixel ratio")
-    return rate, t_step, sample
+
+def bench_sample(cfg, family, seed):
+    """Synthetic work item with 8-bit images: (Sample with float images = u8 / 255, the uint8 tensor)."""
+    from cds_mvsnet_b200 import synthetic
+    s = synthetic.make_sample(cfg, family, seed=seed)
+    u8, f32 = quantize_u8(s.imgs)
+    s.imgs = f32
+    return s, u8
 
 
 def run_reference_arm(args, cfg, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rate, t_step, sample = cpu_oracle_rate(cfg, cores, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    ref = CpuReference(cfg, cores)
+    s, _ = bench_sample(cfg, "plane", 0)
+    times, t_start, cut = [], time.perf_counter(), None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ref(s)
+        dt = time.perf_counter() - t0
+        print(f"[reference arm] step {i + 1}/{args.warmup + args.steps}: {dt:.2f} s", file=sys.stderr, flush=True)
+        if i >= args.warmup:
+            times.append(dt)
+        # fail-safe only: the arm times EXACTLY K steps unless that would run past the driver's own limit
+        if time.perf_counter() - t_start + dt > REFERENCE_ARM_LIMIT_S and len(times) >= 3:
+            cut = f"stopped after {len(times)} of {args.steps} timed steps: the {REFERENCE_ARM_LIMIT_S:.0f} s wall limit of this arm"
+            break
+    t_total = float(np.sum(times))
+    rate = len(times) * cfg["B"] / t_total
+    sample = (f"{ref.what}, the full workload ({cfg['W']}x{cfg['H']} N={cfg['N']} D={list(cfg['ndepths'])} B={cfg['B']}), "
+              f"{len(times)} timed steps of {t_total / len(times):.2f} s after {args.warmup} warm-up steps, {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cfg), "note": "reference algorithm on host CPU cores (oracle port; "
-                   "the pure-Python reference tree does not exist on the GPU box)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, cfg), "same_config": True, "note": ref.what,
+                   "steps_timed": len(times), "cut": cut},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def parity_and_cpu_baseline(cfg, model, dev):
+    """One CPU forward of the reference at the full configuration on the worst-case "noise" input: its duration is the
+    cpu_baseline, its output is what our maps of the SAME input are compared with."""
+    cores = os.cpu_count() or 1
+    ref = CpuReference(cfg, cores)
+    s, u8 = bench_sample(cfg, "noise", 0)
+    t0 = time.perf_counter()
+    r = ref(s)
+    dt = time.perf_counter() - t0
+    out = model(u8.to(dev), {k: v.to(dev) for k, v in s.proj_matrices.items()}, s.depth_values.to(dev), temperature=TEMPERATURE)
+    stages = {}
+    for st in range(1, len(cfg["ndepths"]) + 1):
+        d, rd = out[f"stage{st}"]["depth"].float().cpu(), r[f"stage{st}"]["depth"].float()
+        c, rc = out[f"stage{st}"]["photometric_confidence"].float().cpu(), r[f"stage{st}"]["photometric_confidence"].float()
+        stages[f"stage{st}"] = {"depth_rel_l1": float((d - rd).abs().mean() / rd.abs().mean()), "conf_abs": float((c - rc).abs().mean())}
+    last = stages[f"stage{len(cfg['ndepths'])}"]
+    parity = {"depth_rel_l1": last["depth_rel_l1"], "conf_abs": last["conf_abs"], "stages": stages, "tolerance": 1e-3,
+              "input": f"noise family, seed 0, 8-bit images, full {cfg['W']}x{cfg['H']} N={cfg['N']} workload",
+              "against": ref.what, "pass": bool(all(v["depth_rel_l1"] < 1e-3 for v in stages.values()))}
+    if cfg.get("refine", False):
+        rr = r["refined_depth"].float()
+        parity["refined_depth_rel_l1"] = float((out["refined_depth"].float().cpu() - rr).abs().mean() / rr.abs().mean())
+    cpu = {"value": cfg["B"] / dt, "unit": UNIT, "cores": cores, "kind": ref.kind,
+           "sample": f"{ref.what}, the full workload, 1 forward of {dt:.1f} s on {cores} threads (its output is the parity target)"}
+    return parity, cpu
+
+
+def reference_eager_gpu(cfg, dev, steps=5, warmup=2):
+    """The incumbent: the unmodified reference run eagerly on this GPU (ATen / cuDNN), as test.py runs it
+    (cudnn.benchmark = True, test.py:18), fp32 with TF32 off and with torch's GPU default (TF32 convolutions)."""
+    from oracle import ref_live
+    if not ref_live.available():
+        return {"unavailable": "oracle/_ref/reference_models.zip not shipped"}
+    sd = load_state(cfg)
+    s, _ = bench_sample(cfg, "plane", 0)
+    imgs, dv = s.imgs.to(dev), s.depth_values.to(dev)
+    proj = {k: v.to(dev) for k, v in s.proj_matrices.items()}
+    keep = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    res = {"api": "models.model.CDSMVSNet.forward (oracle/_ref, unmodified), eager, cudnn.benchmark=True, device-resident inputs",
+           "steps": steps, "warmup": warmup}
+    try:
+        model = ref_live.build_model(sd, cfg["ndepths"], cfg["ratios"], refine=bool(cfg.get("refine", False)), device=dev)
+        torch.backends.cudnn.benchmark = True
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(warmup):
+                    model(imgs, proj, dv, temperature=TEMPERATURE)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    model(imgs, proj, dv, temperature=TEMPERATURE)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"value": cfg["B"] / (ms / 1e3), "unit": UNIT, "ms_per_step": ms}
+        res["peak_mem_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+        del model
+    except Exception as exc:   # noqa: BLE001 -- an incumbent that cannot run (e.g. out of memory) is reported, not fatal
+        res["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = keep
+        torch.cuda.empty_cache()
+    return res
 
 
 def workload_name(key, cfg):
@@ -201,7 +293,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--storage", default="float16", choices=["float16", "float32"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference forward (no parity / cpu_baseline fields)")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the reference_eager_gpu leg")
     ap.add_argument("--no-graph", action="store_true", help="issue the forward launch by launch instead of replaying a CUDA graph")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (JSON) here")
     args = ap.parse_args()
@@ -232,18 +325,16 @@ def main():
     storage = getattr(torch, args.storage)
     refine = bool(cfg.get("refine", False))
     model = C.CDSMVSNet(refine=refine, ndepths=cfg["ndepths"], depth_interals_ratio=cfg["ratios"], storage=storage)
-    sd = load_weights()
-    if refine:
-        zr = np.load(os.path.join(ROOT, "tests", "golden", "weights_refine_both_dtu_blended.npz"))
-        sd.update({k: torch.from_numpy(zr[k]) for k in zr.files})
+    sd = load_state(cfg)
     model.load_state_dict({k: v for k, v in sd.items() if k in model.state_dict()})   # fewer stages (cfg1): fewer entries
     model = model.to(dev).eval()
 
-    # every rank works on its own depth map (different seed => different work item)
-    s = synthetic.make_sample(cfg, "plane", seed=rank)
-    host = {"imgs": s.imgs.pin_memory(), "dv": s.depth_values.pin_memory(),
+    # every rank works on its own depth map (different seed => different work item); the images are 8-bit, as the reference's
+    # loader reads them: the host holds the bytes (pinned), the device-resident leg holds their float form u8 / 255
+    s, u8 = bench_sample(cfg, "plane", rank)
+    host = {"imgs": u8.pin_memory(), "dv": s.depth_values.pin_memory(),
             "proj": {k: v.pin_memory() for k, v in s.proj_matrices.items()}}
-    d_imgs, d_dv = host["imgs"].to(dev), host["dv"].to(dev)
+    d_imgs, d_dv = s.imgs.to(dev), s.depth_values.to(dev)
     d_proj = {k: v.to(dev) for k, v in host["proj"].items()}
     B = cfg["B"]
     engine = model.engine(dev)
@@ -297,11 +388,11 @@ def main():
     engine.overlap = overlap_was
 
     # ---- timed region 2: end to end through the public API with HOST buffers -----------------------------------
-    # (a) one call at a time: model(...) on pinned host inputs, results read back, host blocks on every item
-    out_host = None
+    # (a) the reference's call surface, one call at a time: model(...) on inputs uploaded from pinned host memory, result maps
+    #     read back to pinned host memory, the host blocks on every item (test.py:197-208)
+    out_host = {}
 
     def step_e2e():
-        nonlocal out_host
         imgs = host["imgs"].to(dev, non_blocking=True)
         dv = host["dv"].to(dev, non_blocking=True)
         proj = {k: v.to(dev, non_blocking=True) for k, v in host["proj"].items()}
@@ -309,14 +400,14 @@ def main():
         flat = {f"{k}.{kk}": vv for k, v in out.items() if isinstance(v, dict) for kk, vv in v.items()}
         if getattr(model, "refine", False):   # refine=True: the full-resolution refined depth is a map of its own (the streamed leg returns it too)
             flat["refined_depth"] = out["refined_depth"]
-        if out_host is None:
-            out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in flat.items()}
+        if not out_host:
+            out_host.update({k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in flat.items()})
         for k, v in flat.items():
             out_host[k].copy_(v, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the user reads the depth map on the host (test.py:206-207)
 
     step_e2e()
-    h2d = host["imgs"].numel() * 4 + host["dv"].numel() * 4 + sum(v.numel() * 4 for v in host["proj"].values())
+    h2d = (host["imgs"].numel() * host["imgs"].element_size() + host["dv"].numel() * 4 + sum(v.numel() * 4 for v in host["proj"].values()))
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -348,7 +439,7 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     ph2d, pd2h = pipe.bytes_per_item()
-    assert (ph2d, pd2h) == (h2d, d2h), "streamed path moves different bytes than the direct call"
+    assert (ph2d, pd2h) == (h2d, d2h), f"streamed path moves different bytes than the direct call: {(ph2d, pd2h)} vs {(h2d, d2h)}"
     clocks = sampler.stop() if rank == 0 else None
 
     from cds_mvsnet_b200 import parallel
@@ -384,33 +475,53 @@ def main():
         roof = {"bound": "tensor", "achieved": top["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": top["tflops"] / pk["tensor"]}
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": top["gbs"] / pk["hbm"]}
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram read + write bytes per launch)
-    traffic = None
+    # DRAM traffic / tensor-pipe utilisation of the same kernel from the committed `ncu --set full` capture
+    ncu = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{top['kernel']}[{top['tag']}]@{args.workload}")
-    roof.update({"traffic": traffic, "kernel": f"{top['kernel']}[{top['tag']}]", "share_of_step": top["share"],
+        ncu = json.load(open(tpath))
+    tkey = f"{top['kernel']}[{top['tag']}]@{args.workload}"
+    roof.update({"traffic": ncu.get(tkey), "kernel": f"{top['kernel']}[{top['tag']}]", "share_of_step": top["share"],
                  "ms_per_launch": top["ms_per_launch"], "peak_source": pk["src"],
                  "algorithmic": {"gflop_per_launch": top["alg_gflop"], "mb_per_launch": top["alg_mb"]}})
-    if top["kernel"].startswith("cds_dynamic_conv_tc"):
-        # what saturates first in the tap-GEMM formulation is the tensor core's shared-memory operand path, not the math pipe
-        roof["note"] = ("tap-GEMM DynamicConv: every K=16 MMA re-reads its 4 KB A slab pair and its B columns from shared memory; the "
-                        "committed ncu capture (profiles/r01_v12_ncu_conv00_pairs.txt) shows l1tex throughput 84.6 % with the tensor "
-                        "pipe 31 % active -- the kernel sits at ~5/6 of the shared-memory operand roofline (DESIGN.md section 5)")
+    if isinstance(ncu.get("_tensor_pipe_pct"), dict) and tkey in ncu["_tensor_pipe_pct"]:
+        roof["tensor_pipe_pct"] = ncu["_tensor_pipe_pct"][tkey]
+
+    # BASELINE.json's metric also names "warp+3Dconv HBM GB/s vs peak": the kernel groups of the step, each as algorithmic
+    # work / summed measured duration of its launches (the same instrumented K steps)
+    def group(pred):
+        sel = [r for r in rows if pred(r["tag"] or "")]
+        ms = sum(r["ms_per_launch"] * r["launches_per_step"] for r in sel)
+        gb = sum(r["alg_mb"] * r["launches_per_step"] for r in sel) / 1e3
+        tf = sum(r["alg_gflop"] * r["launches_per_step"] for r in sel) / 1e3
+        return {"ms_per_step": ms, "alg_gb_per_step": gb, "alg_tflop_per_step": tf, "gbs": gb / (ms / 1e3) if ms else 0.0,
+                "frac_hbm": gb / (ms / 1e3) / pk["hbm"] if ms else 0.0, "tflops": tf / (ms / 1e3) if ms else 0.0,
+                "frac_tensor": tf / (ms / 1e3) / pk["tensor"] if ms else 0.0, "launches": len(sel)}
+    roof["groups"] = {
+        "costvol": group(lambda t: "costvol" in t),                                        # the plane-sweep warp sweeps (HBM-bound on paper)
+        "regulariser": group(lambda t: ".cr." in t or "softmax_regress" in t or "regress_tail" in t),   # 3-D CNN + soft-argmin tail
+        "feature": group(lambda t: t.startswith("feat.")),                                 # DynamicConv feature extractor (tensor-bound)
+        "visnet": group(lambda t: "visnet" in t),
+    }
     if args.kernel_table:
         os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
         json.dump({"workload": workload_name(args.workload, cfg), "storage": args.storage, "ms_per_step": ms_total / args.steps,
-                   "peaks": pk, "kernels": rows}, open(args.kernel_table, "w"), indent=1)
+                   "peaks": pk, "kernels": rows, "groups": roof["groups"]}, open(args.kernel_table, "w"), indent=1)
     print("top kernels (share of summed kernel time):", file=sys.stderr)
-    for r in rows[:12]:
+    for r in rows[:14]:
         print(f"  {r['share'] * 100:5.1f}%  {r['ms_per_launch']:8.3f} ms  {r['tflops']:7.2f} TFLOP/s  {r['gbs']:7.1f} GB/s  {r['kernel']}[{r['tag']}]",
               file=sys.stderr)
+    for g, v in roof["groups"].items():
+        print(f"  group {g:12s} {v['ms_per_step']:7.3f} ms/step  {v['gbs']:7.1f} GB/s ({v['frac_hbm'] * 100:4.1f} % HBM)  "
+              f"{v['tflops']:7.1f} TFLOP/s ({v['frac_tensor'] * 100:4.1f} % tensor)", file=sys.stderr)
 
-    cpu = None
+    cpu = parity = incumbent = None
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        rate, _, sample = cpu_oracle_rate(cfg, cores, budget_s=25.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        parity, cpu = parity_and_cpu_baseline(cfg, model, dev)
+        print(f"parity vs CPU reference: {json.dumps(parity['stages'])}", file=sys.stderr)
+    if not args.no_incumbent and world == 1:
+        incumbent = reference_eager_gpu(cfg, dev)
+        print(f"incumbent (reference eager on this GPU): {json.dumps(incumbent)}", file=sys.stderr)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -418,6 +529,8 @@ def main():
         "dtype": "f16" if storage == torch.float16 else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, cfg), "storage": f"{args.storage} activations, fp32 accumulate",
                    "weights": "pretrained both_dtu_blended (tests/golden/weights_both_dtu_blended.npz)",
+                   "images": "synthetic photo-consistent plane views quantised to 8 bits (as the reference's loader reads them): "
+                             "fp32 = u8 / 255 resident in HBM for `value`, uint8 in pinned host memory for `e2e`",
                    "parallelism": f"replicas x{world}, work-list sharding, no collective",
                    "launch": "one CUDA graph per forward" if use_graph else "launch by launch",
                    "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
@@ -428,10 +541,13 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "api": "cds_mvsnet_b200.streaming.DepthMapStream (double-buffered copies)",
                 "one_call_at_a_time": {"value": maps / (ms_e2e_seq / 1e3), "ms_per_step": ms_e2e_seq / args.steps,
-                                       "api": "CDSMVSNet.__call__ on pinned host tensors, blocking per item"}},
+                                       "api": "CDSMVSNet.__call__ (the reference's call surface) on inputs uploaded from pinned host "
+                                              "memory, result maps read back, blocking per item"}},
         "gpu_launches": launches,
         "roofline": roof,
+        "parity": parity,
         "cpu_baseline": cpu,
+        "reference_eager_gpu": incumbent,
     }
     emit(line)
     if world > 1:

@@ -52,7 +52,7 @@ def parse_header(path: str = HEADER) -> dict:
 class _Lib:
     def __init__(self):
         self._dll = None
-        self._device_checked = False
+        self._devices_checked = set()   # CUDA device indices cds_check_device has accepted
 
     def load(self):
         if self._dll is not None:
@@ -69,15 +69,19 @@ class _Lib:
         self._dll = dll
         return dll
 
+    def check_device(self, index: int):
+        """cds_check_device on the CUDA runtime's current device (once per device index)."""
+        if index in self._devices_checked:
+            return
+        if not torch.cuda.is_available():
+            raise RuntimeError("cds_b200 needs a CUDA device (B200, sm_100a); none is visible")
+        rc = self.load().cds_check_device()
+        if rc != 0:
+            raise RuntimeError(self._dll.cds_last_error_string().decode())
+        self._devices_checked.add(index)
+
     def call(self, name: str, *args):
         dll = self.load()
-        if not self._device_checked:
-            if not torch.cuda.is_available():
-                raise RuntimeError("cds_b200 needs a CUDA device (B200, sm_100a); none is visible")
-            rc = dll.cds_check_device()
-            if rc != 0:
-                raise RuntimeError(dll.cds_last_error_string().decode())
-            self._device_checked = True
         rc = getattr(dll, name)(*args)
         if rc != 0:
             raise RuntimeError(f"{name} failed (code {rc}): {dll.cds_last_error_string().decode()}")
@@ -86,13 +90,35 @@ class _Lib:
 LIB = _Lib()
 
 
+# The library launches on the CUDA runtime's CURRENT device with the stream it is handed.  ``ptr`` therefore notes the device
+# of every tensor that becomes a kernel argument and ``call`` (1) refuses a launch whose tensors live on different devices,
+# (2) makes that device current for the launch and (3) passes torch's current stream OF THAT DEVICE -- so
+# ``model.to("cuda:1")`` works whatever the process-wide current device is.
+_ARG_DEVICES = []   # device indices of the tensors handed to ``ptr`` since the last launch
+
+
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
-    return None if t is None else t.data_ptr()
+    """Device pointer of a tensor (None -> NULL).  CPU tensors are refused: there is no CPU fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("cds_b200: a CPU tensor reached a kernel argument; there is no CPU fallback")
+    _ARG_DEVICES.append(t.device.index)
+    return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def _launch_device():
+    """Device index the next launch goes to: the one its tensor arguments live on (the current device if it has none)."""
+    if not _ARG_DEVICES:
+        return torch.cuda.current_device()
+    idx = _ARG_DEVICES[0]
+    for d in _ARG_DEVICES:
+        if d != idx:
+            devs = sorted(set(_ARG_DEVICES))
+            _ARG_DEVICES.clear()
+            raise RuntimeError(f"cds_b200: one launch was handed tensors on different devices (cuda:{devs})")
+    _ARG_DEVICES.clear()
+    return idx
 
 
 LAUNCHES = 0   # C-ABI calls issued by this process (every inference entry enqueues exactly one kernel)
@@ -133,15 +159,21 @@ def set_tag(tag, meta=None):
 
 def call(name, *args):
     global LAUNCHES
+    idx = _launch_device()
+    if idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):   # also switches the CUDA runtime's device, which is what the library launches on
+            return call(name, *args)
+    LIB.check_device(idx)
+    st = torch.cuda.current_stream(idx)
     prof = _PROFILE
     if prof is not None:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        LIB.call(name, *args, stream())
-        b.record()
+        a.record(st)
+        LIB.call(name, *args, st.cuda_stream)
+        b.record(st)
         prof.records.append((name, _TAG[0], _TAG[1], a, b))
     else:
-        LIB.call(name, *args, stream())
+        LIB.call(name, *args, st.cuda_stream)
     LAUNCHES += 1
 
 

@@ -598,6 +598,18 @@ __global__ void __launch_bounds__(256) instnorm_act_kernel(const T* __restrict__
 }
 
 // ---- layout converters at the drop-in boundary (fp32 NCHW <-> channels-last storage type) ----
+__global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, long long n4, float4* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const uchar4 v = __ldg(in + i);
+        out[i] = make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f), __fdiv_rn((float)v.z, 255.f),
+                             __fdiv_rn((float)v.w, 255.f));
+    }
+}
+__global__ void u8_to_f32_tail_kernel(const unsigned char* __restrict__ in, long long from, long long n, float* __restrict__ out) {
+    const long long i = from + threadIdx.x;
+    if (i < n) out[i] = __fdiv_rn((float)in[i], 255.f);
+}
+
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, long long HW, T* __restrict__ out) {
     const int n = blockIdx.y;
@@ -738,6 +750,18 @@ int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C
         instnorm_act_kernel<float><<<grid, 256, C * 2 * sizeof(float), stream>>>((const float*)raw, stats, act, C, HW, (float*)out);
     else { cds_set_error("cds_instnorm_act: unknown dtype %d", dtype); return CDS_EARG; }
     return cds_check_launch("cds_instnorm_act");
+}
+
+int cds_image_u8_to_f32(const unsigned char* in, long long count, float* out, cudaStream_t stream) {
+    CDS_REQUIRE(in && out && count > 0, CDS_EARG, "cds_image_u8_to_f32: bad arguments");
+    CDS_REQUIRE(((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 15) == 0, CDS_EARG, "cds_image_u8_to_f32: in must be 4-byte, out 16-byte aligned");
+    const long long n4 = count / 4;
+    if (n4 > 0) {
+        const unsigned grid = (unsigned)std::min<long long>(148 * 16, (n4 + 255) / 256);
+        u8_to_f32_kernel<<<grid, 256, 0, stream>>>((const uchar4*)in, n4, (float4*)out);
+    }
+    if (count % 4) u8_to_f32_tail_kernel<<<1, 4, 0, stream>>>(in, n4 * 4, count, out);
+    return cds_check_launch("cds_image_u8_to_f32");
 }
 
 int cds_nchw_to_nhwc(const float* in, int n, int C, int H, int W, int dtype, void* out, cudaStream_t stream) {

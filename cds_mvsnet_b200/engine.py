@@ -65,9 +65,10 @@ class FeatureExtractor:
         self.storage = storage
         self.dt = _lib.dtype_code(storage)
         self.use_tc = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_DYN", "1") != "0"
-        # opt-in: hi/lo fp16 activation planes into conv10/conv11 (4x lower error in those layers at 2x their MMAs; the
-        # end-to-end gain on the worst-case input is within sample noise)
-        self.split_precision = os.environ.get("CDS_SPLIT", "0") == "1"
+        # hi/lo fp16 activation planes (~22-bit activations) into conv10/conv11, the layers the depth output is most sensitive
+        # to: without it the worst-case "noise" input exceeds north_star's 1e-3 on some seeds (seed 4
+        # 2.6e-3 -> 9e-4).  CDS_SPLIT=0 turns it off (diagnostics only).
+        self.split_precision = os.environ.get("CDS_SPLIT", "1") != "0"
         self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
         # inner1/inner2 (1x1 conv over the concatenation): the 2x2-block CUDA-core form (fp32 math, 0.154 / 0.133 ms at cfg2) beats the
         # gather-form tensor-core kernel (0.289 / 0.156 ms) on this 24- / 48-deep contraction; CDS_TC_INNER=1 selects the latter
@@ -409,25 +410,51 @@ class CascadeEngine:
         kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P + C * D * P * e,
               "cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
               ptr(volume))
-        nc = buf.get(f"s{s}.nc", (B, 1, h, w), f32)
+        nc = self._out_views[s][2]
         kcall(f"s{s}.nc_mean", 0, 4 * P * (2 * V + 1), "cds_nc_mean", ptr(ncsq[:VB]), ptr(ncsq[VB:]), V, B * h * w, ptr(nc))
         logits = self.regs[s].run(buf, f"s{s}.cr", volume, B, D, h, w)
-        depth = buf.get(f"s{s}.depth", (B, h, w), f32)
-        conf = buf.get(f"s{s}.conf", (B, h, w), f32)
+        depth, conf = self._out_views[s][0], self._out_views[s][1]
         kcall(f"s{s}.softmax_regress", 0, 8 * D * P + 8 * P, "cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w,
               ptr(depth), ptr(conf), None)
         return {"depth": depth, "photometric_confidence": conf, "norm_curv": nc}
+
+    def _alloc_outputs(self, B, H, W):
+        """The per-stage result maps (depth, photometric_confidence [B,h,w]; norm_curv [B,1,h,w]) are views of ONE buffer, so a
+        caller that needs private copies (``CDSMVSNet.forward``) makes one device copy instead of nine."""
+        sizes = [B * (H // STAGE_SCALE[s]) * (W // STAGE_SCALE[s]) for s in range(len(self.ndepths))]
+        pack = self._out_pack = self.buf.get("out.pack", (3 * sum(sizes),), torch.float32)
+        self._out_views, o = [], 0
+        for s, n in enumerate(sizes):
+            h, w = H // STAGE_SCALE[s], W // STAGE_SCALE[s]
+            self._out_views.append((pack[o:o + n].view(B, h, w), pack[o + n:o + 2 * n].view(B, h, w),
+                                    pack[o + 2 * n:o + 3 * n].view(B, 1, h, w)))
+            o += 3 * n
+        return pack
+
+    def outputs_from(self, pack, refined=None):
+        """The reference's output dict (models/model.py:199-223) over the maps stored in ``pack`` (a copy of ``out.pack``)."""
+        out, o = {}, 0
+        for s, (d, c, n) in enumerate(self._out_views):
+            k = d.numel()
+            st = {"depth": pack[o:o + k].view(d.shape), "photometric_confidence": pack[o + k:o + 2 * k].view(c.shape),
+                  "norm_curv": pack[o + 2 * k:o + 3 * k].view(n.shape)}
+            o += 3 * k
+            out[f"stage{s + 1}"] = st
+            out.update(st)
+        out["refined_depth"] = refined if refined is not None else out["depth"]
+        return out
 
     # -- whole forward as one CUDA graph ----------------------------------------------------------
     def forward_graph(self, imgs, proj_matrices, depth_values, temperature=0.001):
         """Same as ``forward`` for DEVICE inputs, replayed from a CUDA graph: the ~70 launches of a forward (all on static
         buffers, every argument fixed by the input shapes) are captured once per input signature and re-issued as one graph
         launch; the inputs are copied into the graph's static input tensors first.  Returns the engine's output buffers."""
-        key = (tuple(imgs.shape), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())), tuple(depth_values.shape),
-               float(temperature))
+        key = (tuple(imgs.shape), imgs.dtype, tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
+               tuple(depth_values.shape), float(temperature))
         if getattr(self, "_graph_key", None) != key:
             dev, f32 = self.device, torch.float32
-            self._g_imgs = torch.empty(imgs.shape, dtype=f32, device=dev)
+            self._graph = self._graph_key = None   # the buffers below may move: the old graph must never be replayed again
+            self._g_imgs = torch.empty(imgs.shape, dtype=imgs.dtype if imgs.dtype == torch.uint8 else f32, device=dev)
             self._g_proj = {k: torch.empty(v.shape, dtype=f32, device=dev) for k, v in proj_matrices.items()}
             self._g_dv = torch.empty(depth_values.shape, dtype=f32, device=dev)
             self._copy_inputs(imgs, proj_matrices, depth_values)
@@ -459,6 +486,13 @@ class CascadeEngine:
             raise AssertionError("need at least one source view")
         V = N - 1
         dev = self.device
+        if imgs.dtype == torch.uint8:
+            # 8-bit images as the data layer reads them (datasets/general_eval.py:74: np.float32(img) / 255.): uploaded as bytes
+            # (a quarter of the PCIe traffic) and divided here -- the IEEE fp32 quotient is bit-identical to the host's
+            u8 = imgs.to(device=dev).contiguous()
+            imgs = self.buf.get("in.imgs_f32", tuple(u8.shape), torch.float32)
+            kcall("image_u8_to_f32", 0, 5 * u8.numel(), "cds_image_u8_to_f32", ptr(u8), u8.numel(), ptr(imgs))
+            self._keep_u8 = u8
         imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
         full_imgs, Hf, Wf = imgs, H, W
         if self.refiner is not None:
@@ -474,6 +508,7 @@ class CascadeEngine:
             raise RuntimeError(f"H and W must be divisible by 32 (got {H}x{W}); see SURVEY.md 8c fixture 6")
         depth_values = depth_values.to(device=dev, dtype=torch.float32).contiguous()
         coef, epi = self.camera_setup(proj_matrices, B, N)
+        self._alloc_outputs(B, H, W)
         n = 2 * V * B
         key = ("imgidx", B, N)
         if getattr(self, "_imgidx_key", None) != key:

@@ -16,7 +16,13 @@ The torch ``nn`` sub-modules inside these classes are parameter CONTAINERS only 
 state dict the reference's key names); they are never called.  Every forward runs the CUDA kernels
 of libcds_b200.so through the C ABI and raises if the library or a B200 is missing.  Public tensors
 are fp32 NCHW / NCDHW like the reference's; the fused paths keep channels-last fp16 internally.
-Inference only (eval mode): training-mode forwards raise NotImplementedError.
+``CDSMVSNet`` covers ``refine=False`` and ``refine=True`` (``Refinement``, models/module.py:318-370).  The op-level
+``homo_warping_3D`` / ``depth_regression`` are differentiable (their backward kernels live in csrc/train.cu); the fused
+module forwards are inference only (eval mode): training-mode forwards raise NotImplementedError.
+
+``patch(models_model, models_module, level=...)`` rebinds these names inside an imported reference tree at four depths:
+"leaf" swaps only the leaf operators (DynamicConv, CostRegNet, the warp and regression functions), "ops" also FeatureNet and keeps the reference's own ``CDSMVSNet.forward`` and ``StageNet.forward`` and swaps the operators they call,
+"stage" also swaps ``StageNet`` (the fused cost-volume kernels), "model" swaps ``CDSMVSNet`` itself (one CUDA graph).
 """
 from __future__ import annotations
 
@@ -154,10 +160,36 @@ def conf_regression(p, n=4):
 # weight-cache plumbing shared by the modules
 # ------------------------------------------------------------------------------------------------
 class _CachedModule(nn.Module):
-    """Rebuilds the derived (folded / re-laid-out) weights when parameters may have changed."""
+    """Rebuilds the derived (folded / re-laid-out) weights when parameters may have changed.
+
+    ``load_state_dict`` / ``.to()`` / ``.train()`` of THIS module drop the cache at once; everything else that can change a
+    weight -- ``model.feature.load_state_dict(...)`` on a submodule, ``p.data.copy_()``, an optimizer step, an EMA swap -- is
+    caught by a fingerprint checked at every forward: the (storage address, in-place version counter) of every parameter and
+    buffer below this module."""
 
     def _invalidate(self):
         object.__setattr__(self, "_cache", None)
+        object.__setattr__(self, "_fp", None)
+        object.__setattr__(self, "_fp_tensors", None)
+
+    def _fingerprint(self):
+        ts = self._fp_tensors
+        if ts is None:
+            ts = list(self.parameters()) + list(self.buffers())
+            object.__setattr__(self, "_fp_tensors", ts)
+        return tuple([(t.data_ptr(), t._version) for t in ts])
+
+    def _check_cache(self):
+        """Drop the derived weights if any parameter / buffer was re-allocated or written since they were built."""
+        if self._cache is None:
+            object.__setattr__(self, "_fp_tensors", None)   # the module tree may have changed since the last build
+            object.__setattr__(self, "_fp", self._fingerprint())
+            return
+        fp = self._fingerprint()
+        if fp != self._fp:
+            object.__setattr__(self, "_cache", None)
+            object.__setattr__(self, "_fp_tensors", None)
+            object.__setattr__(self, "_fp", self._fingerprint())
 
     def __init__(self):
         super().__init__()
@@ -173,6 +205,7 @@ class _CachedModule(nn.Module):
         return super().train(mode)
 
     def _require_eval(self):
+        self._check_cache()
         if self.training:
             raise NotImplementedError(f"{type(self).__name__}: the CUDA path is inference-only; call .eval() first "
                                       "(training-mode BatchNorm / autograd are out of scope, SURVEY.md 8f-3)")
@@ -207,6 +240,9 @@ class DynamicConv(_CachedModule):
             raise NotImplementedError("DynamicConv: stride must be 1 (the reference's att_convs ignore stride, "
                                       "models/dynamic_conv.py:85-86, so any other value breaks there too)")
         self.size_kernels = tuple(size_kernels)
+        if len(self.size_kernels) not in (2, 3) or any(k % 2 == 0 or k < 1 for k in self.size_kernels):
+            raise NotImplementedError("DynamicConv: the CUDA kernels take 2 or 3 odd kernel sizes (every layer of the reference's "
+                                      f"FeatureNet, models/module.py:211-234); got {self.size_kernels}")
         self.thresh_scale = thresh_scale
         self.in_c, self.out_c = in_c, out_c
         self.storage = kwargs.pop("storage", DEFAULT_STORAGE)
@@ -238,7 +274,8 @@ class DynamicConv(_CachedModule):
         ks = (ctypes.c_int * len(w.ksizes))(*w.ksizes)
         epi = _f32c(epipole)
         cin_tc = max(8, self.in_c)
-        if (self.use_tc and self.storage == torch.float16
+        # tensor-core path: 8-channel operand slabs -- the 3-channel image (padded by cds_image_to_nhwc8) or C % 8 == 0
+        if (self.use_tc and self.storage == torch.float16 and (self.in_c == 3 or self.in_c % 8 == 0)
                 and _lib.LIB.load().cds_dynamic_conv_tc_supported(cin_tc, self.out_c, H, Wd, len(w.ksizes), ks)):
             # tensor-core path (tcgen05): fp16 channels-last pixels, image zero-padded from 3 to 8 channels
             if w.tc is None:
@@ -353,6 +390,7 @@ class CostRegNet(_CachedModule):
         self.prob = nn.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
 
     def _engine(self, dev):
+        self._check_cache()
         if self._cache is None:
             object.__setattr__(self, "_cache", (Regulariser(W.pack_costreg(self._sd("cr."), "cr", dev), self.storage), Buffers(dev)))
         return self._cache
@@ -491,6 +529,7 @@ class CDSMVSNet(_CachedModule):
             self.refine_network = Refinement()
 
     def engine(self, dev) -> CascadeEngine:
+        self._check_cache()
         if self._cache is None:
             mw = W.pack_model(self.state_dict(), self.num_stage, dev)
             rw = W.pack_refinement({k: v.detach() for k, v in self.state_dict().items()}, "refine_network", dev) if self.refine else None
@@ -499,30 +538,68 @@ class CDSMVSNet(_CachedModule):
         return self._cache
 
     def forward(self, imgs, proj_matrices, depth_values, gt_depths=None, temperature=0.001):
-        """imgs [B,N,3,H,W], proj_matrices {"stageK": [B,N,2,4,4]}, depth_values [B,Dtot] -> the reference's output
-        dict (models/model.py:140-223): per-stage dicts + top-level copies of the last stage + refined_depth."""
+        """imgs [B,N,3,H,W] (fp32 in [0,1], or uint8: divided by 255 on the device), proj_matrices {"stageK": [B,N,2,4,4]},
+        depth_values [B,Dtot] -> the reference's output dict (models/model.py:140-223): per-stage dicts + top-level copies of
+        the last stage + refined_depth.
+
+        The ~70 launches of a forward are replayed as ONE CUDA graph, captured the first time an input signature (shapes,
+        temperature) is seen; ``CDS_GRAPH=0`` or a caller that is itself capturing falls back to launch-by-launch.  The
+        returned tensors are the caller's own (one device copy of the packed result maps), never the engine's buffers."""
         self._require_eval()
         if gt_depths is not None:
             raise NotImplementedError("gt_depths is a training input (out of scope)")
         dev = _dev(imgs)
-        out = self.engine(dev).forward(imgs, proj_matrices, depth_values, temperature)
-        # fresh tensors: the engine's buffers are reused by the next call
-        res = {}
-        for k, v in out.items():
-            res[k] = {kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone()
-        return res
+        eng = self.engine(dev)
+        with torch.cuda.device(dev):
+            graphed = _USE_GRAPH and not torch.cuda.is_current_stream_capturing()
+            out = (eng.forward_graph if graphed else eng.forward)(imgs, proj_matrices, depth_values, temperature)
+            refined = out["refined_depth"].clone() if self.refine else None
+            return eng.outputs_from(eng._out_pack.clone(), refined)
+
+
+_USE_GRAPH = __import__("os").environ.get("CDS_GRAPH", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
-def patch(models_model=None, models_module=None):
-    """Rebind the hot-path names inside an imported reference ``models.model`` / ``models.module`` so that
-    the reference's own driver code constructs and calls the CUDA implementations."""
-    if models_model is not None:
-        for name, obj in (("homo_warping_3D", homo_warping_3D), ("depth_regression", depth_regression),
-                          ("conf_regression", conf_regression), ("CostRegNet", CostRegNet), ("StageNet", StageNet),
-                          ("FeatureNet", FeatureNet), ("Refinement", Refinement), ("CDSMVSNet", CDSMVSNet)):
-            setattr(models_model, name, obj)
-    if models_module is not None:
-        for name, obj in (("DynamicConv", DynamicConv), ("depth_regression", depth_regression),
-                          ("conf_regression", conf_regression), ("CostRegNet", CostRegNet), ("FeatureNet", FeatureNet)):
-            setattr(models_module, name, obj)
+PATCH_LEVELS = ("leaf", "ops", "stage", "model")
+
+
+def patch(models_model=None, models_module=None, level="model"):
+    """Rebind the hot-path names inside an imported reference ``models.model`` / ``models.module`` so that the reference's
+    own code constructs and calls the CUDA implementations (the names are those models/model.py:4-6 imports).
+
+    level="leaf":  only the leaf operators: ``DynamicConv`` (inside the reference's own ``Conv2d`` / ``FeatureNet``),
+                   ``CostRegNet``, ``Refinement``, ``homo_warping_3D``, ``depth_regression``, ``conf_regression``.
+    level="ops":   additionally ``FeatureNet``: the reference's own ``CDSMVSNet.forward`` (models/model.py:140-223) and ``StageNet.forward`` (:16-94) keep
+                   driving the cascade; ``FeatureNet``, ``CostRegNet``, ``Refinement``, ``DynamicConv``, ``homo_warping_3D``,
+                   ``depth_regression`` and ``conf_regression`` are the CUDA ones (state-dict keys unchanged).
+    level="stage": additionally ``StageNet`` = the fused plane-sweep / visibility / aggregation kernels.
+    level="model": additionally ``CDSMVSNet`` itself (feature batching across views, the whole cascade as one CUDA graph).
+    Returns {module: {name: original}} so that ``unpatch`` can restore the reference."""
+    if level not in PATCH_LEVELS:
+        raise ValueError(f"patch level must be one of {PATCH_LEVELS}, got {level!r}")
+    ops = [("homo_warping_3D", homo_warping_3D), ("depth_regression", depth_regression), ("conf_regression", conf_regression),
+           ("CostRegNet", CostRegNet), ("Refinement", Refinement), ("DynamicConv", DynamicConv)]
+    if level != "leaf":
+        ops.append(("FeatureNet", FeatureNet))
+    if level in ("stage", "model"):
+        ops.append(("StageNet", StageNet))
+    if level == "model":
+        ops.append(("CDSMVSNet", CDSMVSNet))
+    saved = {}
+    for mod in (models_model, models_module):
+        if mod is None:
+            continue
+        saved[mod] = {}
+        for name, obj in ops:
+            if hasattr(mod, name):   # only names the reference module itself binds
+                saved[mod][name] = getattr(mod, name)
+                setattr(mod, name, obj)
+    return saved
+
+
+def unpatch(saved):
+    """Undo ``patch`` (its return value)."""
+    for mod, names in saved.items():
+        for name, obj in names.items():
+            setattr(mod, name, obj)

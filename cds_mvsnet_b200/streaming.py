@@ -24,10 +24,12 @@ import torch
 
 class _Slot:
     def __init__(self):
+        self.sig = None           # input signature (shapes, image dtype, projection keys) the buffers below were made for
         self.dev_in = None        # (imgs, proj dict, depth_values) on the device
-        self.dev_out = None       # flat dict of device staging tensors
-        self.host_in = None       # pinned staging for unpinned callers
-        self.host_out = None      # flat dict of pinned host tensors
+        self.dev_out = None       # device staging copies of (packed result maps, refined depth | None)
+        self.host_in = {}         # persistent pinned staging for unpinned callers
+        self.host_pack = None     # pinned copies of the packed result buffer (and the refined depth)
+        self.host_out = None      # flat dict of views of host_pack
         self.ev_in = torch.cuda.Event()       # upload finished
         self.ev_done = torch.cuda.Event()     # compute + staging copy finished (inputs may be overwritten)
         self.ev_out = torch.cuda.Event()      # download finished
@@ -58,23 +60,46 @@ class DepthMapStream:
         self.s_out = torch.cuda.Stream()
 
     @staticmethod
-    def _pinned(t):
-        return t if t.is_pinned() else t.pin_memory()
+    def _signature(imgs, proj_matrices, depth_values):
+        return (tuple(imgs.shape), imgs.dtype, tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
+                tuple(depth_values.shape))
+
+    def _stage_host(self, slot, name, t, dtype):
+        """A pinned host tensor holding ``t``: ``t`` itself if the caller pinned it, else the slot's persistent pinned staging
+        buffer (allocated once per input signature -- cudaHostAlloc per submit would serialise the pipeline)."""
+        t = t if t.dtype == dtype else t.to(dtype)
+        if t.is_pinned():
+            return t
+        buf = slot.host_in.get(name)
+        if buf is None or buf.shape != t.shape or buf.dtype != dtype:
+            buf = slot.host_in[name] = torch.empty(t.shape, dtype=dtype).pin_memory()
+        buf.copy_(t)
+        return buf
 
     def submit(self, imgs, proj_matrices, depth_values):
-        """Enqueue one work item given as HOST tensors; returns a ticket for ``result``."""
+        """Enqueue one work item given as HOST tensors; returns a ticket for ``result``.  ``imgs`` may be fp32 in [0,1] or
+        uint8 (the bytes the data layer read; divided by 255 on the device, a quarter of the upload)."""
         if imgs.is_cuda:
             raise ValueError("DepthMapStream.submit takes host tensors (use model(...) for device-resident inputs)")
         dev = next(self.model.parameters()).device
         compute = torch.cuda.current_stream(dev)
         slot = self.slots[self.n % len(self.slots)]
-        imgs, depth_values = self._pinned(imgs), self._pinned(depth_values)
-        proj_matrices = {k: self._pinned(v) for k, v in proj_matrices.items()}
-        if slot.dev_in is None or slot.dev_in[0].shape != imgs.shape:
-            slot.dev_in = (torch.empty(imgs.shape, dtype=torch.float32, device=dev),
+        img_dtype = torch.uint8 if imgs.dtype == torch.uint8 else torch.float32
+        sig = self._signature(imgs, proj_matrices, depth_values)
+        if slot.sig != sig:
+            # any change of shape, image dtype or projection keys re-creates the slot's device inputs (a stale key from a
+            # previous signature must never reach the engine) and its staging buffers
+            if slot.used:
+                slot.ev_out.synchronize()
+            slot.sig, slot.host_in, slot.dev_out, slot.host_out = sig, {}, None, None
+            slot.dev_in = (torch.empty(imgs.shape, dtype=img_dtype, device=dev),
                            {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in proj_matrices.items()},
                            torch.empty(depth_values.shape, dtype=torch.float32, device=dev))
-            slot.dev_out = None
+        if slot.used:
+            slot.ev_in.synchronize()   # the previous upload out of this slot's pinned staging has finished
+        imgs = self._stage_host(slot, "imgs", imgs, img_dtype)
+        depth_values = self._stage_host(slot, "dv", depth_values, torch.float32)
+        proj_matrices = {k: self._stage_host(slot, "proj." + k, v, torch.float32) for k, v in proj_matrices.items()}
         # ---- upload on its own stream, once the slot's previous occupant has been consumed by the kernels
         with torch.cuda.stream(self.s_in):
             if slot.used:
@@ -88,20 +113,28 @@ class DepthMapStream:
         compute.wait_event(slot.ev_in)
         engine = self.model.engine(dev)
         run = engine.forward_graph if self.use_graph else engine.forward
-        out = _flatten(run(slot.dev_in[0], slot.dev_in[1], slot.dev_in[2], self.temperature))
+        out = run(slot.dev_in[0], slot.dev_in[1], slot.dev_in[2], self.temperature)
+        # the engine keeps every result map in ONE packed buffer (+ the refined depth when refine=True): one staging copy and
+        # one download per item; the host-side dict is a set of views of the pinned copy
+        pack = engine._out_pack
+        refined = out["refined_depth"] if getattr(self.model, "refine", False) else None
         if slot.dev_out is None:
-            slot.dev_out = {k: torch.empty_like(v) for k, v in out.items()}
-            slot.host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+            slot.dev_out = (torch.empty_like(pack), torch.empty_like(refined) if refined is not None else None)
+            slot.host_pack = (torch.empty(pack.shape, dtype=pack.dtype).pin_memory(),
+                              torch.empty(refined.shape, dtype=refined.dtype).pin_memory() if refined is not None else None)
+            slot.host_out = _flatten(engine.outputs_from(*slot.host_pack))
         if slot.used:
             compute.wait_event(slot.ev_out)      # the staging tensors were last read by the slot's previous download
-        for k, v in out.items():                 # engine buffers are reused by the next forward: stage the results
-            slot.dev_out[k].copy_(v, non_blocking=True)
+        slot.dev_out[0].copy_(pack, non_blocking=True)   # engine buffers are reused by the next forward: stage the results
+        if refined is not None:
+            slot.dev_out[1].copy_(refined, non_blocking=True)
         slot.ev_done.record(compute)
         # ---- download on its own stream
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot.ev_done)
-            for k, v in slot.dev_out.items():
-                slot.host_out[k].copy_(v, non_blocking=True)
+            for d, h in zip(slot.dev_out, slot.host_pack):
+                if d is not None:
+                    h.copy_(d, non_blocking=True)
             slot.ev_out.record(self.s_out)
         slot.used = True
         ticket = self.n
@@ -119,6 +152,7 @@ class DepthMapStream:
 
     def bytes_per_item(self):
         slot = next(s for s in self.slots if s.used)
-        h2d = slot.dev_in[0].numel() * 4 + slot.dev_in[2].numel() * 4 + sum(v.numel() * 4 for v in slot.dev_in[1].values())
+        h2d = (slot.dev_in[0].numel() * slot.dev_in[0].element_size() + slot.dev_in[2].numel() * 4 +
+               sum(v.numel() * 4 for v in slot.dev_in[1].values()))
         d2h = sum(v.numel() * v.element_size() for v in slot.host_out.values())
         return h2d, d2h

@@ -29,6 +29,17 @@ COSTREG_CONVS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
 COSTREG_DECONVS = ("conv7", "conv9", "conv11")
 
 
+def _host(sd):
+    """The state dict on the HOST: every fold / re-layout below is host arithmetic (fp64), only the finished operand images are
+    uploaded -- a model that already sits on the GPU must not turn weight packing into hundreds of tiny device kernels."""
+    return {k: v.detach().cpu() for k, v in sd.items()}
+
+
+def _up(t, dtype, device):
+    """Convert and make contiguous on the HOST, then upload (one memcpy, no device kernel)."""
+    return t.detach().cpu().to(dtype).contiguous().to(device)
+
+
 def _bn_fold(sd, prefix):
     g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
     m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
@@ -49,6 +60,7 @@ class DynWeights:
 
 
 def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
+    sd = _host({k: v for k, v in sd.items() if k.startswith(prefix + ".")})
     att, conv, bias = [], [], []
     for i, k in enumerate(ksizes):
         a = sd[f"{prefix}.att_convs.{i}.weight"].double()          # [3,Cin,k,k]
@@ -65,8 +77,8 @@ def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
     w2 = sd[f"{prefix}.att_weights.3.weight"].double().reshape(K, 4)
     gate = torch.cat((w1.reshape(-1), shift.reshape(-1), w2.reshape(-1)))
     f32 = dict(dtype=torch.float32, device=device)
-    return DynWeights(cin, cout, tuple(ksizes), torch.cat(att).to(**f32).contiguous(), torch.cat(conv).to(**f32).contiguous(),
-                      torch.stack(bias).to(**f32).contiguous() if bias else None, gate.to(**f32).contiguous())
+    return DynWeights(cin, cout, tuple(ksizes), torch.cat(att).to(torch.float32).contiguous().to(device), torch.cat(conv).to(torch.float32).contiguous().to(device),
+                      torch.stack(bias).to(torch.float32).contiguous().to(device) if bias else None, gate.to(torch.float32).contiguous().to(device))
 
 
 def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
@@ -81,7 +93,7 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     [k-chunk 2][N/8][8 n][8 k]."""
     cin, cout = w.cin, w.cout
     c8 = max(1, cin // 8)
-    att, conv = w.w_att.detach().double().cpu(), w.w_conv.detach().double().cpu()
+    att, conv = w.w_att.detach().cpu().double(), w.w_conv.detach().cpu().double()
     K, kmax = len(w.ksizes), max(w.ksizes)
     wlo = K == 2                                  # two-branch layers also carry the feature weights' fp16 residual
     fcols = (2 if wlo else 1) * cout               # feature columns per branch; the curvature columns follow
@@ -131,23 +143,24 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     for t in ring:
         assert full[t, :, :npad * (K - 1)].abs().max() == 0     # only the largest kernel reaches the ring
     out = torch.cat((image(slabs_of(inner, True), 0, npad * K), image(slabs_of(ring, False), npad * (K - 1), npad)))
-    return out.to(dtype=torch.float16, device=w.w_conv.device).contiguous()
+    return out.to(torch.float16).contiguous().to(w.w_conv.device)
 
 
 def pack_conv2d(sd, key, device) -> torch.Tensor:
-    w = sd[key].double()                                            # [Cout,Cin,k,k]
+    w = sd[key].detach().cpu().double()                                            # [Cout,Cin,k,k]
     co, ci, k, _ = w.shape
-    return w.permute(2, 3, 1, 0).reshape(k * k, ci, co).to(dtype=torch.float32, device=device).contiguous()
+    return w.permute(2, 3, 1, 0).reshape(k * k, ci, co).to(torch.float32).contiguous().to(device)
 
 
 def pack_visnet(sd, prefix, device) -> torch.Tensor:
+    sd = _host({k: v for k, v in sd.items() if k.startswith(prefix + ".")})
     parts = []
     for j in range(3):
         scale, shift = _bn_fold(sd, f"{prefix}.{j}.bn")
         w = sd[f"{prefix}.{j}.conv.weight"].double() * scale.reshape(-1, 1, 1, 1)   # [16,Cin,3,3]
         parts += [w.permute(2, 3, 1, 0).reshape(-1), shift.reshape(-1)]
     parts += [sd[f"{prefix}.3.weight"].double().reshape(-1), sd[f"{prefix}.3.bias"].double().reshape(-1)]
-    return torch.cat(parts).to(dtype=torch.float32, device=device).contiguous()
+    return torch.cat(parts).to(torch.float32).contiguous().to(device)
 
 
 def pack_visnet_tc(sd, prefix, device):
@@ -179,9 +192,9 @@ def pack_visnet_tc(sd, prefix, device):
             for c in range(2):
                 img[t, c] = wt[:, c * 8:(c + 1) * 8].reshape(2, 8, 8)      # [n-group][n][k]
         parts.append(img.reshape(-1))
-    wgt = torch.cat(parts).to(dtype=torch.float16, device=device).contiguous()
+    wgt = torch.cat(parts).to(torch.float16).contiguous().to(device)
     fp = torch.cat((bs[0], bs[1], bs[2], sd[f"{prefix}.3.weight"].double().reshape(-1).cpu(),
-                    sd[f"{prefix}.3.bias"].double().reshape(-1).cpu())).to(dtype=torch.float32, device=device).contiguous()
+                    sd[f"{prefix}.3.bias"].double().reshape(-1).cpu())).to(torch.float32).contiguous().to(device)
     return wgt, fp
 
 
@@ -195,6 +208,7 @@ class Conv3dWeights:
 
 
 def pack_conv3d(sd, prefix, transposed, device) -> Conv3dWeights:
+    sd = _host({k: v for k, v in sd.items() if k.startswith(prefix + ".")})
     scale, shift = _bn_fold(sd, prefix + ".bn")
     w = sd[prefix + ".conv.weight"].double()
     if transposed:   # [Cin,Cout,3,3,3]
@@ -204,7 +218,7 @@ def pack_conv3d(sd, prefix, transposed, device) -> Conv3dWeights:
         co, ci = w.shape[:2]
         w = (w * scale.reshape(-1, 1, 1, 1, 1)).permute(2, 3, 4, 1, 0)
     f32 = dict(dtype=torch.float32, device=device)
-    return Conv3dWeights(ci, co, w.reshape(27, ci, co).to(**f32).contiguous(), shift.to(**f32).contiguous())
+    return Conv3dWeights(ci, co, w.reshape(27, ci, co).to(torch.float32).contiguous().to(device), shift.to(torch.float32).contiguous().to(device))
 
 
 def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
@@ -215,7 +229,7 @@ def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
     ci, co = l.cin, l.cout
     c8 = ci // 8
     npad = max(16, co)
-    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout]
+    w = l.w.detach().cpu().to(torch.float64)                       # [27, Cin, Cout]
     if c8 == 1:
         slabs = [(0, 0), None] + [(t, 0) for t in range(1, 27)]
     else:
@@ -234,7 +248,7 @@ def pack_conv3d_tc(l: Conv3dWeights) -> torch.Tensor:
             full[:, :co] = hi
             full[:, co:2 * co] = blk - hi
         img[s // 2, s % 2] = full.t().reshape(npad // 8, 8, 8)      # [n-group, n row, k]
-    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+    return img.to(torch.float16).contiguous().to(l.w.device)
 
 
 def pack_deconv3d_tc(l: Conv3dWeights) -> torch.Tensor:
@@ -245,7 +259,7 @@ def pack_deconv3d_tc(l: Conv3dWeights) -> torch.Tensor:
     k=0 from offset 1 (out[2i-1+k] += in[i] w[k]).  Layout [mma][k-chunk 2][N/8][8 n][8 k]."""
     ci, co = l.cin, l.cout
     c8, N = ci // 8, 8 * l.cout
-    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout] folded
+    w = l.w.detach().cpu().to(torch.float64)                       # [27, Cin, Cout] folded
 
     def tap(par, off):
         if par == 0:
@@ -267,7 +281,7 @@ def pack_deconv3d_tc(l: Conv3dWeights) -> torch.Tensor:
             for kc in range(2):
                 c = 2 * q + kc
                 img[j, kc] = blockw[c * 8:(c + 1) * 8].t().reshape(N // 8, 8, 8)
-    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+    return img.to(torch.float16).contiguous().to(l.w.device)
 
 
 def _hi_lo_columns(blk: torch.Tensor) -> torch.Tensor:
@@ -282,7 +296,7 @@ def pack_conv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
     tap-major / channel-chunk minor; an MMA takes two consecutive slabs."""
     ci, co = l.cin, l.cout
     c8, N = ci // 8, 2 * l.cout
-    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout]
+    w = l.w.detach().cpu().to(torch.float64)                       # [27, Cin, Cout]
     slabs = [(0, 0), None] + [(t, 0) for t in range(1, 27)] if c8 == 1 else [(t, c) for t in range(27) for c in range(c8)]
     assert len(slabs) % 2 == 0
     img = torch.zeros(len(slabs) // 2, 2, N // 8, 8, 8, dtype=torch.float64)
@@ -291,7 +305,7 @@ def pack_conv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
             continue
         t, c = sl
         img[s // 2, s % 2] = _hi_lo_columns(w[t, c * 8:(c + 1) * 8, :]).t().reshape(N // 8, 8, 8)
-    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+    return img.to(torch.float16).contiguous().to(l.w.device)
 
 
 def pack_conv3d_roll(l: Conv3dWeights) -> torch.Tensor:
@@ -301,7 +315,7 @@ def pack_conv3d_roll(l: Conv3dWeights) -> torch.Tensor:
     ci, co = l.cin, l.cout
     c8, cw = ci // 8, 2 * l.cout
     npad = (3 * cw + 15) // 16 * 16
-    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout]
+    w = l.w.detach().cpu().to(torch.float64)                       # [27, Cin, Cout]
     slabs = [(0, 0), (1, 0), (2, 0), None] if c8 == 1 else [(kh, c) for kh in range(3) for c in range(c8)]
     mma_kd = len(slabs) // 2
     img = torch.zeros(3 * mma_kd, 2, npad // 8, 8, 8, dtype=torch.float64)
@@ -314,7 +328,7 @@ def pack_conv3d_roll(l: Conv3dWeights) -> torch.Tensor:
             for kw in range(3):
                 full[:, kw * cw:(kw + 1) * cw] = _hi_lo_columns(w[(kd * 3 + kh) * 3 + kw, c * 8:(c + 1) * 8, :])
             img[kd * mma_kd + s // 2, s % 2] = full.t().reshape(npad // 8, 8, 8)
-    return img.to(dtype=torch.float16, device=l.w.device).contiguous()
+    return img.to(torch.float16).contiguous().to(l.w.device)
 
 
 def pack_deconv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
@@ -324,7 +338,7 @@ def pack_deconv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
     Layout per class [tap][chunk pair][k-chunk 2][N/8][8 n][8 k], N = 2*Cout (weights + residual columns)."""
     ci, co = l.cin, l.cout
     c8, N = ci // 8, 2 * l.cout
-    w = l.w.detach().to(torch.float64).cpu()                       # [27, Cin, Cout] folded
+    w = l.w.detach().cpu().to(torch.float64)                       # [27, Cin, Cout] folded
 
     def tap(par, off):
         return 1 if par == 0 else (2 if off == 0 else 0)
@@ -342,7 +356,7 @@ def pack_deconv3d_gtc(l: Conv3dWeights) -> torch.Tensor:
                             c = 2 * q + kc
                             m[kc] = _hi_lo_columns(wt[c * 8:(c + 1) * 8]).t().reshape(N // 8, 8, 8)
                         mmas.append(m)
-    return torch.stack(mmas).to(dtype=torch.float16, device=l.w.device).contiguous()
+    return torch.stack(mmas).to(torch.float16).contiguous().to(l.w.device)
 
 
 @dataclass
@@ -365,12 +379,13 @@ def pack_costreg(sd, prefix, device) -> CostRegWeights:
         layers[n].extra["gtc"] = pack_conv3d_gtc(layers[n])
     for n in ("conv7", "conv9"):
         layers[n].extra["gtc"] = pack_deconv3d_gtc(layers[n])
-    p = sd[prefix + ".prob.weight"].double()                        # [1,8,3,3,3]
-    prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(dtype=torch.float32, device=device).contiguous()
+    p = sd[prefix + ".prob.weight"].detach().cpu().double()                        # [1,8,3,3,3]
+    prob = p.permute(2, 3, 4, 1, 0).reshape(27, p.shape[1]).to(torch.float32).contiguous().to(device)
     cw = CostRegWeights(layers, prob)
     if p.shape[1] == 8:   # tensor-core image of the prob head (8 -> 1)
-        cw.prob_tc = pack_conv3d_tc(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), torch.zeros(1, device=device)))
-        cw.prob_roll = pack_conv3d_roll(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), torch.zeros(1, device=device)))
+        zero = torch.zeros(1).to(device)
+        cw.prob_tc = pack_conv3d_tc(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), zero))
+        cw.prob_roll = pack_conv3d_roll(Conv3dWeights(8, 1, prob.reshape(27, 8, 1), zero))
     return cw
 
 
@@ -380,7 +395,7 @@ def pack_conv2d_gtc(w: torch.Tensor) -> torch.Tensor:
     chunk minor, zero-padded to an even count; an MMA takes two consecutive slabs."""
     taps, ci, co = w.shape
     c8, N = ci // 8, 2 * co
-    w = w.detach().to(torch.float64).cpu()
+    w = w.detach().cpu().to(torch.float64)
     slabs = [(t, c) for t in range(taps) for c in range(c8)]
     if len(slabs) % 2:
         slabs.append(None)
@@ -409,8 +424,8 @@ def pack_feature(sd, device) -> FeatureWeights:
         dyn[n].tc = pack_dynamic_conv_tc(dyn[n])
     fw = FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
                         pack_conv2d(sd, "feature.downsample2.conv.weight", device),
-                        pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16).contiguous(),
-                        pack_conv2d(sd, "feature.inner2.conv.weight", device).reshape(24, 8).contiguous())
+                        pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16),
+                        pack_conv2d(sd, "feature.inner2.conv.weight", device).reshape(24, 8))
     fw.tc = {"downsample1": pack_conv2d_gtc(fw.downsample1).to(device), "downsample2": pack_conv2d_gtc(fw.downsample2).to(device),
              "inner1": pack_conv2d_gtc(fw.inner1.reshape(1, 48, 16)).to(device),
              "inner2": pack_conv2d_gtc(fw.inner2.reshape(1, 24, 8)).to(device)}
@@ -429,21 +444,22 @@ def pack_refinement(sd, prefix, device) -> dict:
     """Folded fp32 weights of the Refinement network (models/module.py:318-335) for csrc/refine.cu: per ConvBnReLU
     (w [Cout][Cin][3][3] * bn scale, bias = bn shift); the transposed conv keeps torch's [Cin][Cout][3][3] with the
     following BatchNorm folded over Cout; res.weight as is."""
+    sd = _host({k: v for k, v in sd.items() if k.startswith(prefix + ".")})
     f32 = dict(dtype=torch.float32, device=device)
     out = {}
     for n in ("conv0", "conv1", "conv2", "conv3"):
         scale, shift = _bn_fold(sd, f"{prefix}.{n}.bn")
         w = sd[f"{prefix}.{n}.conv.weight"].double() * scale.reshape(-1, 1, 1, 1)
-        out[n] = (w.to(**f32).contiguous(), shift.to(**f32).contiguous())
+        out[n] = (w.to(torch.float32).contiguous().to(device), shift.to(torch.float32).contiguous().to(device))
     scale, shift = _bn_fold(sd, f"{prefix}.bn")
     w = sd[f"{prefix}.deconv.weight"].double() * scale.reshape(1, -1, 1, 1)                    # [Cin, Cout, 3, 3]
-    out["deconv"] = (w.to(**f32).contiguous(), shift.to(**f32).contiguous())
-    out["res"] = sd[f"{prefix}.res.weight"].double().reshape(8, 9).to(**f32).contiguous()      # [1, 8, 3, 3]
+    out["deconv"] = (w.to(torch.float32).contiguous().to(device), shift.to(torch.float32).contiguous().to(device))
+    out["res"] = sd[f"{prefix}.res.weight"].double().reshape(8, 9).to(torch.float32).contiguous().to(device)      # [1, 8, 3, 3]
     return out
 
 
 def pack_model(sd, n_stages: int, device, share_cr: bool = False) -> ModelWeights:
-    sd = {k: v.detach() for k, v in sd.items()}
+    sd = _host(sd)
     vis = [pack_visnet(sd, f"stage_net.vis.{s}", device) for s in range(n_stages)]
     if share_cr:
         cr = [pack_costreg(sd, "cost_regularization", device)] * n_stages

@@ -182,6 +182,9 @@ int cds_dynamic_conv(const void* x, int in_mode, const int* img_index, const dou
  * [2,n_images,H,W,Cin] (residual plane second; 16->16 (3,5) layers only); out_lo, if non-NULL, receives the residual
  * plane of out_raw.  cds_conv2d_3x3s2 has the same out_lo. */
 int cds_image_to_nhwc8(const float* img, int n, int H, int W, void* out, cudaStream_t stream);
+/* 8-bit images as the data layer reads them: out[i] = (float)in[i] / 255.f, the IEEE quotient of datasets/general_eval.py:91
+ * (np.float32(img) / 255.) evaluated on the device, so a caller may upload bytes instead of floats.  count elements. */
+int cds_image_u8_to_f32(const unsigned char* in, long long count, float* out, cudaStream_t stream);
 int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act,

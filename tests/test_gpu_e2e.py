@@ -114,16 +114,6 @@ def test_repeatable_and_input_not_mutated(pretrained_sd):
     assert O.rel_l1(a.cpu(), b.cpu()) < 1e-5
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present on this box")
-def test_patch_rebinds_reference_names(pretrained_sd):
-    import sys
-    sys.path.insert(0, "/root/reference")
-    import models.model as rm
-    import models.module as rmod
-    C.patch(rm, rmod)
-    assert rm.homo_warping_3D is C.homo_warping_3D and rmod.DynamicConv is C.DynamicConv
-
-
 def test_depth_map_stream_matches_direct_call(pretrained_sd):
     """DepthMapStream (double-buffered host<->device copies on side streams) returns the same maps as the direct call for
     several different work items in flight (same kernels; the InstanceNorm statistics are accumulated with atomics, so two
