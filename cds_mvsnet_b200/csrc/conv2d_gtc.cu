@@ -27,6 +27,7 @@ constexpr int kSlab = 128 * 16;
 
 struct G2Params {
     const __half* a;          // MODE 0: input [n,Hi,Wi,CA]; MODE 1: half-resolution input [n,H/2,W/2,CA]
+    const __half* a_lo;       // MODE 0, optional: fp16 rounding residual plane of `a` (split-precision storage), same shape
     const double* a_stats;    // [n][CA][2] or null (input used as is)
     const __half* b;          // MODE 1: full-resolution input [n,H,W,CB]
     const double* b_stats;
@@ -41,13 +42,17 @@ struct G2Params {
 
 __device__ __forceinline__ float act_apply(float v, int act) { return act == 1 ? (v > 0.f ? v : 0.1f * v) : v; }
 
-// 8 channels: normalise, activate, round to fp16 (returned) + the fp16 rounding residual (lo)
+// 8 channels: normalise, activate, round to fp16 (returned) + the fp16 rounding residual (lo).  On entry `lo` holds the
+// residual plane of the stored input (zeros when the producer kept one plane only).
 __device__ __forceinline__ uint4 norm8(uint4 raw, const float* nm /* [8][2] mean, rstd */, int act, uint4& lo) {
     __half2* h = reinterpret_cast<__half2*>(&raw);
     __half2* l = reinterpret_cast<__half2*>(&lo);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float2 f = __half22float2(h[j]);
+        const float2 g = __half22float2(l[j]);
+        f.x += g.x;
+        f.y += g.y;
         f.x = act_apply((f.x - nm[4 * j]) * nm[4 * j + 1], act);
         f.y = act_apply((f.y - nm[4 * j + 2]) * nm[4 * j + 3], act);
         h[j] = __floats2half2_rn(f.x, f.y);
@@ -131,7 +136,10 @@ __global__ void __launch_bounds__(128) conv2d_gtc_kernel(const G2Params p) {
     const __half* b_img = MODE == 1 ? p.b + (size_t)n * P * CB : nullptr;
 
     // gather of one tile: the thread's NREAL 16-byte pieces (zeros where the tap falls outside the image / the tile ends)
-    auto gather = [&](int t, uint4 (&raw)[NREAL], bool (&ok)[NREAL]) {
+    constexpr int NLO = MODE == 0 ? NREAL : 1;   // residual-plane pieces (3x3 s2 layers only)
+    const bool has_lo = MODE == 0 && p.a_lo != nullptr;
+    const __half* a_lo_img = has_lo ? p.a_lo + (size_t)n * (size_t)p.Hi * p.Wi * CA : nullptr;
+    auto gather = [&](int t, uint4 (&raw)[NREAL], uint4 (&rlo)[NLO], bool (&ok)[NREAL]) {
         const int m = (blockIdx.x * kTiles + t) * 128 + r;
         const bool live = t < kTiles && m < P;
         const int ox = live ? m % p.Wo : 0, oy = live ? m / p.Wo : 0;
@@ -149,14 +157,15 @@ __global__ void __launch_bounds__(128) conv2d_gtc_kernel(const G2Params p) {
                                  : b_img + (size_t)m * CB + (s - CA / 8) * 8;
             }
             raw[s] = ok[s] ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
+            if (MODE == 0) rlo[s] = (ok[s] && has_lo) ? __ldg(reinterpret_cast<const uint4*>(a_lo_img + (src - a_img))) : make_uint4(0, 0, 0, 0);
         }
     };
     // the NEXT tile's loads are issued before this tile's MMAs / epilogue (when they fit in registers), so that the DRAM
     // round trip is not in every tile's critical path
     constexpr bool PREFETCH = NREAL <= 9;
-    uint4 raw[NREAL];
+    uint4 raw[NREAL], rlo[NLO];
     bool ok[NREAL];
-    gather(0, raw, ok);
+    gather(0, raw, rlo, ok);
 
 #pragma unroll 1
     for (int t = 0; t < kTiles; ++t) {
@@ -166,17 +175,17 @@ __global__ void __launch_bounds__(128) conv2d_gtc_kernel(const G2Params p) {
         const bool live = m < P;
 
         // ---- 1. normalise -> A image --------------------------------------------------------------------------------
-        if (!PREFETCH && t > 0) gather(t, raw, ok);
+        if (!PREFETCH && t > 0) gather(t, raw, rlo, ok);
 #pragma unroll
         for (int s = 0; s < NREAL; ++s) {
             const int c8 = MODE == 0 ? s % C8 : s;
             const int act = (MODE == 1 && c8 >= CA / 8) ? p.b_act : p.a_act;
-            uint4 lo = make_uint4(0, 0, 0, 0);
+            uint4 lo = MODE == 0 ? rlo[s] : make_uint4(0, 0, 0, 0);
             const uint4 v = ok[s] ? norm8(raw[s], s_norm + c8 * 16, act, lo) : make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(sA + s * kSlab + r * 16) = v;
             *reinterpret_cast<uint4*>(sA + (NSLAB + s) * kSlab + r * 16) = lo;
         }
-        if (PREFETCH) gather(t + 1, raw, ok);
+        if (PREFETCH) gather(t + 1, raw, rlo, ok);
         tc::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's operand reads
         tc::tc_fence_before();     // (the previous tile's TMEM loads are ordered before the MMAs below)
         __syncthreads();
@@ -261,14 +270,15 @@ int cds_conv2d_3x3s2_tc_supported(int Cin, int Cout) { return (Cin == 8 && Cout 
 int cds_conv2d_3x3s2_tc_weight_halfs(int Cin, int Cout) { return ((9 * (Cin / 8) + 1) / 2) * (2 * Cout) * 16; }
 
 // in [n,H,W,Cin] fp16 raw (+ stats, activation of its producer) -> out [n,ceil(H/2),ceil(W/2),Cout] fp16 raw + out_stats;
-// out_lo (optional, same shape) receives the fp16 rounding residual of out (split-precision storage)
-int cds_conv2d_3x3s2_tc(const void* in, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin, int Cout, int H,
-                        int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream) {
+// in_lo (optional, shape of in) is the fp16 rounding residual plane of in, out_lo (optional, shape of out) receives that of
+// out (split-precision storage: value + residual = ~22-bit activations)
+int cds_conv2d_3x3s2_tc(const void* in, const void* in_lo, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin,
+                        int Cout, int H, int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream) {
     CDS_REQUIRE(in && wgt_packed && out, CDS_EARG, "cds_conv2d_3x3s2_tc: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), CDS_ESHAPE, "cds_conv2d_3x3s2_tc: bad shape");
     CDS_REQUIRE(cds_conv2d_3x3s2_tc_supported(Cin, Cout), CDS_EUNSUPPORTED, "cds_conv2d_3x3s2_tc: unsupported layer Cin=%d Cout=%d", Cin, Cout);
     G2Params p{};
-    p.a = (const __half*)in; p.a_stats = in_stats; p.a_act = in_act; p.wgt = (const __half*)wgt_packed;
+    p.a = (const __half*)in; p.a_lo = (const __half*)in_lo; p.a_stats = in_stats; p.a_act = in_act; p.wgt = (const __half*)wgt_packed;
     p.out = (__half*)out; p.out_lo = (__half*)out_lo; p.out_stats = out_stats; p.Hi = H; p.Wi = W; p.Ho = (H + 1) / 2; p.Wo = (W + 1) / 2;
     if (Cin == 8) return launch_g2<0, 8, 0, 16>(p, n, stream);
     return launch_g2<0, 16, 0, 32>(p, n, stream);

@@ -328,7 +328,8 @@ template <typename T, int C, int VMAX, int MINB>
 __global__ void __launch_bounds__(256, MINB) aggregate_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                         const float* __restrict__ coef, const float* __restrict__ depth,
                                                         const float* __restrict__ vis, int V, int B, int D, int h, int w,
-                                                        T* __restrict__ volume) {
+                                                        T* __restrict__ volume, __half* __restrict__ vol_hi,
+                                                        __half* __restrict__ vol_lo) {
     constexpr int LPP = C / 8;
     constexpr int OWN = (VMAX + LPP - 1) / LPP;   // views whose projection this lane may own (V <= VMAX)
     // 32-bit indexing: blockIdx.y = batch item, blockIdx.x tiles its pixels (see entropy_kernel)
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(256, MINB) aggregate_kernel(const T* __restric
     }
     const float* dp = depth + (size_t)b * D * P + pofs;
     // channel-blocked volume [B][C/8][D][h][w][8]: one 8-channel slab of a row is contiguous (what conv0's TMA wants)
-    T* outp = volume + (((size_t)b * LPP + chunk) * D * P + pofs) * 8;
+    const size_t oofs = (((size_t)b * LPP + chunk) * D * P + pofs) * 8;
+    T* outp = volume ? volume + oofs : nullptr;
     const T* rbase = ref_fea + ((size_t)b * P + pofs) * C + chunk * 8;
     const T* sbase = src_fea + chunk * 8;
     const size_t vstride = (size_t)B * P * C;
@@ -430,7 +432,18 @@ __global__ void __launch_bounds__(256, MINB) aggregate_kernel(const T* __restric
         float o[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { o[2 * i] = acc[i].x; o[2 * i + 1] = acc[i].y; }
-        if (live) Vec8<T>::store(outp + (size_t)d * P * 8, o);
+        if (live) {
+            if (outp) Vec8<T>::store(outp + (size_t)d * P * 8, o);
+            if (vol_hi) {   // split-precision fp16 volume: value plane + rounding-residual plane (what conv0's tensor cores read)
+                Vec8<__half>::store(vol_hi + oofs + (size_t)d * P * 8, o);
+                if (vol_lo) {
+                    float res[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) res[i] = o[i] - __half2float(__float2half_rn(o[i]));
+                    Vec8<__half>::store(vol_lo + oofs + (size_t)d * P * 8, res);
+                }
+            }
+        }
     }
 }
 
@@ -582,7 +595,8 @@ int launch_entropy(const void* ref, const void* src, const float* coef, const fl
 
 template <typename T>
 int launch_aggregate(const void* ref, const void* src, const float* coef, const float* depth, const float* vis, int V,
-                     int B, int C, int D, int h, int w, void* volume, cudaStream_t st) {
+                     int B, int C, int D, int h, int w, void* volume, cudaStream_t st, __half* vol_hi = nullptr,
+                     __half* vol_lo = nullptr) {
     dim3 blocks(cds_div_up((long long)h * w * (C / 8), 256), B);
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
@@ -608,9 +622,9 @@ int launch_aggregate(const void* ref, const void* src, const float* coef, const 
         }
     }
 #define CDS_AGG(c)                                                                                                 \
-    if (V <= 4 && occ == 2) aggregate_kernel<T, c, 4, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o); \
-    else if (V <= 4) aggregate_kernel<T, c, 4, 3><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);   \
-    else aggregate_kernel<T, c, kMaxViews, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o);    \
+    if (V <= 4 && occ == 2) aggregate_kernel<T, c, 4, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo); \
+    else if (V <= 4) aggregate_kernel<T, c, 4, 3><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo);   \
+    else aggregate_kernel<T, c, kMaxViews, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo);    \
     break;
     switch (C) {
         case 8: CDS_AGG(8)
@@ -650,6 +664,17 @@ int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float*
     if (dtype == CDS_F32) return launch_aggregate<float>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     cds_set_error("cds_costvol_aggregate: unknown dtype %d", dtype);
     return CDS_EARG;
+}
+
+// fp32 features in, split-precision fp16 volume out (value plane + optional rounding-residual plane)
+int cds_costvol_aggregate_split(const float* ref_fea, const float* src_fea, const float* coef, const float* depth, const float* vis,
+                                int V, int B, int C, int D, int h, int w, void* vol_hi, void* vol_lo, cudaStream_t stream) {
+    CDS_REQUIRE(ref_fea && src_fea && coef && depth && vis && vol_hi, CDS_EARG, "cds_costvol_aggregate_split: null pointer");
+    CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
+                "cds_costvol_aggregate_split: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B * h * w < (1ll << 31) && B <= 65535, CDS_ESHAPE,
+                "cds_costvol_aggregate_split: feature map too large for 32-bit offsets");
+    return launch_aggregate<float>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, nullptr, stream, (__half*)vol_hi, (__half*)vol_lo);
 }
 
 int cds_nc_mean(const float* ref_nc_sum, const float* src_nc_sum, int V, long long n, float* out, cudaStream_t stream) {

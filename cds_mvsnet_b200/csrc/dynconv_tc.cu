@@ -53,10 +53,10 @@ struct Cfg {
     static constexpr int HALO = (KMAX - 1) / 2;
     static constexpr int TXO = TX - 2 * HALO;    // valid outputs per row unit
     // per branch: COUT feature columns, (a,b,c) from fp16-rounded curvature weights, (a,b,c) from their residuals
-    // two-branch layers (everything but conv00 / conv01) also carry the fp16 rounding RESIDUAL of the feature weights in
-    // COUT extra columns per branch, summed in the epilogue: the depth error of the fp16 path is dominated by operand
-    // rounding in these cheap layers, and they are not MMA-bound
-    static constexpr bool WLO = K2_ == 0;
+    // Every layer also carries the fp16 rounding RESIDUAL of the feature weights in COUT extra columns per branch, summed in
+    // the epilogue (effectively fp32-accurate weights): on the chaotic "noise" input the stage-1 depth amplifies every
+    // rounding of the trunk ~9x into the final depth, so no trunk layer can afford fp16 weights
+    static constexpr bool WLO = true;
     static constexpr int FCOLS = (WLO ? 2 : 1) * COUT_;         // feature columns per branch; curvature columns follow
     static constexpr int NPAD = (FCOLS + 6 + 15) / 16 * 16;
     // Branches are embedded in the KMAX x KMAX tap grid.  The tensor core re-reads the 4 KB A operand from shared
@@ -161,7 +161,7 @@ __device__ __forceinline__ void issue_unit(uint32_t a_base, uint32_t b_base, uin
 // runs the MMAs of a reference tile ONCE and its epilogue up to GRP times, once per pair: 5 instead of 8 images' worth of
 // tensor work at N = 5.
 template <class C, int TY, bool SPLIT, int GRP = 1>
-__global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 2 : (C::KMAX == 3 ? CDS_K13_CTAS : (C::NK == 3 && C::KMAX == 7 ? CDS_K357_CTAS : 3))) : 2))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
+__global__ void __launch_bounds__(192, (GRP > 1 ? 1 : (C::COUT <= 16 ? (SPLIT ? 2 : (C::KMAX == 3 ? CDS_K13_CTAS : (C::NK == 3 && C::KMAX == 7 ? 2 : 3))) : (SPLIT ? 1 : 2)))) dynconv_tc_kernel(const __grid_constant__ CUtensorMap tmap, DynTcParams p) {
     static_assert(GRP == 1 || (C::COUT == 8 && !SPLIT), "shared-image groups are implemented for the 8-channel image layer");
     constexpr int NK = C::NK, HALO = C::HALO, TXO = C::TXO, C8 = C::C8, CIN = C::CIN, COUT = C::COUT, NPAD = C::NPAD;
     constexpr int ROWS = TY + 2 * HALO;
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 
         tc::mbar_expect_tx(bar_load, A_BYTES + B_BYTES);
         if (C8 == 1) {
             tc::tma_load_4d(sA_u, &tmap, bar_load, 2 * (x0 - HALO), y0 - HALO, img, 0);
+            if constexpr (SPLIT) tc::tma_load_4d(sA_u + CHUNK, &tmap, bar_load, 2 * (x0 - HALO), y0 - HALO, img + (int)p.in_lo_images, 0);
         } else {
 #pragma unroll
             for (int c8 = 0; c8 < C8; ++c8) tc::tma_load_5d(sA_u + c8 * CHUNK, &tmap, bar_load, 0, c8, x0 - HALO, y0 - HALO, img);
@@ -331,11 +332,12 @@ __global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 
             tc::mbar_wait(bar_full + s, (u / (int)NSTG) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * STAGE_COLS;
-            uint32_t ar[NK][8], yr[NK][8];
+            uint32_t ar[NK][8], yr[NK][8], yl[NK][8];
 #pragma unroll
             for (int b = 0; b < NK; ++b) {
                 tc::tmem_ld8_nowait(taddr + b * NPAD + C::FCOLS, ar[b]);
                 tc::tmem_ld8_nowait(taddr + b * NPAD, yr[b]);
+                tc::tmem_ld8_nowait(taddr + b * NPAD + COUT, yl[b]);   // product with the weights' fp16 rounding residual
             }
             tc::tmem_ld_wait();
             tc::tc_fence_before();
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 
                 cb[b] = __uint_as_float(ar[b][1]) + __uint_as_float(ar[b][4]);
                 cc[b] = __uint_as_float(ar[b][2]) + __uint_as_float(ar[b][5]);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) yb[b][c] = __uint_as_float(yr[b][c]) + s_bias[b * COUT + c];
+                for (int c = 0; c < 8; ++c) yb[b][c] = (__uint_as_float(yr[b][c]) + __uint_as_float(yl[b][c])) + s_bias[b * COUT + c];
             }
 #pragma unroll
             for (int it = 0; it < GRP; ++it) {
@@ -395,6 +397,12 @@ __global__ void __launch_bounds__(192, (GRP > 1 ? 2 : (C::COUT <= 16 ? (SPLIT ? 
                     if (valid) {
                         const size_t m = ((size_t)(n + it * nstr) * p.H + gy) * p.W + gx;
                         Vec8<__half>::store(p.out_raw + m * COUT, out);
+                        if (p.out_lo) {   // split-precision storage: what fp16 rounding just dropped
+                            float res[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) res[c] = out[c] - __half2float(__float2half_rn(out[c]));
+                            Vec8<__half>::store(p.out_lo + m * COUT, res);
+                        }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) { st_sum[it][c] += out[c]; st_sq[it][c] += out[c] * out[c]; }
                         if (p.norm_curv) p.norm_curv[m] = nc;
@@ -600,7 +608,6 @@ int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cuda
     constexpr size_t smem = (size_t)(SPLIT ? 2 : 1) * C::C8 * (TY + 2 * C::HALO) * ROW_BYTES + (size_t)C::B_BYTES + 8 * 6 +
                             (2 * C::CIN + GRP * 8 * C::COUT + 28 + C::NK * C::COUT) * 4 + 16;
     static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
-    static_assert(!SPLIT || C::C8 > 1, "split-precision input is implemented for the multi-chunk layers");
     auto kern = dynconv_tc_kernel<C, TY, SPLIT, GRP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cds_set_error("cds_dynamic_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -608,8 +615,8 @@ int launch_dyn_tc(const void* x, int n_images, const DynTcParams& p, int n, cuda
     const uint64_t H = p.H, W = p.W, NI = n_images;
     bool ok;
     if (C::C8 == 1) {   // 16-byte pixels: 8-byte elements so that a box row is 2 KB (128 pixels)
-        const uint64_t dims[4] = {2 * W, H, NI, 1};
-        const uint64_t strides[4] = {0, W * 16, H * W * 16, NI * H * W * 16};
+        const uint64_t dims[4] = {2 * W, H, (SPLIT ? 2 : 1) * NI, 1};   // SPLIT: the residual plane follows
+        const uint64_t strides[4] = {0, W * 16, H * W * 16, (SPLIT ? 2 : 1) * NI * H * W * 16};
         const uint32_t box[4] = {2 * TX, (uint32_t)(TY + 2 * C::HALO), 1, 1};
         ok = tma::make_u64(&tmap, x, 4, dims, strides, box);
     } else {            // (8 ch, chunk, W, H, image): one box per 8-channel chunk lands as a slab
@@ -657,7 +664,7 @@ int cds_dynamic_conv_tc_supported(int Cin, int Cout, int H, int W, int num_kerne
 }
 
 int cds_dynamic_conv_tc_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks) {
-    int kmax = 0, kin = 0, c8 = Cin / 8, npad = ((num_kernels == 2 ? 2 : 1) * Cout + 6 + 15) / 16 * 16;
+    int kmax = 0, kin = 0, c8 = Cin / 8, npad = (2 * Cout + 6 + 15) / 16 * 16;
     for (int i = 0; i < num_kernels; ++i) kmax = ks[i] > kmax ? ks[i] : kmax;
     for (int i = 0; i < num_kernels; ++i) if (ks[i] < kmax && ks[i] > kin) kin = ks[i];
     int nin = kin * kin, nring = kmax * kmax - nin;
@@ -686,11 +693,11 @@ int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const
 // a batch item to one image.  Same results as cds_dynamic_conv_tc; the reference image's convolutions run once per batch item.
 int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index, const float* epipole, float epi_scale,
                               const void* wgt_packed, const float* bias, const float* gate, int V, int B, int Cin, int Cout, int H, int W,
-                              int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, double* out_stats,
+                              int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, void* out_lo, double* out_stats,
                               float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream) {
     CDS_REQUIRE(V >= 1 && B >= 1 && img_index, CDS_EARG, "cds_dynamic_conv_tc_pairs: bad pair batch");
     return dynamic_conv_tc_impl(x, n_images, img_index, nullptr, 0, epipole, epi_scale, wgt_packed, bias, gate, 2 * V * B, Cin, Cout, H, W,
-                                num_kernels, kernel_sizes, temperature, 0, out_raw, nullptr, out_stats, norm_curv, nc_sq, nc_mode, nc_abs,
+                                num_kernels, kernel_sizes, temperature, 0, out_raw, out_lo, out_stats, norm_curv, nc_sq, nc_mode, nc_abs,
                                 V, B, stream);
 }
 
@@ -719,9 +726,12 @@ static int dynamic_conv_tc_impl(const void* x, int n_images, const int* img_inde
         return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 16, false, 4>(x, n_images, p, n, stream);
     }
     if (split_in) {
-        CDS_REQUIRE(lid == 4 && in_stats, CDS_EUNSUPPORTED,
-                    "cds_dynamic_conv_tc: split-precision input is implemented for the 16->16 (3,5) layers with input statistics");
-        return launch_dyn_tc<Cfg<3, 5, 0, 16, 16>, 4, true>(x, n_images, p, n, stream);
+        CDS_REQUIRE((lid == 2 || lid == 4 || lid == 6) && in_stats, CDS_EUNSUPPORTED,
+                    "cds_dynamic_conv_tc: split-precision input is implemented for the trunk layers 8->8 (3,5,7), 16->16 (3,5) and "
+                    "32->32 (1,3), with input statistics");
+        if (lid == 2) return launch_dyn_tc<Cfg<3, 5, 7, 8, 8>, 8, true>(x, n_images, p, n, stream);
+        if (lid == 4) return launch_dyn_tc<Cfg<3, 5, 0, 16, 16>, 4, true>(x, n_images, p, n, stream);
+        return launch_dyn_tc<Cfg<1, 3, 0, 32, 32>, 4, true>(x, n_images, p, n, stream);
     }
     switch (lid) {
         case 1: return launch_dyn_tc<Cfg<3, 7, 11, 8, 8>, 8>(x, n_images, p, n, stream);

@@ -597,6 +597,34 @@ __global__ void __launch_bounds__(256) instnorm_act_kernel(const T* __restrict__
     }
 }
 
+// the same from fp16 value + residual planes to fp32 (nothing is rounded on the way)
+__global__ void __launch_bounds__(256) instnorm_act_split_kernel(const __half* __restrict__ raw, const __half* __restrict__ raw_lo,
+                                                                 const double* __restrict__ stats, int act, int C, long long HW,
+                                                                 float* __restrict__ out) {
+    extern __shared__ float s_norm[];  // [C][2]
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) norm_coeffs(stats, n, C, c, (double)HW, s_norm[2 * c], s_norm[2 * c + 1]);
+    __syncthreads();
+    const int C8 = C / 8;
+    long long total = HW * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c8 = (int)(i % C8);
+        float v[8], l[8];
+        Vec8<__half>::load(raw + (size_t)n * HW * C + i * 8, v);
+        if (raw_lo) {
+            Vec8<__half>::load(raw_lo + (size_t)n * HW * C + i * 8, l);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += l[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int c = c8 * 8 + j;
+            v[j] = apply_act((v[j] - s_norm[2 * c]) * s_norm[2 * c + 1], act);
+        }
+        Vec8<float>::store(out + (size_t)n * HW * C + i * 8, v);
+    }
+}
+
 // ---- layout converters at the drop-in boundary (fp32 NCHW <-> channels-last storage type) ----
 __global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, long long n4, float4* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -750,6 +778,16 @@ int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C
         instnorm_act_kernel<float><<<grid, 256, C * 2 * sizeof(float), stream>>>((const float*)raw, stats, act, C, HW, (float*)out);
     else { cds_set_error("cds_instnorm_act: unknown dtype %d", dtype); return CDS_EARG; }
     return cds_check_launch("cds_instnorm_act");
+}
+
+int cds_instnorm_act_split_f32(const void* raw, const void* raw_lo, const double* stats, int act, int n, int C, int H, int W,
+                               float* out, cudaStream_t stream) {
+    CDS_REQUIRE(raw && stats && out, CDS_EARG, "cds_instnorm_act_split_f32: null pointer");
+    CDS_REQUIRE(n > 0 && n <= 65535 && C % 8 == 0 && C > 0, CDS_ESHAPE, "cds_instnorm_act_split_f32: bad shape");
+    long long HW = (long long)H * W;
+    dim3 grid((unsigned)std::min<long long>(148 * 8, (HW * (C / 8) + 255) / 256), n);
+    instnorm_act_split_kernel<<<grid, 256, C * 2 * sizeof(float), stream>>>((const __half*)raw, (const __half*)raw_lo, stats, act, C, HW, out);
+    return cds_check_launch("cds_instnorm_act_split_f32");
 }
 
 int cds_image_u8_to_f32(const unsigned char* in, long long count, float* out, cudaStream_t stream) {

@@ -97,7 +97,7 @@ class FeatureExtractor:
             if in_mode == 1 and self.pairs is not None and self.share_ref and not split_in:
                 V, B = self.pairs   # the reference image's convolutions are shared by its V pairs
                 call("cds_dynamic_conv_tc_pairs", ptr(x), n_images, ptr(img_index), ptr(epi), float(epi_scale), ptr(w.tc), ptr(w.bias),
-                     ptr(w.gate), V, B, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T), ptr(out), ptr(out_stats),
+                     ptr(w.gate), V, B, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T), ptr(out), ptr(out_lo), ptr(out_stats),
                      ptr(norm_curv), ptr(nc_sq), nc_mode, ptr(nc_abs))
                 return
             call("cds_dynamic_conv_tc", ptr(x), n_images, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
@@ -111,16 +111,17 @@ class FeatureExtractor:
              _ksizes(w.ksizes), float(T), self.dt, ptr(out), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode,
              ptr(nc_abs))
 
-    def _down(self, name, x, x_stats, w32, n, cin, cout, H, W, out, out_stats, split):
-        """3x3 stride-2 conv of FeatureNet.downsample1/2 (out: [1 or 2 planes, n, H/2, W/2, cout])."""
+    def _down(self, name, x, x_stats, w32, n, cin, cout, H, W, out, out_stats, split, x_lo=None):
+        """3x3 stride-2 conv of FeatureNet.downsample1/2 (out: [1 or 2 planes, n, H/2, W/2, cout]; x_lo: residual plane of x)."""
         e = _esize(self.storage)
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
         _lib.set_tag("feat." + name, (2.0 * 9 * cin * cout * n * Ho * Wo, float(n * (H * W * cin + Ho * Wo * cout) * e)))
         if (self.use_tc2d and self.storage == torch.float16 and name in self.fw.tc
                 and _lib.LIB.load().cds_conv2d_3x3s2_tc_supported(cin, cout)):
-            call("cds_conv2d_3x3s2_tc", ptr(x), ptr(x_stats), ACT_LRELU, ptr(self.fw.tc[name]), n, cin, cout, H, W, ptr(out[0]),
+            call("cds_conv2d_3x3s2_tc", ptr(x), ptr(x_lo), ptr(x_stats), ACT_LRELU, ptr(self.fw.tc[name]), n, cin, cout, H, W, ptr(out[0]),
                  ptr(out[1]) if split else None, ptr(out_stats))
             return
+        assert x_lo is None, "split-precision activations exist on the tensor-core path only"
         call("cds_conv2d_3x3s2", ptr(x), ptr(x_stats), ACT_LRELU, ptr(w32), n, cin, cout, H, W, self.dt, ptr(out[0]),
              ptr(out[1]) if split else None, ptr(out_stats))
 
@@ -136,10 +137,17 @@ class FeatureExtractor:
         call("cds_conv2d_1x1_cat", ptr(a), ptr(a_stats), a_act, ptr(b), ptr(b_stats), ACT_LRELU, ptr(w32), n, ca, cb, cout, H, W,
              self.dt, ptr(out), ptr(out_stats))
 
-    def _split_ok(self, H2, W2):
-        w = self.fw.dyn["conv10"]
-        return bool(self.use_tc and self.split_precision and w.tc is not None and self.storage == torch.float16
-                    and _lib.LIB.load().cds_dynamic_conv_tc_supported(16, 16, H2, W2, 2, _ksizes(w.ksizes)))
+    def _split_ok(self, H, W):
+        """The precise trunk (split-precision storage + operands in every layer between the image and the stage-1 feature) needs
+        the tensor-core kernels of all of them."""
+        if not (self.use_tc and self.use_tc2d and self.split_precision and self.storage == torch.float16):
+            return False
+        lib = _lib.LIB.load()
+        for name, (h, w) in (("conv01", (H, W)), ("conv10", (H // 2, W // 2)), ("conv20", (H // 4, W // 4))):
+            d = self.fw.dyn[name]
+            if d.tc is None or not lib.cds_dynamic_conv_tc_supported(max(8, d.cin), d.cout, h, w, len(d.ksizes), _ksizes(d.ksizes)):
+                return False
+        return True
 
     def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature, pairs=None, after_stage1=None):
         """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
@@ -161,19 +169,23 @@ class FeatureExtractor:
             return sviews[i]
 
         f32 = torch.float32
-        raw00 = buf.get("f.raw00", (n, H, W, 8), st)
-        raw01 = buf.get("f.raw01", (n, H, W, 8), st)
-        # conv10 / conv11 are the layers the depth output is most sensitive to: on the tensor-core path
-        # their inputs are kept as two fp16 planes (value + rounding residual) and fed as twice as many K slabs
-        split = self._split_ok(H2, W2)
-        rawd1 = buf.get("f.rawd1", (2 if split else 1, n, H2, W2, 16), st)
-        raw10 = buf.get("f.raw10", (2 if split else 1, n, H2, W2, 16), st)
-        raw11 = buf.get("f.raw11", (n, H2, W2, 16), st)
-        rawd2 = buf.get("f.rawd2", (n, H4, W4, 32), st)
-        raw20 = buf.get("f.raw20", (n, H4, W4, 32), st)
-        raw21 = buf.get("f.raw21", (n, H4, W4, 32), st)
-        rawo1 = buf.get("f.rawo1", (n, H4, W4, 32), st)
-        fea1 = buf.get("f.fea1", (n, H4, W4, 32), st)
+        # Precise trunk: every activation between the image and the stage-1 feature is kept as two fp16 planes (value + rounding
+        # residual = ~22 bits) and fed to the tensor cores as twice as many K slabs, and every weight carries its residual in
+        # extra N columns.  The stage-1 depth of the chaotic "noise" input amplifies each rounding of this chain ~9x into the
+        # final depth; the heads of stages 2 / 3 (inner1/2, out2/3) are not on it and stay single-plane.
+        split = self._split_ok(H, W)
+        P2 = 2 if split else 1
+        lo = lambda t: t[1] if split else None
+        raw00 = buf.get("f.raw00", (P2, n, H, W, 8), st)
+        raw01 = buf.get("f.raw01", (P2, n, H, W, 8), st)
+        rawd1 = buf.get("f.rawd1", (P2, n, H2, W2, 16), st)
+        raw10 = buf.get("f.raw10", (P2, n, H2, W2, 16), st)
+        raw11 = buf.get("f.raw11", (P2, n, H2, W2, 16), st)
+        rawd2 = buf.get("f.rawd2", (P2, n, H4, W4, 32), st)
+        raw20 = buf.get("f.raw20", (P2, n, H4, W4, 32), st)
+        raw21 = buf.get("f.raw21", (P2, n, H4, W4, 32), st)
+        rawo1 = buf.get("f.rawo1", (P2, n, H4, W4, 32), st)
+        fea1 = buf.get("f.fea1", (n, H4, W4, 32), f32 if split else st)   # precise: fp32 stage-1 feature
         rawi1 = buf.get("f.rawi1", (n, H2, W2, 16), st)
         rawo2 = buf.get("f.rawo2", (n, H2, W2, 16), st)
         fea2 = buf.get("f.fea2", (n, H2, W2, 16), st)
@@ -185,29 +197,38 @@ class FeatureExtractor:
         T = temperature
         fw = self.fw
         # full resolution
-        self._dyn("conv00", imgs, 1, img_index, None, ACT_NONE, epipoles, 1.0, n, H, W, T, raw00, sv(0, 8), ncsq[2], 0, None)
-        self._dyn("conv01", raw00, 0, None, sv(0, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, raw01, sv(1, 8), ncsq[2], 1, None)
+        self._dyn("conv00", imgs, 1, img_index, None, ACT_NONE, epipoles, 1.0, n, H, W, T, raw00[0], sv(0, 8), ncsq[2], 0, None,
+                  out_lo=lo(raw00))
+        self._dyn("conv01", raw00, 0, None, sv(0, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, raw01[0], sv(1, 8), ncsq[2], 1, None,
+                  split_in=split, out_lo=lo(raw01))
         # 1/2 resolution
-        self._down("downsample1", raw01, sv(1, 8), fw.downsample1, n, 8, 16, H, W, rawd1, sv(2, 16), split)
+        self._down("downsample1", raw01[0], sv(1, 8), fw.downsample1, n, 8, 16, H, W, rawd1, sv(2, 16), split, x_lo=lo(raw01))
         self._dyn("conv10", rawd1, 0, None, sv(2, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw10[0], sv(3, 16), ncsq[1], 0, None,
-                  split_in=split, out_lo=raw10[1] if split else None)
-        self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11, sv(4, 16), ncsq[1], 1, None,
-                  split_in=split)
+                  split_in=split, out_lo=lo(raw10))
+        self._dyn("conv11", raw10, 0, None, sv(3, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, raw11[0], sv(4, 16), ncsq[1], 1, None,
+                  split_in=split, out_lo=lo(raw11))
         # 1/4 resolution
-        self._down("downsample2", raw11, sv(4, 16), fw.downsample2, n, 16, 32, H2, W2, rawd2.unsqueeze(0), sv(5, 32), False)
-        self._dyn("conv20", rawd2, 0, None, sv(5, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw20, sv(6, 32), ncsq[0], 0, None)
-        self._dyn("conv21", raw20, 0, None, sv(6, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw21, sv(7, 32), ncsq[0], 1, None)
+        self._down("downsample2", raw11[0], sv(4, 16), fw.downsample2, n, 16, 32, H2, W2, rawd2, sv(5, 32), split, x_lo=lo(raw11))
+        self._dyn("conv20", rawd2, 0, None, sv(5, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw20[0], sv(6, 32), ncsq[0], 0, None,
+                  split_in=split, out_lo=lo(raw20))
+        self._dyn("conv21", raw20, 0, None, sv(6, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, raw21[0], sv(7, 32), ncsq[0], 1, None,
+                  split_in=split, out_lo=lo(raw21))
         # stage-1 output
-        self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1, sv(8, 32), ncsq[0], 2, ncab[0])
-        kcall("feat.act1", 0, 2 * n * H4 * W4 * 32 * e, "cds_instnorm_act", ptr(rawo1), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
+        self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1[0], sv(8, 32), ncsq[0], 2, ncab[0],
+                  split_in=split, out_lo=lo(rawo1))
+        if split:
+            kcall("feat.act1", 0, n * H4 * W4 * 32 * (2 * e + 4), "cds_instnorm_act_split_f32", ptr(rawo1[0]), ptr(rawo1[1]), ptr(sv(8, 32)),
+                  ACT_TANH, n, 32, H4, W4, ptr(fea1))
+        else:
+            kcall("feat.act1", 0, 2 * n * H4 * W4 * 32 * e, "cds_instnorm_act", ptr(rawo1[0]), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
         if after_stage1 is not None:   # the stage-1 feature is complete: the caller may start stage 1 on another stream
             after_stage1((fea1, ncsq[0], ncab[0]))
         # stage-2 output: inner1 over cat(up2(conv21), conv11)
-        self._inner("inner1", raw21, sv(7, 32), ACT_LRELU, raw11, sv(4, 16), fw.inner1, n, 32, 16, 16, H2, W2, rawi1, sv(9, 16))
+        self._inner("inner1", raw21[0], sv(7, 32), ACT_LRELU, raw11[0], sv(4, 16), fw.inner1, n, 32, 16, 16, H2, W2, rawi1, sv(9, 16))
         self._dyn("out2", rawi1, 0, None, sv(9, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, rawo2, sv(10, 16), ncsq[1], 2, ncab[1])
         kcall("feat.act2", 0, 2 * n * H2 * W2 * 16 * e, "cds_instnorm_act", ptr(rawo2), ptr(sv(10, 16)), ACT_TANH, n, 16, H2, W2, dt, ptr(fea2))
         # stage-3 output: inner2 over cat(up2(stage-2 feature), conv01)
-        self._inner("inner2", fea2, None, ACT_NONE, raw01, sv(1, 8), fw.inner2, n, 16, 8, 8, H, W, rawi2, sv(11, 8))
+        self._inner("inner2", fea2, None, ACT_NONE, raw01[0], sv(1, 8), fw.inner2, n, 16, 8, 8, H, W, rawi2, sv(11, 8))
         self._dyn("out3", rawi2, 0, None, sv(11, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, rawo3, sv(12, 8), ncsq[2], 2, ncab[2])
         kcall("feat.act3", 0, 2 * n * H * W * 8 * e, "cds_instnorm_act", ptr(rawo3), ptr(sv(12, 8)), ACT_TANH, n, 8, H, W, dt, ptr(fea3))
         return {0: (fea1, ncsq[0], ncab[0]), 1: (fea2, ncsq[1], ncab[1]), 2: (fea3, ncsq[2], ncab[2])}
@@ -395,9 +416,13 @@ class CascadeEngine:
         kcall(f"s{s}.hypotheses", 0, 4 * D * P + 4 * B * hp * wp, "cds_depth_hypotheses", ptr(depth_values), depth_values.shape[1],
               ptr(prev_depth), hp, wp, B, D, self.ratios[s], H, W, scale, ptr(samples))
         ref_fea, src_fea = fea[:VB], fea[VB:]
+        # precise stage 1: its feature arrives in fp32 (FeatureExtractor.run) and both plane sweeps run their fp32-feature forms;
+        # the volume goes to the regulariser as fp16 value (+ residual) planes
+        fea_f32 = fea.dtype == torch.float32 and self.storage == torch.float16
+        fdt, fe = (_lib.CDS_F32, 4) if fea_f32 else (self.dt, e)
         entropy = buf.get(f"s{s}.entropy", (V, B, h, w), f32)
-        kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P, "cds_costvol_entropy",
-              ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, self.dt, ptr(entropy))
+        kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * fe + 4) + 4 * D * P, "cds_costvol_entropy",
+              ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, fdt, ptr(entropy))
         vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
         if (self.use_tc and self.w.vis_tc and self.storage == torch.float16 and _lib.LIB.load().cds_visnet_tc_supported(h, w)):
             wgt, fp = self.w.vis_tc[s]
@@ -407,9 +432,14 @@ class CascadeEngine:
             kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet", ptr(entropy), ptr(ncabs[:VB]), ptr(self.w.vis[s]),
                   VB, h, w, ptr(vis))
         volume = buf.get(f"s{s}.volume", (B, C // 8, D, h, w, 8), self.storage)
-        kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P + C * D * P * e,
-              "cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
-              ptr(volume))
+        if fea_f32:
+            kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * fe + 4) + 4 * D * P + C * D * P * e,
+                  "cds_costvol_aggregate_split", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w,
+                  ptr(volume), None)
+        else:
+            kcall(f"s{s}.costvol_aggregate", 2.0 * 10 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P + C * D * P * e,
+                  "cds_costvol_aggregate", ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), ptr(vis), V, B, C, D, h, w, self.dt,
+                  ptr(volume))
         nc = self._out_views[s][2]
         kcall(f"s{s}.nc_mean", 0, 4 * P * (2 * V + 1), "cds_nc_mean", ptr(ncsq[:VB]), ptr(ncsq[VB:]), V, B * h * w, ptr(nc))
         logits = self.regs[s].run(buf, f"s{s}.cr", volume, B, D, h, w)

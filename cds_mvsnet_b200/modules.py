@@ -165,7 +165,12 @@ class _CachedModule(nn.Module):
     ``load_state_dict`` / ``.to()`` / ``.train()`` of THIS module drop the cache at once; everything else that can change a
     weight -- ``model.feature.load_state_dict(...)`` on a submodule, ``p.data.copy_()``, an optimizer step, an EMA swap -- is
     caught by a fingerprint checked at every forward: the (storage address, in-place version counter) of every parameter and
-    buffer below this module."""
+    buffer below this module.  The one thing the fingerprint cannot see is a write through ``p.data`` (it bypasses autograd's
+    version counter): call ``invalidate_cache()`` after such an edit."""
+
+    def invalidate_cache(self):
+        """Drop the derived weights (folded BatchNorm, operand images, CUDA graph); they are rebuilt by the next forward."""
+        self._invalidate()
 
     def _invalidate(self):
         object.__setattr__(self, "_cache", None)

@@ -85,8 +85,8 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     """fp16 B-operand image for csrc/dynconv_tc.cu (Cin 3 is zero-padded to 8).
 
     Every branch is embedded in the kmax x kmax tap grid.  Branch b owns N columns [b*NPAD, (b+1)*NPAD) with
-    NPAD = roundup16(F + 6): F feature columns (Cout; for the two-branch layers 2*Cout = fp16-rounded weights followed by
-    their rounding residuals), then (a, b, c) rounded to fp16, then the rounding residuals of (a, b, c).
+    NPAD = roundup16(F + 6): F = 2*Cout feature columns (fp16-rounded weights followed by their rounding residuals), then
+    (a, b, c) rounded to fp16, then the rounding residuals of (a, b, c).
     K = 16 per MMA = two 8-channel slabs: for Cin <= 8 two consecutive taps ([tap0, zero pad], [tap1, tap2], ...), for
     Cin > 8 two channel chunks of one tap.  First the MMAs of the inner taps (support of the second-largest kernel;
     all branches, N = K*NPAD), then those of the outer ring (largest kernel only, N = NPAD); per MMA
@@ -95,7 +95,7 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     c8 = max(1, cin // 8)
     att, conv = w.w_att.detach().cpu().double(), w.w_conv.detach().cpu().double()
     K, kmax = len(w.ksizes), max(w.ksizes)
-    wlo = K == 2                                  # two-branch layers also carry the feature weights' fp16 residual
+    wlo = True                                    # every layer carries the feature weights' fp16 rounding residual
     fcols = (2 if wlo else 1) * cout               # feature columns per branch; the curvature columns follow
     npad = (fcols + 6 + 15) // 16 * 16
     ntap = kmax * kmax

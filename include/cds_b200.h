@@ -85,6 +85,10 @@ int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float*
                           const float* vis, int V, int B, int C, int D, int h, int w, int dtype, void* volume,
                           cudaStream_t stream);
 /* out[i] = sum_v (ref_nc_sum[v,i] + src_nc_sum[v,i]) / 2 / V   (models/model.py:60,79) */
+/* cds_costvol_aggregate from fp32 features to a split-precision fp16 volume: vol_hi = fp16 value plane, vol_lo (optional) = its
+ * fp16 rounding residual plane, both [B,C/8,D,h,w,8] (stage 1 of the cascade, whose rounding the later stages amplify). */
+int cds_costvol_aggregate_split(const float* ref_fea, const float* src_fea, const float* coef, const float* depth, const float* vis,
+                                int V, int B, int C, int D, int h, int w, void* vol_hi, void* vol_lo, cudaStream_t stream);
 int cds_nc_mean(const float* ref_nc_sum, const float* src_nc_sum, int V, long long n, float* out, cudaStream_t stream);
 
 /* ---- A3: visibility net ----------------------------------------------------------------------- */
@@ -199,7 +203,7 @@ int cds_dynamic_conv_tc(const void* x, int n_images, const int* img_index, const
  * batch; the reference image's branch convolutions (which do not depend on the epipole) run once per batch item. */
 int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index, const float* epipole, float epi_scale,
                               const void* wgt_packed, const float* bias, const float* gate, int V, int B, int Cin, int Cout, int H, int W,
-                              int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, double* out_stats,
+                              int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, void* out_lo, double* out_stats,
                               float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream);
 int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
                      int W, int dtype, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
@@ -213,8 +217,9 @@ int cds_conv2d_1x1_cat(const void* a, const double* a_stats, int a_act, const vo
  * weights' fp16 rounding residual in columns [Cout, 2*Cout) (host: weights.py pack_conv2d_gtc). */
 int cds_conv2d_3x3s2_tc_supported(int Cin, int Cout);
 int cds_conv2d_3x3s2_tc_weight_halfs(int Cin, int Cout);
-int cds_conv2d_3x3s2_tc(const void* in, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin, int Cout, int H,
-                        int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
+/* in_lo (optional, shape of in): the fp16 rounding residual plane of in; out_lo (optional, shape of out) receives that of out. */
+int cds_conv2d_3x3s2_tc(const void* in, const void* in_lo, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin,
+                        int Cout, int H, int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
 int cds_conv2d_1x1_cat_tc_supported(int Ca, int Cb, int Cout);
 int cds_conv2d_1x1_cat_tc_weight_halfs(int Ca, int Cb, int Cout);
 int cds_conv2d_1x1_cat_tc(const void* a, const double* a_stats, int a_act, const void* b, const double* b_stats, int b_act,
@@ -223,6 +228,10 @@ int cds_conv2d_1x1_cat_tc(const void* a, const double* a_stats, int a_act, const
 /* InstanceNorm2d(affine=False, eps 1e-5, biased variance) + activation, materialised. */
 int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C, int H, int W, int dtype, void* out,
                      cudaStream_t stream);
+/* Same from split-precision fp16 storage: raw + raw_lo (its fp16 rounding residual plane, may be NULL) -> fp32 out [n,H,W,C]
+ * (the stage-1 feature of the cascade, whose rounding the later stages amplify: DESIGN.md section 3). */
+int cds_instnorm_act_split_f32(const void* raw, const void* raw_lo, const double* stats, int act, int n, int C, int H, int W,
+                               float* out, cudaStream_t stream);
 /* fp32 NCHW <-> channels-last storage type, for the op-level drop-ins' public signatures. */
 int cds_nchw_to_nhwc(const float* in, int n, int C, int H, int W, int dtype, void* out, cudaStream_t stream);
 int cds_nhwc_to_nchw(const void* in, int n, int C, int H, int W, int dtype, float* out, cudaStream_t stream);

@@ -177,9 +177,15 @@ def test_stale_weight_cache_is_detected(pretrained_sd):
     model.feature.load_state_dict(fsd)                       # a submodule's load: the parent's hooks do not fire
     b = run(model, s)["depth"].clone()
     assert O.rel_l1(b.cpu(), a.cpu()) > 1e-6, "folded weights were not rebuilt after a submodule load_state_dict"
-    model.feature.conv01.conv.convs[1].weight.data.div_(1.5)  # in-place edit
+    with torch.no_grad():
+        model.feature.conv01.conv.convs[1].weight.div_(1.5)   # in-place edit (what an optimizer step / EMA swap does)
     c = run(model, s)["depth"]
     assert O.rel_l1(c.cpu(), a.cpu()) < 2e-5, "folded weights were not rebuilt after an in-place parameter edit"
+    # an edit through ``.data`` bypasses autograd's version counter: the documented escape hatch is invalidate_cache()
+    model.feature.conv01.conv.convs[1].weight.data.mul_(1.5)
+    model.invalidate_cache()
+    d = run(model, s)["depth"]
+    assert O.rel_l1(d.cpu(), b.cpu()) < 2e-5
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
