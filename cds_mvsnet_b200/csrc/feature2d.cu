@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(256) instnorm_act_kernel(const T* __restrict__
 // the same from fp16 value + residual planes to fp32 (nothing is rounded on the way)
 __global__ void __launch_bounds__(256) instnorm_act_split_kernel(const __half* __restrict__ raw, const __half* __restrict__ raw_lo,
                                                                  const double* __restrict__ stats, int act, int C, long long HW,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, __half* __restrict__ out16) {
     extern __shared__ float s_norm[];  // [C][2]
     const int n = blockIdx.y;
     for (int c = threadIdx.x; c < C; c += blockDim.x) norm_coeffs(stats, n, C, c, (double)HW, s_norm[2 * c], s_norm[2 * c + 1]);
@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(256) instnorm_act_split_kernel(const __half* _
             v[j] = apply_act((v[j] - s_norm[2 * c]) * s_norm[2 * c + 1], act);
         }
         Vec8<float>::store(out + (size_t)n * HW * C + i * 8, v);
+        if (out16) Vec8<__half>::store(out16 + (size_t)n * HW * C + i * 8, v);
     }
 }
 
@@ -781,12 +782,13 @@ int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C
 }
 
 int cds_instnorm_act_split_f32(const void* raw, const void* raw_lo, const double* stats, int act, int n, int C, int H, int W,
-                               float* out, cudaStream_t stream) {
+                               float* out, void* out_f16, cudaStream_t stream) {
     CDS_REQUIRE(raw && stats && out, CDS_EARG, "cds_instnorm_act_split_f32: null pointer");
     CDS_REQUIRE(n > 0 && n <= 65535 && C % 8 == 0 && C > 0, CDS_ESHAPE, "cds_instnorm_act_split_f32: bad shape");
     long long HW = (long long)H * W;
     dim3 grid((unsigned)std::min<long long>(148 * 8, (HW * (C / 8) + 255) / 256), n);
-    instnorm_act_split_kernel<<<grid, 256, C * 2 * sizeof(float), stream>>>((const __half*)raw, (const __half*)raw_lo, stats, act, C, HW, out);
+    instnorm_act_split_kernel<<<grid, 256, C * 2 * sizeof(float), stream>>>((const __half*)raw, (const __half*)raw_lo, stats, act, C, HW, out,
+                                                                            (__half*)out_f16);
     return cds_check_launch("cds_instnorm_act_split_f32");
 }
 

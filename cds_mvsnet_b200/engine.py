@@ -76,6 +76,8 @@ class FeatureExtractor:
         self._buf = None
         self.pairs = None   # (V, B) when the batch is the cascade's (side, v, b) pair batch
         self.share_ref = os.environ.get("CDS_SHARE_REF", "1") != "0"
+        # trunk layers on the row-folded persistent kernel (csrc/dynconv_kh.cu); CDS_DYN_KH=0 keeps them on the tap GEMM
+        self.use_kh = os.environ.get("CDS_DYN_KH", "1") != "0"
 
     def _dyn(self, name, x, in_mode, img_index, in_stats, in_act, epi, epi_scale, n, H, W, T, out, out_stats, nc_sq,
              nc_mode, nc_abs, norm_curv=None, split_in=False, out_lo=None):
@@ -94,6 +96,13 @@ class FeatureExtractor:
                 img8 = self._buf.get("f.img8", (n_images, H, W, 8), torch.float16)
                 call("cds_image_to_nhwc8", ptr(x), n_images, H, W, ptr(img8))
                 x = img8
+            if (self.use_kh and w.kh is not None
+                    and _lib.LIB.load().cds_dynamic_conv_kh_supported(max(8, w.cin), w.cout, H, W, len(w.ksizes), ks)):
+                pv, pb = self.pairs if (in_mode == 1 and self.pairs is not None and self.share_ref) else (0, 0)
+                call("cds_dynamic_conv_kh", ptr(x), n_images, ptr(img_index), ptr(in_stats), in_act, ptr(epi), float(epi_scale),
+                     ptr(w.kh), ptr(w.bias), ptr(w.gate), n, max(8, w.cin), w.cout, H, W, len(w.ksizes), ks, float(T),
+                     int(split_in), ptr(out), ptr(out_lo), ptr(out_stats), ptr(norm_curv), ptr(nc_sq), nc_mode, ptr(nc_abs), pv, pb)
+                return
             if in_mode == 1 and self.pairs is not None and self.share_ref and not split_in:
                 V, B = self.pairs   # the reference image's convolutions are shared by its V pairs
                 call("cds_dynamic_conv_tc_pairs", ptr(x), n_images, ptr(img_index), ptr(epi), float(epi_scale), ptr(w.tc), ptr(w.bias),
@@ -216,13 +225,18 @@ class FeatureExtractor:
         # stage-1 output
         self._dyn("out1", raw21, 0, None, sv(7, 32), ACT_LRELU, epipoles, 0.25, n, H4, W4, T, rawo1[0], sv(8, 32), ncsq[0], 2, ncab[0],
                   split_in=split, out_lo=lo(rawo1))
+        fea1_16 = None
         if split:
+            # the similarity-entropy sweep of stage 1 only feeds the visibility net: it reads an fp16 copy of the feature (half the
+            # gather bytes; measured no change of the depth error at cfg2: 8.27e-4 vs 8.31e-4).  CDS_S0_ENTROPY_F16=0: fp32.
+            if os.environ.get("CDS_S0_ENTROPY_F16", "1") != "0":
+                fea1_16 = buf.get("f.fea1_16", (n, H4, W4, 32), st)
             kcall("feat.act1", 0, n * H4 * W4 * 32 * (2 * e + 4), "cds_instnorm_act_split_f32", ptr(rawo1[0]), ptr(rawo1[1]), ptr(sv(8, 32)),
-                  ACT_TANH, n, 32, H4, W4, ptr(fea1))
+                  ACT_TANH, n, 32, H4, W4, ptr(fea1), ptr(fea1_16))
         else:
             kcall("feat.act1", 0, 2 * n * H4 * W4 * 32 * e, "cds_instnorm_act", ptr(rawo1[0]), ptr(sv(8, 32)), ACT_TANH, n, 32, H4, W4, dt, ptr(fea1))
         if after_stage1 is not None:   # the stage-1 feature is complete: the caller may start stage 1 on another stream
-            after_stage1((fea1, ncsq[0], ncab[0]))
+            after_stage1((fea1, ncsq[0], ncab[0], fea1_16))
         # stage-2 output: inner1 over cat(up2(conv21), conv11)
         self._inner("inner1", raw21[0], sv(7, 32), ACT_LRELU, raw11[0], sv(4, 16), fw.inner1, n, 32, 16, 16, H2, W2, rawi1, sv(9, 16))
         self._dyn("out2", rawi1, 0, None, sv(9, 16), ACT_LRELU, epipoles, 0.5, n, H2, W2, T, rawo2, sv(10, 16), ncsq[1], 2, ncab[1])
@@ -231,7 +245,7 @@ class FeatureExtractor:
         self._inner("inner2", fea2, None, ACT_NONE, raw01[0], sv(1, 8), fw.inner2, n, 16, 8, 8, H, W, rawi2, sv(11, 8))
         self._dyn("out3", rawi2, 0, None, sv(11, 8), ACT_LRELU, epipoles, 1.0, n, H, W, T, rawo3, sv(12, 8), ncsq[2], 2, ncab[2])
         kcall("feat.act3", 0, 2 * n * H * W * 8 * e, "cds_instnorm_act", ptr(rawo3), ptr(sv(12, 8)), ACT_TANH, n, 8, H, W, dt, ptr(fea3))
-        return {0: (fea1, ncsq[0], ncab[0]), 1: (fea2, ncsq[1], ncab[1]), 2: (fea3, ncsq[2], ncab[2])}
+        return {0: (fea1, ncsq[0], ncab[0], fea1_16), 1: (fea2, ncsq[1], ncab[1]), 2: (fea3, ncsq[2], ncab[2])}
 
 
 class Regulariser:
@@ -408,7 +422,8 @@ class CascadeEngine:
         D, scale, C = self.ndepths[s], STAGE_SCALE[s], STAGE_CHANNELS[s]
         h, w = H // scale, W // scale
         buf, f32 = self.buf, torch.float32
-        fea, ncsq, ncabs = feats_s
+        fea, ncsq, ncabs = feats_s[:3]
+        fea16 = feats_s[3] if len(feats_s) > 3 else None   # optional fp16 copy of a precise (fp32) stage-1 feature
         VB = V * B
         samples = buf.get(f"s{s}.samples", (B, D, h, w), f32)
         hp, wp = (prev_depth.shape[1], prev_depth.shape[2]) if prev_depth is not None else (0, 0)
@@ -421,8 +436,12 @@ class CascadeEngine:
         fea_f32 = fea.dtype == torch.float32 and self.storage == torch.float16
         fdt, fe = (_lib.CDS_F32, 4) if fea_f32 else (self.dt, e)
         entropy = buf.get(f"s{s}.entropy", (V, B, h, w), f32)
-        kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * fe + 4) + 4 * D * P, "cds_costvol_entropy",
-              ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, fdt, ptr(entropy))
+        if fea16 is not None:
+            kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * e + 4) + 4 * D * P, "cds_costvol_entropy",
+                  ptr(fea16[:VB]), ptr(fea16[VB:]), ptr(coef_s), ptr(samples), V, B, C, D, h, w, self.dt, ptr(entropy))
+        else:
+            kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * fe + 4) + 4 * D * P, "cds_costvol_entropy",
+                  ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, fdt, ptr(entropy))
         vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
         if (self.use_tc and self.w.vis_tc and self.storage == torch.float16 and _lib.LIB.load().cds_visnet_tc_supported(h, w)):
             wgt, fp = self.w.vis_tc[s]

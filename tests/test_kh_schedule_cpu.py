@@ -1,0 +1,104 @@
+"""CPU model of the MMA schedule of csrc/dynconv_kh.cu (kernel rows folded into N): the packed operand images of
+``weights.pack_dynamic_conv_kh`` are pushed through exactly the index arithmetic the kernel's issuers use -- row streaming,
+column-group ranges clipped to the tile, the step's A-slab offsets, accumulation into zeroed slots -- and the accumulator
+tile must equal the branch convolutions / curvature convolutions of the oracle.  Host logic only: no kernel runs here."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cds_mvsnet_b200 import weights as W
+
+TX = 128
+
+
+def emulate(layer, sd, x, TY):
+    """x [Cin_pad, H, W] fp64 (the staged operand) -> per branch [H, W, NPAD] accumulators, via the kernel's schedule."""
+    cin, cout, ks, pre = W.DYN_LAYERS[layer]
+    w = W.pack_dynamic_conv(sd, pre, cin, cout, ks, "cpu")
+    img = W.pack_dynamic_conv_kh(w).double().numpy()
+    c8 = max(1, cin // 8)
+    npad = (cout + 3 + 15) // 16 * 16
+    hmax = (max(ks) - 1) // 2
+    txo = TX - 2 * hmax
+    _, H, Wd = x.shape
+    # operand images per branch: [t (hi, lo)][j][q][n][kk]
+    imgs, o = [], 0
+    for k in ks:
+        nj = (k + 1) // 2 if c8 == 1 else k * c8 // 2
+        sz = nj * 2 * k * npad * 8
+        per = []
+        for _t in range(2):
+            per.append(img[o:o + sz].reshape(nj, 2, k * npad // 8, 8, 8).transpose(0, 1, 2, 3, 4).reshape(nj, 2, k * npad, 8))
+            o += sz
+        imgs.append(per)
+    assert o == img.size
+    out = [np.full((H, Wd, npad), np.nan) for _ in ks]
+    xt, yt = -(-Wd // txo), -(-H // TY)
+    for ty in range(yt):
+        for tx in range(xt):
+            y0, x0 = ty * TY, max(0, min(tx * txo, Wd - txo))
+            acc = [np.zeros((TY, TX, npad)) for _ in ks]                 # TMEM tile: every slot is handed over zeroed by the epilogue
+            for R in range(max(y0 - hmax, 0), min(y0 + TY - 1 + hmax, H - 1) + 1):
+                # the staged row segment: pixels x0-hmax .. +128 (+ spill), zero outside the image, [px][c8][8]
+                row = np.zeros((TX + 2 * hmax + 2, c8 * 8))
+                for px in range(TX + 2 * hmax + 2):
+                    gx = x0 - hmax + px
+                    if 0 <= gx < Wd and px < TX:
+                        row[px] = x[:, R, gx]
+                    elif px >= TX:
+                        row[px] = 7.0      # spill past the segment: finite garbage that only reaches discarded rows / zero weights
+                for b, k in enumerate(ks):
+                    hb = (k - 1) // 2
+                    ylo, yhi = max(y0, R - hb), min(min(y0 + TY - 1, H - 1), R + hb)
+                    if ylo > yhi:
+                        continue
+                    g0, ng = ylo - (R - hb), yhi - ylo + 1
+                    nj = (k + 1) // 2 if c8 == 1 else k * c8 // 2
+                    for prod in range(2):          # (A, W_hi), (A, W_lo); the A_lo product reuses W_hi with another plane
+                        for j in range(nj):
+                            A = np.zeros((TX, 16))
+                            for q in range(2):
+                                if c8 == 1:
+                                    off, ch = hmax - hb + 2 * j + q, 0
+                                else:
+                                    off, ch = hmax - hb + (2 * j) // c8, (2 * j) % c8 + q
+                                A[:, q * 8:(q + 1) * 8] = row[off:off + TX, ch * 8:(ch + 1) * 8]
+                            Bm = imgs[b][prod][j]                                           # [q][n][kk]
+                            Bfull = np.concatenate((Bm[0], Bm[1]), axis=1)                  # [n, 16]
+                            for g in range(g0, g0 + ng):                                  # every MMA accumulates
+                                s = (R - hb + g) - y0
+                                acc[b][s] += A @ Bfull[g * npad:(g + 1) * npad].T                # [128, NPAD]
+            for b in range(len(ks)):
+                for s in range(TY):
+                    y = y0 + s
+                    if y >= H:
+                        continue
+                    for r in range(txo):
+                        gx = x0 + r
+                        if gx < Wd and gx >= tx * txo:
+                            out[b][y, gx] = acc[b][s, r]
+    return out, (cin, cout, ks, pre)
+
+
+@pytest.mark.parametrize("layer,TY,hw", [("conv01", 10, (23, 140)), ("conv00", 10, (13, 131)), ("conv10", 8, (19, 30)),
+                                         ("conv20", 5, (7, 130))])
+def test_kh_schedule_reproduces_branch_convolutions(pretrained_sd, layer, TY, hw):
+    torch.manual_seed(0)
+    cin, cout, ks, pre = W.DYN_LAYERS[layer]
+    H, Wd = hw
+    x = torch.randn(max(8, cin), H, Wd, dtype=torch.float64)
+    if cin == 3:   # the image layer: channels 3..5 carry the residual of 0..2, 6..7 are zero
+        x[3:6] = x[0:3] * 1e-3
+        x[6:] = 0
+    out, _ = emulate(layer, pretrained_sd, x.numpy(), TY)
+    xin = (x[0:3] + x[3:6]) if cin == 3 else x[:cin]
+    for b, k in enumerate(ks):
+        ref_f = F.conv2d(xin[None], pretrained_sd[f"{pre}.convs.{b}.weight"].double(), padding=(k - 1) // 2)[0]
+        ref_a = F.conv2d(xin[None], pretrained_sd[f"{pre}.att_convs.{b}.weight"].double(), padding=(k - 1) // 2)[0]
+        got = torch.from_numpy(out[b])
+        assert not torch.isnan(got[..., :cout + 3]).any(), "a pixel was never written"
+        scale = ref_f.abs().max()
+        assert (got[..., :cout].permute(2, 0, 1) - ref_f).abs().max() < 1e-5 * scale + 1e-7
+        assert (got[..., cout:cout + 3].permute(2, 0, 1) - ref_a).abs().max() < 1e-5 * ref_a.abs().max() + 1e-7
+        assert got[..., cout + 3:].abs().max() == 0
