@@ -21,6 +21,8 @@
 #include <cstdlib>
 #include <type_traits>
 #include "cds_common.cuh"
+#include "tc_common.cuh"
+#include "tma_host.h"
 
 namespace {
 
@@ -570,6 +572,251 @@ __global__ void nc_mean_kernel(const float* __restrict__ ref_nc, const float* __
     out[i] = s / (float)V;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stage-3 form of both sweeps (C = 8 fp16 features, D = 8 hypotheses around the previous stage's depth): TMA-staged source
+// tiles.  The D samples of a pixel lie within a few pixels of each other along its epipolar line, so the footprints of a
+// 32 x 8 tile of reference pixels fall, for one source view, into a small box of the source image.  The CTA
+//   1. projects its pixels' D samples into every view and reduces the bounding box of the footprints (warp shuffles + smem),
+//   2. has ONE thread fetch each view's box (BW x BH pixels, 16 B each) by TMA into shared memory (out-of-image pixels arrive
+//      as zeros = grid_sample's zero padding, warping.py:100-101), all views in flight at once,
+//   3. gathers the 4 x D taps per view from shared memory (30-cycle LDS instead of dependent L2 round trips: the global form
+//      of this sweep is latency-bound at D = 8) and finishes exactly like the global-gather kernels.
+// A view whose box does not fit (depth discontinuities inside the tile, wild coordinates) takes the global-gather path for
+// that view, so the result never depends on the staging.
+// ---------------------------------------------------------------------------------------------
+constexpr int S3_TW = 32, S3_TH = 8, S3_D = 8, S3_BW = 48, S3_BH = 16, S3_VMAX = 4;
+constexpr int S3_BOX_BYTES = S3_BW * S3_BH * 16;
+
+struct S3Params {
+    const __half* ref_fea;   // [V,B,h,w,8]
+    const __half* src_fea;   // [V,B,h,w,8] (global-gather path)
+    const float* coef;       // [B,V,12]
+    const float* depth;      // [B,8,h,w]
+    const float* vis;        // [V,B,h,w]   (aggregate)
+    float* entropy;          // [V,B,h,w]   (entropy)
+    __half* volume;          // [B,1,8,h,w,8] (aggregate)
+    int V, B, h, w;
+};
+
+// sample position of depth `dep` for a pixel ray: explicit FMAs, so that the bounding-box pass and the sweep compute the
+// SAME bits (a coordinate that differed by an ulp across an integer could step outside the staged box)
+__device__ __forceinline__ void s3_project(float rx, float ry, float rz, float tx, float ty, float tz, float dep, float& u, float& v) {
+    const float iz = __frcp_rn(__fmaf_rn(rz, dep, tz));
+    u = __fmul_rn(__fmaf_rn(rx, dep, tx), iz);
+    v = __fmul_rn(__fmaf_rn(ry, dep, ty), iz);
+}
+
+// the 4 taps (raw 8-channel chunks) and bilinear weights of one sample: from the staged box, or from global memory
+struct S3Taps {
+    uint4 t00, t01, t10, t11;
+    float w00, w01, w10, w11;
+};
+__device__ __forceinline__ S3Taps s3_taps(bool staged, const uint8_t* box, int bx, int by, const __half* gsrc, unsigned pix0, int w, int h,
+                                          float u, float vv) {
+    S3Taps t;
+    if (staged) {   // block-uniform
+        const float xf = floorf(u), yf = floorf(vv);
+        const float fx = u - xf, fy = vv - yf, gx = 1.f - fx, gy = 1.f - fy;
+        t.w00 = gx * gy; t.w01 = fx * gy; t.w10 = gx * fy; t.w11 = fx * fy;
+        const uint8_t* q = box + (((int)yf - by) * S3_BW + ((int)xf - bx)) * 16;
+        t.t00 = *reinterpret_cast<const uint4*>(q);
+        t.t01 = *reinterpret_cast<const uint4*>(q + 16);
+        t.t10 = *reinterpret_cast<const uint4*>(q + S3_BW * 16);
+        t.t11 = *reinterpret_cast<const uint4*>(q + S3_BW * 16 + 16);
+    } else {
+        const Foot f = make_foot(u, vv, w, h);
+        const TapAddr<__half, 8> ta(gsrc, pix0, w, f);
+        t.t00 = __ldg(reinterpret_cast<const uint4*>(ta.t00())); t.t01 = __ldg(reinterpret_cast<const uint4*>(ta.t01()));
+        t.t10 = __ldg(reinterpret_cast<const uint4*>(ta.t10())); t.t11 = __ldg(reinterpret_cast<const uint4*>(ta.t11()));
+        t.w00 = f.w00; t.w01 = f.w01; t.w10 = f.w10; t.w11 = f.w11;
+    }
+    return t;
+}
+
+template <int MODE>   // 0: similarity entropy per view; 1: visibility-weighted aggregate
+__global__ void __launch_bounds__(256, 4) costvol_s3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const S3Params p) {
+    extern __shared__ __align__(128) uint8_t s3_smem[];
+    uint8_t (*s_box)[S3_BOX_BYTES] = reinterpret_cast<uint8_t (*)[S3_BOX_BYTES]>(s3_smem);
+    __shared__ float s_red[S3_VMAX][8][4];
+    __shared__ int s_org[S3_VMAX][3];          // box origin x, y, staged flag
+    __shared__ __align__(8) uint64_t s_bar;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, P = p.h * p.w;
+    const int x = min((int)blockIdx.x * S3_TW + lane, p.w - 1), y = min((int)blockIdx.y * S3_TH + warp, p.h - 1);
+    const bool live = (int)blockIdx.x * S3_TW + lane < p.w && (int)blockIdx.y * S3_TH + warp < p.h;
+    const size_t pofs = (size_t)y * p.w + x;
+    if (threadIdx.x == 0) { tc::mbar_init(&s_bar, 1); tc::mbar_fence_init(); }
+
+    float dep[S3_D];
+#pragma unroll
+    for (int d = 0; d < S3_D; ++d) dep[d] = __ldg(p.depth + ((size_t)b * S3_D + d) * P + pofs);
+
+    bool ascending = true;   // the cascade's hypotheses are (module.py:394-415); any other caller falls back to the global gathers
+#pragma unroll
+    for (int d = 1; d < S3_D; ++d) ascending = ascending && dep[d - 1] <= dep[d];
+    // ---- 1. bounding boxes of the footprints, all views ------------------------------------------------------------------
+    float rx[S3_VMAX], ry[S3_VMAX], rz[S3_VMAX], tx[S3_VMAX], ty[S3_VMAX], tz[S3_VMAX];
+#pragma unroll
+    for (int v = 0; v < S3_VMAX; ++v) {
+        if (v < p.V) {
+            const WarpCoef k = load_coef(p.coef + ((size_t)b * p.V + v) * 12);
+            pixel_ray(k, (float)x, (float)y, rx[v], ry[v], rz[v]);
+            tx[v] = k.t[0]; ty[v] = k.t[1]; tz[v] = k.t[2] + 1e-6f;
+            // a sample moves MONOTONICALLY along its epipolar line with depth (u, v are Moebius functions of the depth while the
+            // denominator keeps its sign), and the hypotheses are ascending: the extremes are taken at the first and last plane
+            float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+            const bool same_side = (__fmaf_rn(rz[v], dep[0], tz[v]) > 0.f) == (__fmaf_rn(rz[v], dep[S3_D - 1], tz[v]) > 0.f);
+#pragma unroll
+            for (int d = 0; d < S3_D; d += S3_D - 1) {
+                float u, vv;
+                s3_project(rx[v], ry[v], rz[v], tx[v], ty[v], tz[v], dep[d], u, vv);
+                // NaN-proof: a NaN coordinate makes the box infinite, which sends the view to the global path
+                umin = (u < umin) ? u : (u == u ? umin : -INFINITY); umax = (u > umax) ? u : (u == u ? umax : INFINITY);
+                vmin = (vv < vmin) ? vv : (vv == vv ? vmin : -INFINITY); vmax = (vv > vmax) ? vv : (vv == vv ? vmax : INFINITY);
+            }
+            if (!same_side || !ascending) { umin = vmin = -INFINITY; umax = vmax = INFINITY; }   // pole inside the range / arbitrary planes: global path
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+                vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            }
+            if (lane == 0) { s_red[v][warp][0] = umin; s_red[v][warp][1] = umax; s_red[v][warp][2] = vmin; s_red[v][warp][3] = vmax; }
+        } else {
+            rx[v] = ry[v] = rz[v] = tx[v] = ty[v] = 0.f; tz[v] = 1.f;
+        }
+    }
+    __syncthreads();
+    // ---- 2. one thread: box origins, TMA fetches of every view's box ---------------------------------------------------------
+    if (threadIdx.x == 0) {
+        uint32_t bytes = 0;
+        for (int v = 0; v < p.V; ++v) {
+            float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+            for (int i = 0; i < 8; ++i) {
+                umin = fminf(umin, s_red[v][i][0]); umax = fmaxf(umax, s_red[v][i][1]);
+                vmin = fminf(vmin, s_red[v][i][2]); vmax = fmaxf(vmax, s_red[v][i][3]);
+            }
+            // footprint columns floor(umin) .. floor(umax) + 1, rows likewise; staged when the box holds them and the
+            // coordinates are small integers (everything far outside the image is zero anyway: global path)
+            int staged = 0, bx = 0, by = 0;
+            if (umin > -65536.f && umax < 65536.f && vmin > -65536.f && vmax < 65536.f) {
+                bx = (int)floorf(umin); by = (int)floorf(vmin);
+                const int ex = (int)floorf(umax) + 1, ey = (int)floorf(vmax) + 1;
+                staged = (ex - bx < S3_BW && ey - by < S3_BH) ? 1 : 0;
+            }
+            s_org[v][0] = bx; s_org[v][1] = by; s_org[v][2] = staged;
+            if (staged) bytes += S3_BOX_BYTES;
+        }
+        if (bytes) {
+            tc::mbar_expect_tx(&s_bar, bytes);
+            for (int v = 0; v < p.V; ++v)
+                if (s_org[v][2])
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+                                 "r"(tc::smem_u32(&s_box[v][0])), "l"(&tmap), "r"(tc::smem_u32(&s_bar)), "r"(2 * s_org[v][0]), "r"(s_org[v][1]),
+                                 "r"(v * p.B + b) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(&s_bar)) : "memory");
+        }
+    }
+    // reference chunks / visibility shares while the boxes are in flight
+    uint4 rf[S3_VMAX];
+    float sc[S3_VMAX];
+    float vsum = 0.f;
+#pragma unroll
+    for (int v = 0; v < S3_VMAX; ++v) {
+        rf[v] = v < p.V ? __ldg(reinterpret_cast<const uint4*>(p.ref_fea + (((size_t)v * p.B + b) * P + pofs) * 8)) : make_uint4(0, 0, 0, 0);
+        sc[v] = 0.f;
+        if (MODE == 1 && v < p.V) { sc[v] = __ldg(p.vis + ((size_t)v * p.B + b) * P + pofs); vsum += sc[v]; }   // reference order (model.py:59)
+    }
+    if (MODE == 1) {
+        const float inv = 1.f / (vsum + 1e-6f);
+#pragma unroll
+        for (int v = 0; v < S3_VMAX; ++v) sc[v] *= inv;
+    }
+    __syncthreads();                 // s_org visible
+    tc::mbar_wait(&s_bar, 0);        // every staged box has landed
+
+    // ---- 3. the sweep ------------------------------------------------------------------------------------------------------
+    if (MODE == 0) {
+#pragma unroll
+        for (int v = 0; v < S3_VMAX; ++v) {
+            if (v >= p.V) break;   // block-uniform
+            const int bx = s_org[v][0], by = s_org[v][1];
+            const bool staged = s_org[v][2] != 0;
+            const unsigned pix0 = (unsigned)((v * p.B + b) * P);
+            float m = -INFINITY, S = 0.f, A = 0.f;
+#pragma unroll
+            for (int d = 0; d < S3_D; ++d) {
+                float u, vv;
+                s3_project(rx[v], ry[v], rz[v], tx[v], ty[v], tz[v], dep[d], u, vv);
+                const S3Taps t = s3_taps(staged, &s_box[v][0], bx, by, p.src_fea, pix0, p.w, p.h, u, vv);
+                const float s = t.w11 * dot8_f16(rf[v], t.t11) + (t.w10 * dot8_f16(rf[v], t.t10) + (t.w01 * dot8_f16(rf[v], t.t01) + t.w00 * dot8_f16(rf[v], t.t00)));
+                if (s > m) {
+                    const float delta = m - s;
+                    const float e = __expf(delta);
+                    const bool first = S == 0.f;
+                    A = first ? 0.f : e * (A + delta * S);
+                    S = first ? 0.f : S * e;
+                    m = s;
+                }
+                const float z = s - m, e = __expf(z);
+                S += e;
+                A += z * e;
+            }
+            if (live) p.entropy[((size_t)v * p.B + b) * P + pofs] = __logf(S) - A / S;
+        }
+    } else {
+        __half* outp = p.volume + ((size_t)b * S3_D * P + pofs) * 8;
+#pragma unroll 1
+        for (int d = 0; d < S3_D; ++d) {
+            float acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+            const float depd = __ldg(p.depth + ((size_t)b * S3_D + d) * P + pofs);   // (L1 hit; keeps dep[] out of a dynamic index)
+#pragma unroll
+            for (int v = 0; v < S3_VMAX; ++v) {
+                if (v >= p.V) break;   // block-uniform
+                float u, vv;
+                s3_project(rx[v], ry[v], rz[v], tx[v], ty[v], tz[v], depd, u, vv);
+                const S3Taps t = s3_taps(s_org[v][2] != 0, &s_box[v][0], s_org[v][0], s_org[v][1], p.src_fea, (unsigned)((v * p.B + b) * P), p.w,
+                                         p.h, u, vv);
+                // same arithmetic as aggregate_f16_kernel: visibility share folded into the weights, packed-half blend, FHFMA
+                const __half2 h00 = __floats2half2_rn(t.w00 * sc[v], t.w00 * sc[v]), h01 = __floats2half2_rn(t.w01 * sc[v], t.w01 * sc[v]);
+                const __half2 h10 = __floats2half2_rn(t.w10 * sc[v], t.w10 * sc[v]), h11 = __floats2half2_rn(t.w11 * sc[v], t.w11 * sc[v]);
+                const uint32_t* a = &t.t00.x; const uint32_t* bq = &t.t01.x; const uint32_t* c = &t.t10.x; const uint32_t* e = &t.t11.x;
+                const uint32_t* r = &rf[v].x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t sblend = as_u32(__hfma2(h11, as_half2(e[i]), __hfma2(h10, as_half2(c[i]),
+                                                   __hfma2(h01, as_half2(bq[i]), __hmul2(h00, as_half2(a[i]))))));
+                    acc[2 * i] = fhfma((uint16_t)(r[i] & 0xffffu), (uint16_t)(sblend & 0xffffu), acc[2 * i]);
+                    acc[2 * i + 1] = fhfma((uint16_t)(r[i] >> 16), (uint16_t)(sblend >> 16), acc[2 * i + 1]);
+                }
+            }
+            if (live) Vec8<__half>::store(outp + (size_t)d * P * 8, acc);
+        }
+    }
+}
+
+template <int MODE>
+int launch_s3_tma(const S3Params& p, cudaStream_t st) {
+    CUtensorMap tmap;
+    const uint64_t dims[3] = {2 * (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.V * p.B};
+    const uint64_t strides[3] = {0, (uint64_t)p.w * 16, (uint64_t)p.h * p.w * 16};
+    const uint32_t box[3] = {2 * S3_BW, S3_BH, 1};
+    if (!tma::make_u64(&tmap, p.src_fea, 3, dims, strides, box)) return CDS_EUNSUPPORTED;
+    dim3 grid(cds_div_up(p.w, S3_TW), cds_div_up(p.h, S3_TH), p.B);
+    constexpr int smem = S3_VMAX * S3_BOX_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(costvol_s3_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { cds_set_error("cds_costvol: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    costvol_s3_tma_kernel<MODE><<<grid, 256, smem, st>>>(tmap, p);
+    return cds_check_launch(MODE == 0 ? "cds_costvol_entropy" : "cds_costvol_aggregate");
+}
+// the staged form covers the last cascade stage's shape; CDS_COSTVOL_TMA=0 keeps the global-gather kernels
+bool s3_tma_applies(int V, int B, int C, int D, int h, int w, int dtype) {
+    static const bool on = [] { const char* e = getenv("CDS_COSTVOL_TMA"); return !(e && e[0] == '0'); }();
+    return on && dtype == CDS_F16 && C == 8 && D == S3_D && V <= S3_VMAX && B <= 65535 && w >= 8 && h >= 2;
+}
+
 template <typename T>
 int launch_entropy(const void* ref, const void* src, const float* coef, const float* depth, int V, int B, int C, int D,
                    int h, int w, float* entropy, cudaStream_t st) {
@@ -646,6 +893,10 @@ int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* c
                 "cds_costvol_entropy: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
     CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B * h * w < (1ll << 31) && (long long)V * B <= 65535, CDS_ESHAPE,
                 "cds_costvol_entropy: feature map too large for 32-bit offsets");
+    if (s3_tma_applies(V, B, C, D, h, w, dtype)) {
+        S3Params p{(const __half*)ref_fea, (const __half*)src_fea, coef, depth, nullptr, entropy, nullptr, V, B, h, w};
+        return launch_s3_tma<0>(p, stream);
+    }
     if (dtype == CDS_F16) return launch_entropy<__half>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     if (dtype == CDS_F32) return launch_entropy<float>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     cds_set_error("cds_costvol_entropy: unknown dtype %d", dtype);
@@ -660,6 +911,10 @@ int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float*
                 "cds_costvol_aggregate: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
     CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B * h * w < (1ll << 31) && B <= 65535, CDS_ESHAPE,
                 "cds_costvol_aggregate: feature map too large for 32-bit offsets");
+    if (s3_tma_applies(V, B, C, D, h, w, dtype)) {
+        S3Params p{(const __half*)ref_fea, (const __half*)src_fea, coef, depth, vis, nullptr, (__half*)volume, V, B, h, w};
+        return launch_s3_tma<1>(p, stream);
+    }
     if (dtype == CDS_F16) return launch_aggregate<__half>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     if (dtype == CDS_F32) return launch_aggregate<float>(ref_fea, src_fea, coef, depth, vis, V, B, C, D, h, w, volume, stream);
     cds_set_error("cds_costvol_aggregate: unknown dtype %d", dtype);

@@ -294,6 +294,54 @@ def test_costvol_vs_oracle(C_, storage, tol, V):
     assert O.rel_l1(from_blocked(vol_out.float().cpu()), vol) < tol
 
 
+@pytest.mark.parametrize("V", [2, 4])
+@pytest.mark.parametrize("hw", [(27, 45), (120, 200)], ids=lambda v: f"{v[0]}x{v[1]}")
+@pytest.mark.parametrize("regime", ["smooth", "noisy", "step"])
+def test_costvol_stage3_tma_staged_vs_oracle(V, hw, regime):
+    """The last stage's shape (C = 8, D = 8, fp16) runs the TMA-staged form of both sweeps: source boxes in shared memory when
+    a tile's samples stay together ("smooth": hypotheses around a smooth depth map), the global gathers when they do not
+    ("noisy": independent depths per pixel), and a mix of both inside one launch ("step": a depth discontinuity)."""
+    from cds_mvsnet_b200 import synthetic
+    import ctypes
+    torch.manual_seed(V + hw[0])
+    B, D, C_ = 2, 8, 8
+    h, w = hw
+    s = synthetic.make_sample(dict(W=4 * w, H=4 * h, N=V + 1, ndepths=(8,), ratios=(1.0,), B=B, Dtot=192, interval=2.65))
+    pm = s.proj_matrices["stage1"]
+    ref_fea = torch.tanh(torch.randn(V, B, C_, h, w)).half().float()
+    src_fea = torch.tanh(torch.randn(V, B, C_, h, w)).half().float()
+    ys, xs = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    centre = 600 + 0.8 * xs - 0.5 * ys
+    if regime == "noisy":
+        centre = 450 + 450 * torch.rand(h, w)
+    elif regime == "step":
+        centre = torch.where(xs > w / 2, centre + 150.0, centre)
+    dv = (centre.reshape(1, 1, h, w) + 2.0 * (torch.arange(D).float() - 3.5).reshape(1, D, 1, 1)).repeat(B, 1, 1, 1).contiguous()
+    vis = torch.rand(V, B, h, w)
+    refP = O.compose_projection(pm[:, 0])
+    ents, vol = [], 0.0
+    for v in range(V):
+        warped = O.homo_warp(src_fea[v], O.compose_projection(pm[:, v + 1]), refP, dv)
+        prod, ent = O.similarity_entropy(ref_fea[v], warped)
+        ents.append(ent[:, 0])
+        vol = vol + prod * vis[v].unsqueeze(1).unsqueeze(1)
+    vol = vol / (vis.sum(0).unsqueeze(1).unsqueeze(1) + 1e-6)
+    pmc = cu(pm)
+    coef = torch.empty(1, B, V, 12, device=DEV)
+    call("cds_camera_setup", (ctypes.c_void_p * 1)(pmc.data_ptr()), 1, 0, B, V + 1, ptr(coef), None)
+    rf = cu(ref_fea.permute(0, 1, 3, 4, 2).contiguous()).half()
+    sf = cu(src_fea.permute(0, 1, 3, 4, 2).contiguous()).half()
+    dvc, visc = cu(dv), cu(vis)
+    ent_out = torch.full((V, B, h, w), float("nan"), device=DEV)
+    call("cds_costvol_entropy", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), V, B, C_, D, h, w, _lib.CDS_F16, ptr(ent_out))
+    close(ent_out, torch.stack(ents), 2e-4, 1e-4)
+    vol_out = torch.full((B, 1, D, h, w, 8), float("nan"), device=DEV, dtype=torch.float16)
+    call("cds_costvol_aggregate", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), ptr(visc), V, B, C_, D, h, w, _lib.CDS_F16, ptr(vol_out))
+    torch.cuda.synchronize()
+    assert not torch.isnan(vol_out.float()).any()
+    assert O.rel_l1(from_blocked(vol_out.float().cpu()), vol) < 2e-3
+
+
 def test_costvol_rejects_too_many_views():
     z = torch.zeros(16, device=DEV)
     with pytest.raises(RuntimeError, match="V="):
