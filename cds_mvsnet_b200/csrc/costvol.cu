@@ -849,6 +849,8 @@ int launch_aggregate(const void* ref, const void* src, const float* coef, const 
     const T* s = (const T*)src;
     T* o = (T*)volume;
     // fp32 storage (and CDS_COSTVOL_BLEND=f32): fp32 blend.  fp16 storage: packed-half blend, see aggregate_f16_kernel.
+    // The fp32-feature form with the split fp16 volume (stage 1 of the precise cascade) runs two resident blocks: at three it
+    // spills (measured 0.878 -> 0.740 ms at cfg2).
     static const int occ = [] { const char* e = getenv("CDS_AGG_OCC"); return e ? atoi(e) : 0; }();
     static const bool blend32 = [] { const char* e = getenv("CDS_COSTVOL_BLEND"); return e && e[0] == 'f' && e[1] == '3'; }();
     if constexpr (std::is_same<T, __half>::value) {
@@ -869,7 +871,7 @@ int launch_aggregate(const void* ref, const void* src, const float* coef, const 
         }
     }
 #define CDS_AGG(c)                                                                                                 \
-    if (V <= 4 && occ == 2) aggregate_kernel<T, c, 4, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo); \
+    if (V <= 4 && (occ == 2 || (occ == 0 && vol_hi))) aggregate_kernel<T, c, 4, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo); \
     else if (V <= 4) aggregate_kernel<T, c, 4, 3><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo);   \
     else aggregate_kernel<T, c, kMaxViews, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo);    \
     break;

@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
         }
     } else if (warp >= kEpiWarp0) {
         // ---- epilogue: gate + blend, one pixel per thread; two sets of four warps --------------------------------------------
-        const int set = (warp - kEpiWarp0) >> 2;     // GRP == 1: set handles the slots s = set (mod 2); GRP > 1: the items it = set (mod 2)
+        // Two sets of four warps.  A tile with ONE item (every layer but the image layer's shared-image groups): set e drains
+        // the slots s = e (mod 2).  A shared-image group (cnt > 1 items on one set of accumulators): both sets read every slot,
+        // set e handles the items it = e (mod 2), set 0 hands the slot back.
+        const int set = (warp - kEpiWarp0) >> 2;
         const int lg = warp & 3;                     // TMEM lane quadrant this warp may read
         const int r = lg * 32 + lane;                // MMA row = pixel x0 + r (valid while r < TXO)
         constexpr int NIT = GRP > 1 ? (GRP + 1) / 2 : 1;   // items this set handles per slot
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
             if (cur_z < 0 || !p.out_stats) return;
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
-                const int itx = GRP > 1 ? 2 * i + set : 0;
+                const int itx = (GRP > 1 && cur_cnt > 1) ? 2 * i + set : (i == 0 ? 0 : GRP);
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
                     const float a = warp_sum(st_sum[i][c]), qq = warp_sum(st_sq[i][c]);
@@ -444,12 +447,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                 group_of<GRP>(p, q.z, cur_n, cur_cnt, cur_nstr);
             }
             const int n = cur_n, cnt = cur_cnt, nstr = cur_nstr;
+            const bool shared = GRP > 1 && cnt > 1;   // warp-uniform: several items on one set of accumulators
             const int gx = q.x0 + r;
             const bool col_ok = r < TXO && gx < p.W && gx >= q.tx * TXO;   // strips overlap at the right edge: one owner per pixel
             float ex[NIT], ey[NIT];
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
-                const int itx = GRP > 1 ? min(2 * i + set, cnt - 1) : 0;
+                const int itx = shared ? min(2 * i + set, cnt - 1) : 0;
                 ex[i] = __ldg(p.epipole + 2 * (n + itx * nstr)) * p.epi_scale;
                 ey[i] = __ldg(p.epipole + 2 * (n + itx * nstr) + 1) * p.epi_scale;
             }
@@ -457,14 +461,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
             // sits in every row's critical path)
             auto load_nc = [&](int s) {
                 const int gy = q.y0 + s;
-                const bool ok = GRP == 1 && s < TY && col_ok && gy < p.H && p.nc_sq && p.nc_mode != 0;
+                const bool ok = !shared && s < TY && col_ok && gy < p.H && p.nc_sq && p.nc_mode != 0;
                 return ok ? __ldcg(p.nc_sq + ((size_t)n * p.H + gy) * p.W + gx) : 0.f;
             };
-            const int s_first = GRP == 1 ? set : 0, s_step = GRP == 1 ? 2 : 1;
+            const int s_first = shared ? 0 : set, s_step = shared ? 1 : 2;
             float nc_next = load_nc(s_first);
 #pragma unroll 1
             for (int s = 0; s < TY; ++s) {
-                const bool mine = GRP > 1 || (s & 1) == set;
+                const bool mine = shared || (s & 1) == set;
                 if (!mine) continue;
                 const float nc_old = nc_next;
                 nc_next = load_nc(s + s_step);
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                 tc::tc_fence_after();
                 const int gy = q.y0 + s;
                 if (gy >= p.H) {   // slot not used by this tile (never accumulated into: still zero)
-                    if ((GRP == 1 || set == 0) && lane == 0) mbar_arrive(acc_empty + s);
+                    if ((!shared || set == 0) && lane == 0) mbar_arrive(acc_empty + s);
                     continue;
                 }
                 const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * NPAD;
@@ -485,6 +489,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                 float wgt[NIT][NK], ncv[NIT];
 #pragma unroll
                 for (int i = 0; i < NIT; ++i) {
+                    if (i > 0 && !shared) { ncv[i] = 0.f; continue; }   // warp-uniform: a single-item tile has one gate per pixel
                     float uu = (float)gx - ex[i], vv = (float)gy - ey[i];
                     const float rinv = __frcp_rn(sqrtf(uu * uu + vv * vv) + 1e-6f);
                     uu *= rinv;
@@ -529,8 +534,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                     if (c8 == COUT / 8 - 1) {
                         // every accumulator column of the slot is in registers (of both sets, for a shared-image group): hand the
                         // slot back ZEROED -- every MMA accumulates, whichever issuer's MMA arrives first
-                        if constexpr (GRP > 1) named_barrier(2, 256);
-                        if (GRP == 1 || set == 0) {
+                        if (shared) named_barrier(2, 256);
+                        if (!shared || set == 0) {
 #pragma unroll
                             for (int b = 0; b < NK; ++b)
 #pragma unroll
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                     }
 #pragma unroll
                     for (int i = 0; i < NIT; ++i) {
-                        const int itx = GRP > 1 ? 2 * i + set : 0;
+                        const int itx = shared ? 2 * i + set : (i == 0 ? 0 : GRP);
                         if (itx < cnt) {   // warp-uniform
                             float out[8];
 #pragma unroll
@@ -570,13 +575,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                 // 3. curvature maps
 #pragma unroll
                 for (int i = 0; i < NIT; ++i) {
-                    const int itx = GRP > 1 ? 2 * i + set : 0;
+                    const int itx = shared ? 2 * i + set : (i == 0 ? 0 : GRP);
                     if (itx < cnt && valid) {
                         const size_t m = ((size_t)(n + itx * nstr) * p.H + gy) * p.W + gx;
                         const float nc = ncv[i];
                         if (p.norm_curv) p.norm_curv[m] = nc;
                         if (p.nc_sq) {
-                            const float old = GRP == 1 ? nc_old : (p.nc_mode != 0 ? p.nc_sq[m] : 0.f);
+                            const float old = !shared ? nc_old : (p.nc_mode != 0 ? p.nc_sq[m] : 0.f);
                             if (p.nc_mode == 0) p.nc_sq[m] = nc * nc;
                             else if (p.nc_mode == 1) p.nc_sq[m] = old + nc * nc;
                             else p.nc_sq[m] = (old + nc * nc) / 3.f;

@@ -52,20 +52,14 @@ def save_pfm(filename, image, scale=1):
 
 
 def write_cam(filename, cam):
-    """cam [2,4,4] = (extrinsic, intrinsic; row [1,3] = depth_min, interval, ndepth, depth_max)   (test.py:132-149)"""
+    """cam [2,4,4] = (extrinsic, intrinsic; row [1,3] = depth_min, interval, ndepth, depth_max).  Same bytes as the text file
+    of test.py:132-149: every number as ``str()`` of the array element, a trailing blank after each matrix entry."""
+    cam = np.asarray(cam)
+    row = lambda r: "".join(str(v) + " " for v in r)
+    lines = ["extrinsic"] + [row(cam[0, i]) for i in range(4)] + ["", "intrinsic"] + [row(cam[1, i, :3]) for i in range(3)]
+    lines += ["", " ".join(str(v) for v in cam[1, 3])]
     with open(filename, "w") as f:
-        f.write("extrinsic\n")
-        for i in range(4):
-            for j in range(4):
-                f.write(str(cam[0][i][j]) + " ")
-            f.write("\n")
-        f.write("\n")
-        f.write("intrinsic\n")
-        for i in range(3):
-            for j in range(3):
-                f.write(str(cam[1][i][j]) + " ")
-            f.write("\n")
-        f.write("\n" + str(cam[1][3][0]) + " " + str(cam[1][3][1]) + " " + str(cam[1][3][2]) + " " + str(cam[1][3][3]) + "\n")
+        f.write("\n".join(lines) + "\n")
 
 
 def resize_nearest(a, h, w):
