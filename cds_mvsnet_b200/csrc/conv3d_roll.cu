@@ -70,6 +70,10 @@ struct RollParams {
     const float* bias;   // [COUT] (conv0) or null (prob head)
     __half* out;         // conv0: [D, H, W, 8] (one batch item)
     float* logits;       // prob head: fp32 [D, H, W]
+    // prob head with the fused tail (models/model.py:85-92): softmax over D + expectation + 4-bin confidence in the epilogue
+    const float* samples;   // depth hypotheses [D, H, W] of this batch item, or null: logits only
+    float* depth_out;       // [H, W]
+    float* conf_out;        // [H, W]
     int D, H, W, relu;
     int xt, yt;          // columns along x and y
 };
@@ -238,6 +242,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_roll_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < COUT; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
         uint32_t uc0 = 0, planes = 0;        // unit counter at the start of the current plane
+        // fused tail (prob head only): online softmax over the planes of a column, per owned row unit -- running max, sum of
+        // e^(l-m), and the two expectations (depth, plane index) rescaled together; same arithmetic, plane order and
+        // intrinsics as softmax_regress_kernel (conv3d.cu), so the fused and the separate tail agree bit for bit
+        float sm_m[UPG], sm_S[UPG], sm_ed[UPG], sm_ei[UPG];
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int x0 = max(0, min((tile % p.xt) * TXO, p.W - TXO));
@@ -319,7 +327,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_roll_kernel(const __grid_c
                             }
                             Vec8<__half>::store(p.out + vox * 8, o);
                         } else {
-                            p.logits[vox] = part[i][0];
+                            const float l = part[i][0];
+                            p.logits[vox] = l;
+                            if (p.samples) {
+                                if (d == 0) { sm_m[i] = -INFINITY; sm_S[i] = 0.f; sm_ed[i] = 0.f; sm_ei[i] = 0.f; }
+                                const float dep = __ldg(p.samples + vox);
+                                if (l > sm_m[i]) {
+                                    const float r = __expf(sm_m[i] - l);   // 0 on the first plane (m = -inf)
+                                    sm_S[i] *= r; sm_ed[i] *= r; sm_ei[i] *= r;
+                                    sm_m[i] = l;
+                                }
+                                const float e = __expf(l - sm_m[i]);
+                                sm_S[i] += e;
+                                sm_ed[i] += e * dep;
+                                sm_ei[i] += e * (float)d;
+                                if (d == p.D - 1) {
+                                    const float inv = 1.f / sm_S[i];
+                                    const size_t pix = (size_t)y * p.W + x;
+                                    p.depth_out[pix] = sm_ed[i] * inv;
+                                    // photometric confidence: the four probabilities around trunc(expected index)
+                                    // (models/module.py:382-391); their logits were written by this thread a few planes ago
+                                    const int idx = min(max((int)(sm_ei[i] * inv), 0), p.D - 1);
+                                    float c = 0.f;
+                                    for (int j = idx - 1; j <= idx + 2; ++j)
+                                        if (j >= 0 && j < p.D) c += __expf(p.logits[((size_t)j * p.H + y) * p.W + x] - sm_m[i]) * inv;
+                                    p.conf_out[pix] = c;
+                                }
+                            }
                         }
                     }
                 }
@@ -343,7 +377,8 @@ int sm_count() {
 }
 
 template <int CIN, int COUT, int TY>
-int launch_roll(const void* in, const void* wgt, const float* bias, int B, int D, int H, int W, int relu, void* out, cudaStream_t st) {
+int launch_roll(const void* in, const void* wgt, const float* bias, int B, int D, int H, int W, int relu, void* out, cudaStream_t st,
+                const float* samples = nullptr, float* depth_out = nullptr, float* conf_out = nullptr) {
     using C = RollCfg<CIN, COUT, TY>;
     static_assert(C::SMEM <= 227 * 1024, "rolling-conv ring does not fit in shared memory");
     auto kern = conv3d_roll_kernel<CIN, COUT, TY>;
@@ -365,6 +400,9 @@ int launch_roll(const void* in, const void* wgt, const float* bias, int B, int D
         if (!tma::make_u64(&tmap, base, 4, dims, strides, box)) return CDS_EUNSUPPORTED;
         p.out = COUT == 1 ? nullptr : (__half*)out + (size_t)b * D * H * W * COUT;
         p.logits = COUT == 1 ? (float*)out + (size_t)b * D * H * W : nullptr;
+        p.samples = samples ? samples + (size_t)b * D * H * W : nullptr;
+        p.depth_out = depth_out ? depth_out + (size_t)b * H * W : nullptr;
+        p.conf_out = conf_out ? conf_out + (size_t)b * H * W : nullptr;
         kern<<<grid, NTHREADS, C::SMEM, st>>>(tmap, p);
     }
     return cds_check_launch("cds_conv3d_k3_roll");
@@ -395,6 +433,16 @@ int cds_conv3d_k3_roll(const void* in, const void* wgt_packed, const float* bias
     if (Cin == 8) return launch_roll<8, 8, 8>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     if (Cin == 16) return launch_roll<16, 8, 8>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
     return launch_roll<32, 8, 4>(in, wgt_packed, bias, B, D, H, W, relu, out, stream);
+}
+
+// The regulariser's tail in one kernel (models/module.py:303 prob head, models/model.py:85-92 softmax + depth_regression +
+// conf_regression): in [B, D, H, W, 8] fp16 -> logits [B, D, H, W] fp32 (kept: the confidence re-reads four of them),
+// depth [B, H, W] = sum_d softmax(logits)_d * samples_d, conf [B, H, W]; samples [B, D, H, W] per-pixel hypotheses.
+int cds_prob_head_regress(const void* in, const void* wgt_packed, const float* samples, int B, int D, int H, int W, float* logits,
+                          float* depth, float* conf, cudaStream_t stream) {
+    CDS_REQUIRE(in && wgt_packed && samples && logits && depth && conf, CDS_EARG, "cds_prob_head_regress: null pointer");
+    CDS_REQUIRE(cds_conv3d_k3_roll_supported(8, 1, D, H, W), CDS_EUNSUPPORTED, "cds_prob_head_regress: unsupported shape D=%d H=%d W=%d", D, H, W);
+    return launch_roll<8, 1, 8>(in, wgt_packed, nullptr, B, D, H, W, 0, logits, stream, samples, depth, conf);
 }
 
 }  // extern "C"

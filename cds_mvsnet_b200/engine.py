@@ -294,8 +294,11 @@ class Regulariser:
             return
         call("cds_deconv3d_k3s2", ptr(x), ptr(l.w), ptr(l.bias), ptr(skip), B, l.cin, l.cout, D, H, W, self.dt, ptr(out))
 
-    def run(self, buf: Buffers, tag, volume, B, D, H, W):
-        """volume [B,C/8,D,H,W,8] (channel-blocked) -> fp32 logits [B,D,H,W]."""
+    def run(self, buf: Buffers, tag, volume, B, D, H, W, samples=None, depth=None, conf=None):
+        """volume [B,C/8,D,H,W,8] (channel-blocked) -> fp32 logits [B,D,H,W].  With samples / depth / conf given and the rolling
+        prob head available, the tail (softmax over D, depth_regression, conf_regression: models/model.py:85-92) runs fused in
+        the prob head's epilogue and ``self.fused_tail`` is set."""
+        self.fused_tail = False
         if D % 8 or H % 8 or W % 8:
             raise RuntimeError(f"CostRegNet needs D, H, W divisible by 8 (got {D}x{H}x{W}); the reference fails the "
                                "same way at its skip additions (models/module.py:310-312)")
@@ -328,8 +331,16 @@ class Regulariser:
         m = B * D * H * W
         if (self.use_roll and st == torch.float16 and self.cw.prob_roll is not None
                 and _lib.LIB.load().cds_conv3d_k3_roll_supported(b, 1, D, H, W)):
-            kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_conv3d_k3_roll", ptr(u11), ptr(self.cw.prob_roll), None,
-                  B, b, 1, D, H, W, 0, ptr(logits))
+            # CDS_FUSED_TAIL=1: softmax + regression in the prob head's epilogue (cds_prob_head_regress).  Measured at cfg2: the
+            # three fused launches cost 0.09 ms MORE than prob head + cds_softmax_regress (the prob head is bound by its
+            # epilogue warps, which the exp / hypothesis loads lengthen), so the separate tail stays the default.
+            if samples is not None and depth is not None and conf is not None and os.environ.get("CDS_FUSED_TAIL", "0") == "1":
+                kcall(f"{tag}.prob_regress_tail", 2.0 * 27 * b * m, m * (b * _esize(st) + 8) + 8 * B * H * W, "cds_prob_head_regress",
+                      ptr(u11), ptr(self.cw.prob_roll), ptr(samples), B, D, H, W, ptr(logits), ptr(depth), ptr(conf))
+                self.fused_tail = True
+            else:
+                kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_conv3d_k3_roll", ptr(u11), ptr(self.cw.prob_roll), None,
+                      B, b, 1, D, H, W, 0, ptr(logits))
         elif (self.use_tc and st == torch.float16 and self.cw.prob_tc is not None
                 and _lib.LIB.load().cds_conv3d_k3_tc_supported(b, 1, D, H, W, 1)):
             kcall(f"{tag}.prob", 2.0 * 27 * b * m, m * (b * _esize(st) + 4), "cds_conv3d_k3_tc", ptr(u11), ptr(self.cw.prob_tc), None,
@@ -461,10 +472,11 @@ class CascadeEngine:
                   ptr(volume))
         nc = self._out_views[s][2]
         kcall(f"s{s}.nc_mean", 0, 4 * P * (2 * V + 1), "cds_nc_mean", ptr(ncsq[:VB]), ptr(ncsq[VB:]), V, B * h * w, ptr(nc))
-        logits = self.regs[s].run(buf, f"s{s}.cr", volume, B, D, h, w)
         depth, conf = self._out_views[s][0], self._out_views[s][1]
-        kcall(f"s{s}.softmax_regress", 0, 8 * D * P + 8 * P, "cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w,
-              ptr(depth), ptr(conf), None)
+        logits = self.regs[s].run(buf, f"s{s}.cr", volume, B, D, h, w, samples=samples, depth=depth, conf=conf)
+        if not self.regs[s].fused_tail:
+            kcall(f"s{s}.softmax_regress", 0, 8 * D * P + 8 * P, "cds_softmax_regress", ptr(logits), ptr(samples), 1, 0, B, D, h, w,
+                  ptr(depth), ptr(conf), None)
         return {"depth": depth, "photometric_confidence": conf, "norm_curv": nc}
 
     def _alloc_outputs(self, B, H, W):

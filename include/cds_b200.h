@@ -148,6 +148,12 @@ int cds_conv3d_k3_roll_supported(int Cin, int Cout, int D, int H, int W);
 int cds_conv3d_k3_roll_weight_halfs(int Cin, int Cout);
 int cds_conv3d_k3_roll(const void* in, const void* wgt_packed, const float* bias, int B, int Cin, int Cout, int D, int H, int W,
                        int relu, void* out, cudaStream_t stream);
+/* The regulariser's tail in ONE kernel: prob head (models/module.py:303) with softmax over D, depth_regression and
+ * conf_regression (models/model.py:85-92, models/module.py:373-391) fused into its epilogue.  in [B,D,H,W,8] fp16 (conv11's
+ * output), samples [B,D,H,W] fp32 per-pixel hypotheses -> depth, conf [B,H,W] fp32; logits [B,D,H,W] fp32 is still written
+ * (the confidence re-reads the four around the expected index).  Same results as cds_conv3d_k3_roll + cds_softmax_regress. */
+int cds_prob_head_regress(const void* in, const void* wgt_packed, const float* samples, int B, int D, int H, int W, float* logits,
+                          float* depth, float* conf, cudaStream_t stream);
 /* prob head: plain Conv3d(8,1,3,p=1,bias=False) (models/module.py:303) -> fp32 logits [B,D,H,W]. */
 int cds_prob_conv(const void* in, const float* wgt, int B, int Cin, int D, int H, int W, int dtype, float* logits,
                   cudaStream_t stream);

@@ -342,6 +342,35 @@ def test_costvol_stage3_tma_staged_vs_oracle(V, hw, regime):
     assert O.rel_l1(from_blocked(vol_out.float().cpu()), vol) < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(8, 24, 40), (48, 37, 150), (32, 64, 300)], ids=lambda v: "x".join(map(str, v)))
+def test_prob_head_fused_tail_matches_separate(pretrained_sd, shape):
+    """cds_prob_head_regress (softmax over D + depth / confidence regression in the prob head's epilogue) against the rolling
+    prob head followed by cds_softmax_regress: same arithmetic (logits and depth bit-identical); and both against torch."""
+    D, H, Wd = shape
+    torch.manual_seed(D)
+    B = 2
+    x = torch.relu(torch.randn(B, 8, D, H, Wd))
+    wp = pretrained_sd["cost_regularization.2.prob.weight"]
+    l = W.Conv3dWeights(8, 1, wp.permute(2, 3, 4, 1, 0).reshape(27, 8, 1).contiguous().to(DEV), torch.zeros(1, device=DEV))
+    packed = W.pack_conv3d_roll(l)
+    xb = cu(to_blocked(x)).half()
+    samples = cu(450 + 30 * torch.arange(D).float().reshape(1, D, 1, 1) + 5 * torch.rand(B, D, H, Wd)).contiguous()
+    logits_a = torch.empty(B, D, H, Wd, device=DEV); logits_b = torch.empty_like(logits_a)
+    depth_a = torch.empty(B, H, Wd, device=DEV); conf_a = torch.empty_like(depth_a)
+    depth_b = torch.full((B, H, Wd), float("nan"), device=DEV); conf_b = torch.full_like(depth_b, float("nan"))
+    call("cds_conv3d_k3_roll", ptr(xb), ptr(packed), None, B, 8, 1, D, H, Wd, 0, ptr(logits_a))
+    call("cds_softmax_regress", ptr(logits_a), ptr(samples), 1, 0, B, D, H, Wd, ptr(depth_a), ptr(conf_a), None)
+    call("cds_prob_head_regress", ptr(xb), ptr(packed), ptr(samples), B, D, H, Wd, ptr(logits_b), ptr(depth_b), ptr(conf_b))
+    torch.cuda.synchronize()
+    assert torch.equal(logits_a, logits_b)
+    assert torch.equal(depth_a, depth_b)
+    torch.testing.assert_close(conf_a, conf_b, rtol=1e-6, atol=1e-7)   # the window sum may contract into FMAs differently
+    ref_l = torch.nn.functional.conv3d(xb.float().cpu().permute(0, 1, 5, 2, 3, 4).reshape(B, 8, D, H, Wd), wp, padding=1)[:, 0]
+    pr = torch.softmax(ref_l, 1)
+    assert O.rel_l1(depth_b.cpu(), O.depth_regression(pr, samples.cpu())) < 1e-4
+    assert (conf_b.cpu() - O.conf_regression(pr)).abs().mean() < 2e-3
+
+
 def test_costvol_rejects_too_many_views():
     z = torch.zeros(16, device=DEV)
     with pytest.raises(RuntimeError, match="V="):
