@@ -454,7 +454,11 @@ class CascadeEngine:
             kcall(f"s{s}.costvol_entropy", 2.0 * 9 * C * D * P * V, V * P * (2 * C * fe + 4) + 4 * D * P, "cds_costvol_entropy",
                   ptr(ref_fea), ptr(src_fea), ptr(coef_s), ptr(samples), V, B, C, D, h, w, fdt, ptr(entropy))
         vis = buf.get(f"s{s}.vis", (V, B, h, w), f32)
-        if (self.use_tc and self.w.vis_tc and self.storage == torch.float16 and _lib.LIB.load().cds_visnet_tc_supported(h, w)):
+        # precise stage 1: the fp32 CUDA-core visibility net (its fp16 tensor-core form costs 1.5e-4 of final depth error on the
+        # noise input at cfg2 through the stage-to-stage amplification; at quarter resolution the fp32 form is 0.1 ms)
+        vis_precise = fea_f32 and os.environ.get("CDS_S0_VIS_F32", "1") != "0"
+        if (self.use_tc and not vis_precise and self.w.vis_tc and self.storage == torch.float16
+                and _lib.LIB.load().cds_visnet_tc_supported(h, w)):
             wgt, fp = self.w.vis_tc[s]
             kcall(f"s{s}.visnet", 9824.0 * P * V, 12 * P * V, "cds_visnet_tc", ptr(entropy), ptr(ncabs[:VB]), ptr(wgt), ptr(fp),
                   VB, h, w, ptr(vis))
