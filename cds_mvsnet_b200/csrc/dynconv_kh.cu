@@ -47,6 +47,15 @@ constexpr int NMW = 3;                 // MMA-issuing warps (one per branch; the
 constexpr int NSTG = 96;               // staging threads (warps 5-7)
 constexpr int NTHREADS = 512;          // warps: 0 TMA, 1-3 MMA, 4 idle, 5-7 staging, 8-11 / 12-15 epilogue sets
 constexpr int kEpiWarp0 = 8;
+// Column groups of NPAD = Cout + 3 curvature columns rounded up to 4 (12 / 20 / 36) instead of 16 (16 / 32 / 48): a quarter
+// to a third fewer B-operand bytes and math per MMA, and more output rows per TMEM tile (13 / 11 / 6 instead of 10 / 8 / 5:
+// fewer halo rows).  An M = 128 MMA needs N % 16 = 0, so a range of ng groups is issued with N = roundup16(ng * NPAD): the
+// up to 12 extra columns multiply either the zero padding behind the branch's last group or, for a range clipped at the
+// tile's last row, the next group's real weights -- and land in the first columns of the NEXT slot, which is therefore
+// always one the issuer already owns (it waits one slot ahead) and, at the tile's end, a spare slot nobody reads.
+constexpr bool KH_TIGHT = true;
+__host__ __device__ constexpr int kh_npad(int cout) { return KH_TIGHT ? (cout + 3 + 3) / 4 * 4 : (cout + 3 + 15) / 16 * 16; }
+__host__ __device__ constexpr int kh_ncols(int cout, int k) { return KH_TIGHT ? (k * kh_npad(cout) + 15) / 16 * 16 + 16 : k * kh_npad(cout); }
 
 template <int K0_, int K1_, int K2_, int CIN_, int COUT_, int TY_, bool SPLIT_>
 struct Kh {
@@ -60,11 +69,12 @@ struct Kh {
     static constexpr int KMAX = K2_ > K1_ ? (K2_ > K0_ ? K2_ : K0_) : (K1_ > K0_ ? K1_ : K0_);
     static constexpr int HMAX = (KMAX - 1) / 2;
     static constexpr int TXO = TX - 2 * HMAX;
-    static constexpr int NPAD = (COUT_ + 3 + 15) / 16 * 16;
+    static constexpr int NPAD = kh_npad(COUT_);
+    static constexpr int SLOTS = KH_TIGHT ? TY_ + 1 : TY_;      // accumulator slots per branch (+ the spare one)
     __host__ __device__ static constexpr int nj(int b) { return C8 == 1 ? (kb(b) + 1) / 2 : kb(b) * C8 / 2; }
-    __host__ __device__ static constexpr int nbf(int b) { return kb(b) * NPAD; }                  // full N of a branch
-    __host__ __device__ static constexpr int reg(int b) { return b * TY * NPAD; }                 // TMEM column base
-    static constexpr int ACC_COLS = NK * TY * NPAD;
+    __host__ __device__ static constexpr int nbf(int b) { return kh_ncols(COUT_, kb(b)); }        // columns of a branch's weight image
+    __host__ __device__ static constexpr int reg(int b) { return b * SLOTS * NPAD; }              // TMEM column base
+    static constexpr int ACC_COLS = NK * SLOTS * NPAD;
     static_assert(ACC_COLS <= 512, "accumulator tile exceeds TMEM");
     __host__ __device__ static constexpr uint32_t b_img(int b) { return (uint32_t)nj(b) * 2 * nbf(b) * 16; }   // one image
     __host__ __device__ static constexpr uint32_t b_off(int b, int lo) {
@@ -177,7 +187,8 @@ __device__ __forceinline__ void issue_branch(const KhParams& p, int R, int y0, u
     constexpr int hb = C::hb(B);
     const int ylo = max(y0, R - hb), yhi = min(min(y0 + C::TY - 1, p.H - 1), R + hb);
     if (ylo > yhi) return;   // warp-uniform
-    const uint32_t g0 = (uint32_t)(ylo - (R - hb)) * C::NPAD, n = (uint32_t)(yhi - ylo + 1) * C::NPAD;   // column range of the weights
+    const uint32_t g0 = (uint32_t)(ylo - (R - hb)) * C::NPAD;                                      // first column of the weights
+    const uint32_t n = ((uint32_t)(yhi - ylo + 1) * C::NPAD + 15u) & ~15u;                         // N % 16 = 0 (see KH_TIGHT)
     const uint32_t d_col = tmem + (uint32_t)C::reg(B) + (uint32_t)(ylo - y0) * C::NPAD;
     const uint32_t idesc = tc::instr_desc_f16(128, 0) | ((n >> 3) << 17);
     issue_prod<C, W, B, 0>(a_row16, b16, d_col, g0, idesc, elected, std::make_integer_sequence<int, C::nj(B)>{});
@@ -195,7 +206,23 @@ __device__ __forceinline__ void issue_row(const KhParams& p, int R, int y0, uint
 __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr), "r"(0u) : "memory");
 }
+__device__ __forceinline__ void tmem_zero4(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(taddr), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+// this warp's lanes of one accumulator slot (every branch region) <- 0
+template <class C>
+__device__ __forceinline__ void zero_slot(uint32_t taddr) {
+#pragma unroll
+    for (int b = 0; b < C::NK; ++b) {
+#pragma unroll
+        for (int c = 0; c + 8 <= C::NPAD; c += 8) tmem_zero8(taddr + C::reg(b) + c);
+        if constexpr (C::NPAD % 8 != 0) tmem_zero4(taddr + C::reg(b) + C::NPAD - 4);
+    }
+}
 
 template <class C, int GRP>
 __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_constant__ CUtensorMap tmap, const KhParams p) {
@@ -298,13 +325,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
             const Tile q = tile_of<C>(p, t);
             const int r0 = max(q.y0 - HMAX, 0), r1 = min(q.y0 + TY - 1 + HMAX, p.H - 1);
             const int ylast = min(q.y0 + TY - 1, p.H - 1);
+            int waited = 0;   // slots [0, waited) of this tile have been handed over (drained and zeroed) by the epilogue
 #pragma unroll 1
             for (int R = r0; R <= r1; ++R, ++rc) {
                 const uint32_t slot = rc % NR;
-                // accumulator slots touched for the first time with row R must have been drained (and zeroed) by the epilogue
+                // Row R writes the slots up to y = R + HMAX -- and, with tight column groups, the first columns of the slot
+                // after its range (N is rounded up to 16): every slot up to R + HMAX + 1 must have been handed over, including
+                // the first unused slot of a partial tile.
                 {
-                    const int ya = R == 0 ? q.y0 : R + HMAX, yb = R == 0 ? min(ylast, HMAX) : R + HMAX;
-                    for (int y = max(ya, q.y0); y <= min(yb, ylast); ++y) tc::mbar_wait(acc_empty + (y - q.y0), (it & 1) ^ 1);
+                    const int upto = min(R + HMAX + (KH_TIGHT ? 1 : 0) - q.y0, TY - 1);
+                    for (; waited <= upto; ++waited) tc::mbar_wait(acc_empty + waited, (it & 1) ^ 1);
                 }
                 tc::mbar_wait((staged ? ring_ready : ring_full) + slot, (rc / NR) & 1);
                 tc::tc_fence_after();
@@ -325,8 +355,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
             // be gated by the epilogue's drain of the PREVIOUS tile, like a first touch: an ungated arrival lets this side run
             // two phases ahead, and a parity wait cannot tell phase k from phase k+2 (the epilogue would wait forever)
             for (int s = ylast - q.y0 + 1; s < TY; ++s) {
-                tc::mbar_wait(acc_empty + s, (it & 1) ^ 1);
-                if (elected) mbar_arrive(acc_full + s);
+                if (s >= waited) tc::mbar_wait(acc_empty + s, (it & 1) ^ 1);
+                // (tight column groups: the first unused slot caught rounding columns and is cleaned by the epilogue -- which
+                // must not start before those MMAs have completed: a commit, not a plain arrival)
+                if (elected) {
+                    if constexpr (KH_TIGHT) tc::mma_commit(acc_full + s);
+                    else mbar_arrive(acc_full + s);
+                }
             }
             __syncwarp();
         }
@@ -475,15 +510,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                 tc::mbar_wait(acc_full + s, it & 1);
                 tc::tc_fence_after();
                 const int gy = q.y0 + s;
-                if (gy >= p.H) {   // slot not used by this tile (never accumulated into: still zero)
-                    if ((!shared || set == 0) && lane == 0) mbar_arrive(acc_empty + s);
+                const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * NPAD;
+                if (gy >= p.H) {
+                    // slot not used by this tile; with tight column groups the first unused one caught the rounding columns of
+                    // the last row's ranges (real weights): clean it before it is handed back
+                    if (!shared || set == 0) {
+                        if constexpr (KH_TIGHT) {
+                            zero_slot<C>(taddr);
+                            tmem_st_wait();
+                            tc::tc_fence_before();
+                            __syncwarp();
+                        }
+                        if (lane == 0) mbar_arrive(acc_empty + s);
+                    }
                     continue;
                 }
-                const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)s * NPAD;
                 // 1. curvature columns of every branch
-                uint32_t ar[NK][8];
+                uint32_t ar[NK][4];
 #pragma unroll
-                for (int b = 0; b < NK; ++b) tc::tmem_ld8_nowait(taddr + C::reg(b) + COUT, ar[b]);
+                for (int b = 0; b < NK; ++b) tmem_ld4_nowait(taddr + C::reg(b) + COUT, ar[b]);
                 tc::tmem_ld_wait();
                 const bool valid = col_ok;
                 float wgt[NIT][NK], ncv[NIT];
@@ -536,10 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                         // slot back ZEROED -- every MMA accumulates, whichever issuer's MMA arrives first
                         if (shared) named_barrier(2, 256);
                         if (!shared || set == 0) {
-#pragma unroll
-                            for (int b = 0; b < NK; ++b)
-#pragma unroll
-                                for (int c = 0; c < NPAD; c += 8) tmem_zero8(taddr + C::reg(b) + c);
+                            zero_slot<C>(taddr);
                             tmem_st_wait();
                             tc::tc_fence_before();
                             __syncwarp();
@@ -660,14 +702,19 @@ int cds_dynamic_conv_kh_supported(int Cin, int Cout, int H, int W, int num_kerne
 
 // fp16 elements of the packed weight image: per branch two images (weights, residuals) of nj steps x 2 k-chunks x k*NPAD columns x 8
 int cds_dynamic_conv_kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks) {
-    const int c8 = Cin / 8, npad = (Cout + 3 + 15) / 16 * 16;
+    const int c8 = Cin / 8;
     long long n = 0;
     for (int b = 0; b < num_kernels; ++b) {
         const int nj = c8 == 1 ? (ks[b] + 1) / 2 : ks[b] * c8 / 2;
-        n += 2ll * nj * 2 * ks[b] * npad * 8;
+        n += 2ll * nj * 2 * kh_ncols(Cout, ks[b]) * 8;
     }
     return (int)n;
 }
+
+// layout of the packed weight images (the host packer asks instead of restating it): columns per kernel-row group, columns
+// of one image of a k x k branch (groups, then zero padding)
+int cds_dynamic_conv_kh_group_cols(int Cout) { return kh_npad(Cout); }
+int cds_dynamic_conv_kh_image_cols(int Cout, int k) { return kh_ncols(Cout, k); }
 
 // Same contract as cds_dynamic_conv_tc (+ the pair batch of cds_dynamic_conv_tc_pairs when pair_v > 0): x fp16 [planes *
 // n_images, H, W, Cin] (split_in: the residual plane follows), item i reads image img_index[i]; out_raw / out_lo fp16
@@ -683,6 +730,8 @@ int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const
     const int lid = kh_layer_id(Cin, Cout, num_kernels, kernel_sizes);
     CDS_REQUIRE(lid != 0 && W >= 8, CDS_EUNSUPPORTED, "cds_dynamic_conv_kh: unsupported layer (Cin=%d Cout=%d W=%d)", Cin, Cout, W);
     CDS_REQUIRE(!split_in || in_stats, CDS_EARG, "cds_dynamic_conv_kh: split-precision input needs the input statistics");
+    // output rows per TMEM tile: 512 columns / (branches x (rows + spare) x group columns)
+    constexpr int TY8 = KH_TIGHT ? 13 : 10, TY16 = KH_TIGHT ? 11 : 8, TY32 = KH_TIGHT ? 6 : 5;
     KhParams p{};
     p.img_index = img_index; p.in_stats = in_stats; p.epipole = epipole; p.wgt = (const __half*)wgt_packed; p.bias = bias; p.gate = gate;
     p.out_raw = (__half*)out_raw; p.out_lo = (__half*)out_lo; p.out_stats = out_stats; p.norm_curv = norm_curv; p.nc_sq = nc_sq;
@@ -691,18 +740,18 @@ int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const
     if (pair_v > 0) {
         CDS_REQUIRE(lid == 1 && !in_stats && !split_in && img_index && n == 2 * pair_v * pair_b, CDS_EUNSUPPORTED,
                     "cds_dynamic_conv_kh: the pair batch is implemented for the image layer (3,7,11)");
-        return launch_kh<Kh<3, 7, 11, 8, 8, 10, false>, 4>(x, p, stream);
+        return launch_kh<Kh<3, 7, 11, 8, 8, TY8, false>, 4>(x, p, stream);
     }
     if (split_in) {
         CDS_REQUIRE(lid != 1, CDS_EUNSUPPORTED, "cds_dynamic_conv_kh: the image layer takes its residual in spare operand channels");
-        if (lid == 2) return launch_kh<Kh<3, 5, 7, 8, 8, 10, true>, 1>(x, p, stream);
-        if (lid == 4) return launch_kh<Kh<3, 5, 0, 16, 16, 8, true>, 1>(x, p, stream);
-        return launch_kh<Kh<1, 3, 0, 32, 32, 5, true>, 1>(x, p, stream);
+        if (lid == 2) return launch_kh<Kh<3, 5, 7, 8, 8, TY8, true>, 1>(x, p, stream);
+        if (lid == 4) return launch_kh<Kh<3, 5, 0, 16, 16, TY16, true>, 1>(x, p, stream);
+        return launch_kh<Kh<1, 3, 0, 32, 32, TY32, true>, 1>(x, p, stream);
     }
-    if (lid == 1) return launch_kh<Kh<3, 7, 11, 8, 8, 10, false>, 1>(x, p, stream);
-    if (lid == 2) return launch_kh<Kh<3, 5, 7, 8, 8, 10, false>, 1>(x, p, stream);
-    if (lid == 4) return launch_kh<Kh<3, 5, 0, 16, 16, 8, false>, 1>(x, p, stream);
-    return launch_kh<Kh<1, 3, 0, 32, 32, 5, false>, 1>(x, p, stream);
+    if (lid == 1) return launch_kh<Kh<3, 7, 11, 8, 8, TY8, false>, 1>(x, p, stream);
+    if (lid == 2) return launch_kh<Kh<3, 5, 7, 8, 8, TY8, false>, 1>(x, p, stream);
+    if (lid == 4) return launch_kh<Kh<3, 5, 0, 16, 16, TY16, false>, 1>(x, p, stream);
+    return launch_kh<Kh<1, 3, 0, 32, 32, TY32, false>, 1>(x, p, stream);
 }
 
 }  // extern "C"

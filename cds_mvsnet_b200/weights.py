@@ -149,21 +149,30 @@ def pack_dynamic_conv_tc(w: DynWeights) -> torch.Tensor:
     return out.to(torch.float16).contiguous().to(w.w_conv.device)
 
 
+def kh_layout(cout: int, k: int) -> tuple[int, int]:
+    """(columns of one kernel-row group, columns of one image of a k x k branch) of csrc/dynconv_kh.cu -- asked of the library,
+    which owns the layout."""
+    from . import _lib
+    lib = _lib.LIB.load()
+    return int(lib.cds_dynamic_conv_kh_group_cols(cout)), int(lib.cds_dynamic_conv_kh_image_cols(cout, k))
+
+
 def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
     """fp16 B-operand images for csrc/dynconv_kh.cu (kernel rows folded into N; Cin 3 is padded to 8 with the image's
     residual channels).
 
     Per branch b (kernel k, in the order of ``ksizes``) two images -- the fp16-rounded weights, then their fp16 rounding
-    residuals -- each ``nj`` steps of [k-chunk 2][k*NPAD/8][8 n][8 k]:  NPAD = roundup16(Cout + 3); column n = g*NPAD + c with
-    column group g <-> kernel row dy = k-1-g (so that group g feeds output row y = R - h + g of input row R), c < Cout the
-    feature weights, c in [Cout, Cout+3) the curvature weights (a, b, c), the rest zero.  K: Cin <= 8: step j = horizontal
-    taps (2j, 2j+1) x 8 channels (zero past the kernel); Cin > 8: tap (2j)//C8, channel chunks (2j)%C8 and +1."""
+    residuals -- each ``nj`` steps of [k-chunk 2][NCOLS/8][8 n][8 k].  Column n = g*NPAD + c with column group g <-> kernel
+    row dy = k-1-g (so that group g feeds output row y = R - h + g of input row R), c < Cout the feature weights, c in
+    [Cout, Cout+3) the curvature weights (a, b, c), the rest -- and the columns from k*NPAD to NCOLS -- zero; NPAD and NCOLS
+    come from ``kh_layout``.  K: Cin <= 8: step j = horizontal taps (2j, 2j+1) x 8 channels (zero past the kernel); Cin > 8:
+    tap (2j)//C8, channel chunks (2j)%C8 and +1."""
     cin, cout = w.cin, w.cout
     c8 = max(1, cin // 8)
     att, conv = w.w_att.detach().cpu().double(), w.w_conv.detach().cpu().double()
-    npad = (cout + 3 + 15) // 16 * 16
     parts, t0 = [], 0
     for k in w.ksizes:
+        npad, ncols = kh_layout(cout, k)
         full = torch.zeros(k, k, c8 * 8, npad, dtype=torch.float64)           # [dy, dx, cin, n]
         for dy in range(k):
             for dx in range(k):
@@ -176,7 +185,7 @@ def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
         hi = full.to(torch.float16).to(torch.float64)
         nj = (k + 1) // 2 if c8 == 1 else k * c8 // 2
         for img_w in (hi, full - hi):
-            img = torch.zeros(nj, 2, k * npad // 8, 8, 8, dtype=torch.float64)
+            img = torch.zeros(nj, 2, ncols, 8, dtype=torch.float64)             # [step, k-chunk, column n, 8 k]
             for j in range(nj):
                 for q in range(2):
                     if c8 == 1:
@@ -186,8 +195,7 @@ def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
                     if dx >= k:
                         continue
                     for g in range(k):
-                        blk = img_w[k - 1 - g, dx, ch * 8:(ch + 1) * 8, :]           # [8 k, NPAD]
-                        img[j, q, g * npad // 8:(g + 1) * npad // 8] = blk.t().reshape(npad // 8, 8, 8)
+                        img[j, q, g * npad:(g + 1) * npad] = img_w[k - 1 - g, dx, ch * 8:(ch + 1) * 8, :].t()
             parts.append(img.reshape(-1))
     return torch.cat(parts).to(torch.float16).contiguous().to(w.w_conv.device)
 

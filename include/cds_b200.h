@@ -218,6 +218,10 @@ int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index,
  * pack_dynamic_conv_kh): weights AND their fp16 rounding residuals, multiplied as separate accumulating products. */
 int cds_dynamic_conv_kh_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* kernel_sizes);
+/* layout of the packed images: columns of one kernel-row group (Cout + 3 curvature columns, rounded up), columns of one image
+ * of a k x k branch (k groups + zero padding) */
+int cds_dynamic_conv_kh_group_cols(int Cout);
+int cds_dynamic_conv_kh_image_cols(int Cout, int k);
 int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const double* in_stats, int in_act, const float* epipole,
                         float epi_scale, const void* wgt_packed, const float* bias, const float* gate, int n, int Cin, int Cout, int H,
                         int W, int num_kernels, const int* kernel_sizes, float temperature, int split_in, void* out_raw, void* out_lo,
