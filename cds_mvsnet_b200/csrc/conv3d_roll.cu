@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_roll_kernel(const __grid_c
             const int x0 = max(0, min((tile % p.xt) * TXO, p.W - TXO));
             const int y0 = (tile / p.xt) * TY;
             const int x = x0 - 1 + r;
-            const bool col_ok = r >= 1 && r <= TXO && x < p.W;
+            // the last column strip is shifted left to stay inside the volume and overlaps its neighbour: one owner per voxel
+            // (the kw fold associates differently at the warp seams, so two owners would differ in the last bit)
+            const bool col_ok = r >= 1 && r <= TXO && x < p.W && x >= (tile % p.xt) * TXO;
 #pragma unroll 1
             for (int d = 0; d < p.D; ++d, ++planes, uc0 += TY) {
                 float* xb = xch + (planes & 1) * (TY * 4 * 2 * COUT);

@@ -681,13 +681,15 @@ int launch_kh(const void* x, KhParams p, cudaStream_t st) {
     return cds_check_launch("cds_dynamic_conv_kh");
 }
 
-// layer shapes covered (the trunk of the feature extractor, models/module.py:211-221); 0 = not covered
+// layer shapes covered (the trunk of the feature extractor and the three output heads, models/module.py:211-231); 0 = not covered
 int kh_layer_id(int Cin, int Cout, int nk, const int* ks) {
     if (!ks) return 0;
     if (Cin == 8 && Cout == 8 && nk == 3 && ks[0] == 3 && ks[1] == 7 && ks[2] == 11) return 1;   // conv00 (image padded to 8)
     if (Cin == 8 && Cout == 8 && nk == 3 && ks[0] == 3 && ks[1] == 5 && ks[2] == 7) return 2;    // conv01
     if (Cin == 16 && Cout == 16 && nk == 2 && ks[0] == 3 && ks[1] == 5) return 4;                // conv10, conv11
     if (Cin == 32 && Cout == 32 && nk == 2 && ks[0] == 1 && ks[1] == 3) return 6;                // conv20, conv21, out1
+    if (Cin == 16 && Cout == 16 && nk == 2 && ks[0] == 1 && ks[1] == 3) return 7;                // out2
+    if (Cin == 8 && Cout == 8 && nk == 2 && ks[0] == 1 && ks[1] == 3) return 8;                  // out3
     return 0;
 }
 
@@ -732,6 +734,7 @@ int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const
     CDS_REQUIRE(!split_in || in_stats, CDS_EARG, "cds_dynamic_conv_kh: split-precision input needs the input statistics");
     // output rows per TMEM tile: 512 columns / (branches x (rows + spare) x group columns)
     constexpr int TY8 = KH_TIGHT ? 13 : 10, TY16 = KH_TIGHT ? 11 : 8, TY32 = KH_TIGHT ? 6 : 5;
+    constexpr int TY8H = KH_TIGHT ? 20 : 15;   // two-branch head of 8 channels (out3)
     KhParams p{};
     p.img_index = img_index; p.in_stats = in_stats; p.epipole = epipole; p.wgt = (const __half*)wgt_packed; p.bias = bias; p.gate = gate;
     p.out_raw = (__half*)out_raw; p.out_lo = (__half*)out_lo; p.out_stats = out_stats; p.norm_curv = norm_curv; p.nc_sq = nc_sq;
@@ -744,6 +747,7 @@ int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const
     }
     if (split_in) {
         CDS_REQUIRE(lid != 1, CDS_EUNSUPPORTED, "cds_dynamic_conv_kh: the image layer takes its residual in spare operand channels");
+        CDS_REQUIRE(lid < 7, CDS_EUNSUPPORTED, "cds_dynamic_conv_kh: the stage-2/3 heads take single-plane input");
         if (lid == 2) return launch_kh<Kh<3, 5, 7, 8, 8, TY8, true>, 1>(x, p, stream);
         if (lid == 4) return launch_kh<Kh<3, 5, 0, 16, 16, TY16, true>, 1>(x, p, stream);
         return launch_kh<Kh<1, 3, 0, 32, 32, TY32, true>, 1>(x, p, stream);
@@ -751,6 +755,8 @@ int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const
     if (lid == 1) return launch_kh<Kh<3, 7, 11, 8, 8, TY8, false>, 1>(x, p, stream);
     if (lid == 2) return launch_kh<Kh<3, 5, 7, 8, 8, TY8, false>, 1>(x, p, stream);
     if (lid == 4) return launch_kh<Kh<3, 5, 0, 16, 16, TY16, false>, 1>(x, p, stream);
+    if (lid == 7) return launch_kh<Kh<1, 3, 0, 16, 16, TY16, false>, 1>(x, p, stream);
+    if (lid == 8) return launch_kh<Kh<1, 3, 0, 8, 8, TY8H, false>, 1>(x, p, stream);
     return launch_kh<Kh<1, 3, 0, 32, 32, TY32, false>, 1>(x, p, stream);
 }
 

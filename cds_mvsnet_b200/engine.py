@@ -70,6 +70,7 @@ class FeatureExtractor:
         # 2.6e-3 -> 9e-4).  CDS_SPLIT=0 turns it off (diagnostics only).
         self.split_precision = os.environ.get("CDS_SPLIT", "1") != "0"
         self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
+        self.use_rows = os.environ.get("CDS_S2_ROWS", "1") != "0"   # stride-2 layers on the row-streaming kernel (conv2d_s2rows.cu)
         # inner1/inner2 (1x1 conv over the concatenation): the 2x2-block CUDA-core form (fp32 math, 0.154 / 0.133 ms at cfg2) beats the
         # gather-form tensor-core kernel (0.289 / 0.156 ms) on this 24- / 48-deep contraction; CDS_TC_INNER=1 selects the latter
         self.tc_inner = os.environ.get("CDS_TC_INNER", "0") != "0"
@@ -125,6 +126,11 @@ class FeatureExtractor:
         e = _esize(self.storage)
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
         _lib.set_tag("feat." + name, (2.0 * 9 * cin * cout * n * Ho * Wo, float(n * (H * W * cin + Ho * Wo * cout) * e)))
+        if (self.use_tc2d and self.use_rows and self.storage == torch.float16 and name in self.fw.rows
+                and _lib.LIB.load().cds_conv2d_3x3s2_rows_supported(cin, cout, H, W)):
+            call("cds_conv2d_3x3s2_rows", ptr(x), ptr(x_lo), ptr(x_stats), ACT_LRELU, ptr(self.fw.rows[name]), n, cin, cout, H, W,
+                 ptr(out[0]), ptr(out[1]) if split else None, ptr(out_stats))
+            return
         if (self.use_tc2d and self.storage == torch.float16 and name in self.fw.tc
                 and _lib.LIB.load().cds_conv2d_3x3s2_tc_supported(cin, cout)):
             call("cds_conv2d_3x3s2_tc", ptr(x), ptr(x_lo), ptr(x_stats), ACT_LRELU, ptr(self.fw.tc[name]), n, cin, cout, H, W, ptr(out[0]),
@@ -404,6 +410,13 @@ class CascadeEngine:
         self.overlap = os.environ.get("CDS_OVERLAP", "1") != "0"   # stage 1 on a side stream under the feature heads
         self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.launches = 0
+
+    def clone(self) -> "CascadeEngine":
+        """A second cascade over the SAME packed weights with buffers, side stream and CUDA graph of its own: lets two depth maps
+        be in flight on two streams (the tails and small grids of one map's kernels leave SMs idle that the other fills:
+        measured +6 % maps/s at cfg2, streaming.DepthMapStream)."""
+        return CascadeEngine(self.w, self.ndepths, self.ratios, self.storage, self.device,
+                             refine_weights=self.refiner.rw if self.refiner is not None else None)
 
     # -- pieces -------------------------------------------------------------------------------
     def camera_setup(self, proj_matrices, B, N):

@@ -1,21 +1,23 @@
-"""Double-buffered host <-> device streaming around ``CDSMVSNet``: the way a depth-map job (the loop of the
-reference's test.py:197-248, one batch per reference view) is fed on a B200.
+"""Pipelined host <-> device streaming around ``CDSMVSNet``: the way a depth-map job (the loop of the reference's
+test.py:197-248, one batch per reference view) is fed on a B200.
 
-One depth map moves ~114 MB of images in and ~30 MB of maps out; on one stream that is 2.5 ms of PCIe time
-against ~13 ms of kernels.  Here the upload of work item i+1 and the download of item i-1 run on their own
-streams while item i computes, so the job runs at the speed of the kernels:
+One depth map moves ~28 MB of 8-bit images in and ~30 MB of maps out; on one stream that is ~1.2 ms of PCIe time
+against ~11 ms of kernels.  Here the upload of work item i+1 and the download of item i-1 run on their own
+streams while item i computes, and ``in_flight`` (default 2) work items compute at the same time, each on a cascade
+engine and a stream of its own: one map's kernels leave SMs idle (tails of persistent kernels, the small grids of
+the deep regulariser levels) that the other map's kernels fill -- measured +6 % maps/s at cfg2 over one map at a time.
 
     stream = DepthMapStream(model, temperature=0.01)
-    t_prev = None
+    pending = []
     for item in work_list:                       # item = (imgs, proj_matrices, depth_values) on the HOST
-        t = stream.submit(*item)
-        if t_prev is not None:
-            consume(stream.result(t_prev))       # host tensors (pinned), valid until two submits later
-        t_prev = t
-    consume(stream.result(t_prev))
+        pending.append(stream.submit(*item))
+        if len(pending) > stream.in_flight:
+            consume(stream.result(pending.pop(0)))   # host tensors (pinned), valid until `depth` submits later
+    for t in pending:
+        consume(stream.result(t))
 
-Every numerical step is still ``model.engine().forward`` (the CUDA kernels); this module only owns streams, events
-and staging buffers.
+Every numerical step is still ``CascadeEngine.forward`` (the CUDA kernels); this module only owns streams, events,
+staging buffers and the extra engines (which share the model's packed weights).
 """
 from __future__ import annotations
 
@@ -50,14 +52,29 @@ def _flatten(out):
 
 
 class DepthMapStream:
-    def __init__(self, model, temperature=0.001, depth=2, use_graph=True):
+    def __init__(self, model, temperature=0.001, depth=None, use_graph=True, in_flight=2):
         self.model = model
         self.use_graph = use_graph      # replay the forward as one CUDA graph (captured on the first item of a shape)
         self.temperature = float(temperature)
+        self.in_flight = max(1, int(in_flight))            # work items computing at the same time (one engine + stream each)
+        depth = self.in_flight + 1 if depth is None else int(depth)
+        if depth < self.in_flight:
+            raise ValueError("depth (buffered work items) must be at least in_flight")
         self.slots = [_Slot() for _ in range(depth)]
         self.n = 0
         self.s_in = torch.cuda.Stream()
         self.s_out = torch.cuda.Stream()
+        self.s_comp = [torch.cuda.Stream() for _ in range(self.in_flight)] if self.in_flight > 1 else [None]
+        self._base = None               # the model's own engine the extra ones were cloned from
+        self._extra = []
+
+    def _engine(self, k, dev):
+        """Engine of compute lane k: the model's own for lane 0, clones over the same packed weights for the others (re-made
+        when the model re-packs its weights)."""
+        base = self.model.engine(dev)
+        if base is not self._base:
+            self._base, self._extra = base, [base.clone() for _ in range(self.in_flight - 1)]
+        return base if k == 0 else self._extra[k - 1]
 
     @staticmethod
     def _signature(imgs, proj_matrices, depth_values):
@@ -82,7 +99,11 @@ class DepthMapStream:
         if imgs.is_cuda:
             raise ValueError("DepthMapStream.submit takes host tensors (use model(...) for device-resident inputs)")
         dev = next(self.model.parameters()).device
-        compute = torch.cuda.current_stream(dev)
+        lane = self.n % self.in_flight
+        caller = torch.cuda.current_stream(dev)
+        compute = caller if self.in_flight == 1 else self.s_comp[lane]
+        if compute is not caller:
+            compute.wait_stream(caller)     # work the caller queued before this submit stays ahead of it
         slot = self.slots[self.n % len(self.slots)]
         img_dtype = torch.uint8 if imgs.dtype == torch.uint8 else torch.float32
         sig = self._signature(imgs, proj_matrices, depth_values)
@@ -109,11 +130,26 @@ class DepthMapStream:
                 slot.dev_in[1][k].copy_(v, non_blocking=True)
             slot.dev_in[2].copy_(depth_values, non_blocking=True)
             slot.ev_in.record(self.s_in)
-        # ---- kernels on the caller's stream
+        # ---- kernels: on the caller's stream (in_flight = 1) or on this lane's stream and engine
         compute.wait_event(slot.ev_in)
-        engine = self.model.engine(dev)
+        engine = self._engine(lane, dev)
         run = engine.forward_graph if self.use_graph else engine.forward
-        out = run(slot.dev_in[0], slot.dev_in[1], slot.dev_in[2], self.temperature)
+        with torch.cuda.stream(compute):
+            out = run(slot.dev_in[0], slot.dev_in[1], slot.dev_in[2], self.temperature)
+            self._stage_out(slot, engine, out, compute)
+        # ---- download on its own stream
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot.ev_done)
+            for d, h in zip(slot.dev_out, slot.host_pack):
+                if d is not None:
+                    h.copy_(d, non_blocking=True)
+            slot.ev_out.record(self.s_out)
+        slot.used = True
+        ticket = self.n
+        self.n += 1
+        return ticket
+
+    def _stage_out(self, slot, engine, out, compute):
         # the engine keeps every result map in ONE packed buffer (+ the refined depth when refine=True): one staging copy and
         # one download per item; the host-side dict is a set of views of the pinned copy
         pack = engine._out_pack
@@ -129,21 +165,10 @@ class DepthMapStream:
         if refined is not None:
             slot.dev_out[1].copy_(refined, non_blocking=True)
         slot.ev_done.record(compute)
-        # ---- download on its own stream
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(slot.ev_done)
-            for d, h in zip(slot.dev_out, slot.host_pack):
-                if d is not None:
-                    h.copy_(d, non_blocking=True)
-            slot.ev_out.record(self.s_out)
-        slot.used = True
-        ticket = self.n
-        self.n += 1
-        return ticket
 
     def result(self, ticket):
         """Block until work item ``ticket`` is on the host; returns {"stageK.depth" | ".photometric_confidence" | ".norm_curv"}
-        pinned host tensors, valid until ``depth`` further submits."""
+        pinned host tensors, valid until ``depth`` (default in_flight + 1) further submits."""
         if ticket < self.n - len(self.slots) or ticket >= self.n:
             raise ValueError(f"ticket {ticket} is no longer (or not yet) buffered")
         slot = self.slots[ticket % len(self.slots)]

@@ -25,7 +25,9 @@ DYN_LAYERS = {
     "out1": (32, 32, (1, 3), "feature.out1"), "out2": (16, 16, (1, 3), "feature.out2"),
     "out3": (8, 8, (1, 3), "feature.out3"),
 }
-# trunk layers (image -> stage-1 feature) that run on csrc/dynconv_kh.cu; CDS_KH_LAYERS overrides (diagnostics)
+# DynamicConv layers that run on csrc/dynconv_kh.cu: the trunk image -> stage-1 feature.  The kernel also covers the stage-2/3
+# heads (out2, out3), but its eight epilogue warps per SM are the bound of such light layers: measured 0.245 / 0.505 ms against
+# 0.181 / 0.318 ms of csrc/dynconv_tc.cu (several small CTAs per SM).  CDS_KH_LAYERS overrides (diagnostics)
 KH_LAYERS = tuple(n for n in __import__("os").environ.get("CDS_KH_LAYERS", "conv00,conv01,conv10,conv11,conv20,conv21,out1").split(",") if n)
 COSTREG_CONVS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
 COSTREG_DECONVS = ("conv7", "conv9", "conv11")
@@ -462,6 +464,28 @@ def pack_conv2d_gtc(w: torch.Tensor) -> torch.Tensor:
     return img.to(dtype=torch.float16).contiguous()
 
 
+def pack_conv2d_s2rows(w: torch.Tensor) -> torch.Tensor:
+    """fp16 B-operand images for csrc/conv2d_s2rows.cu from tap-major weights [9, Cin, Cout] of a 3x3 stride-2 conv:
+    [kernel row dy][image][k-chunk 2][N/8][8 n][8 k], N = 2*Cout (weights | fp16 rounding residuals).  Cin 8: image 0 = taps
+    (dx 0, dx 2) -- the odd-phase pixels left and right --, image 1 = (dx 1, dx 1): the even pixel's value and residual slabs
+    share one weight block; Cin 16: image dx = the tap's channel chunks (0, 1)."""
+    taps, ci, co = w.shape
+    assert taps == 9 and ci in (8, 16)
+    N = 2 * co
+    w = w.detach().cpu().to(torch.float64)
+    blk = lambda t, c: _hi_lo_columns(w[t, c * 8:(c + 1) * 8, :]).t().reshape(N // 8, 8, 8)
+    nimg = 2 if ci == 8 else 3
+    img = torch.zeros(3, nimg, 2, N // 8, 8, 8, dtype=torch.float64)
+    for dy in range(3):
+        if ci == 8:
+            img[dy, 0, 0], img[dy, 0, 1] = blk(dy * 3 + 0, 0), blk(dy * 3 + 2, 0)
+            img[dy, 1, 0], img[dy, 1, 1] = blk(dy * 3 + 1, 0), blk(dy * 3 + 1, 0)
+        else:
+            for dx in range(3):
+                img[dy, dx, 0], img[dy, dx, 1] = blk(dy * 3 + dx, 0), blk(dy * 3 + dx, 1)
+    return img.to(dtype=torch.float16).contiguous()
+
+
 @dataclass
 class FeatureWeights:
     dyn: dict             # name -> DynWeights
@@ -470,6 +494,7 @@ class FeatureWeights:
     inner1: torch.Tensor  # [48,16]
     inner2: torch.Tensor  # [24,8]
     tc: dict = field(default_factory=dict)   # name -> fp16 tensor-core operand image (csrc/conv2d_gtc.cu)
+    rows: dict = field(default_factory=dict)   # stride-2 layers: operand images of csrc/conv2d_s2rows.cu
 
 
 def pack_feature(sd, device) -> FeatureWeights:
@@ -482,6 +507,7 @@ def pack_feature(sd, device) -> FeatureWeights:
                         pack_conv2d(sd, "feature.downsample2.conv.weight", device),
                         pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16),
                         pack_conv2d(sd, "feature.inner2.conv.weight", device).reshape(24, 8))
+    fw.rows = {"downsample1": pack_conv2d_s2rows(fw.downsample1).to(device), "downsample2": pack_conv2d_s2rows(fw.downsample2).to(device)}
     fw.tc = {"downsample1": pack_conv2d_gtc(fw.downsample1).to(device), "downsample2": pack_conv2d_gtc(fw.downsample2).to(device),
              "inner1": pack_conv2d_gtc(fw.inner1.reshape(1, 48, 16)).to(device),
              "inner2": pack_conv2d_gtc(fw.inner2.reshape(1, 24, 8)).to(device)}

@@ -242,6 +242,14 @@ int cds_conv2d_3x3s2_tc_weight_halfs(int Cin, int Cout);
 /* in_lo (optional, shape of in): the fp16 rounding residual plane of in; out_lo (optional, shape of out) receives that of out. */
 int cds_conv2d_3x3s2_tc(const void* in, const void* in_lo, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin,
                         int Cout, int H, int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
+/* The same stride-2 layer as a persistent row-streaming kernel (csrc/conv2d_s2rows.cu; models/module.py:214,218): every
+ * input row is loaded once by TMA (even / odd pixel phases as dense operand slabs) and normalised once.  Needs W even and the
+ * input statistics; wgt_packed = [kernel row 3][image][k-chunk 2][2*Cout/8][8 n][8 k] fp16 (host: weights.py
+ * pack_conv2d_s2rows).  Same tensors as cds_conv2d_3x3s2_tc. */
+int cds_conv2d_3x3s2_rows_supported(int Cin, int Cout, int H, int W);
+int cds_conv2d_3x3s2_rows_weight_halfs(int Cin, int Cout);
+int cds_conv2d_3x3s2_rows(const void* in, const void* in_lo, const double* in_stats, int in_act, const void* wgt_packed, int n, int Cin,
+                          int Cout, int H, int W, void* out, void* out_lo, double* out_stats, cudaStream_t stream);
 int cds_conv2d_1x1_cat_tc_supported(int Ca, int Cb, int Cout);
 int cds_conv2d_1x1_cat_tc_weight_halfs(int Ca, int Cb, int Cout);
 int cds_conv2d_1x1_cat_tc(const void* a, const double* a_stats, int a_act, const void* b, const double* b_stats, int b_act,

@@ -129,10 +129,38 @@ def test_kh_image_layer_pair_batch(pretrained_sd, V, B, hw):
     assert O.rel_l1(res[0], res[1]) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["out1", "out2", "out3"])
+@pytest.mark.parametrize("hw", [(24, 40), (45, 300), (150, 700)], ids=lambda hw: f"{hw[0]}x{hw[1]}")
+def test_kh_output_heads_vs_oracle(pretrained_sd, name, hw):
+    """The three output heads (1x1 + 3x3 branches, with bias, curvature accumulator in its closing mode)."""
+    w, cin, cout, ks, pre = _weights(pretrained_sd, name)
+    torch.manual_seed(hw[0] + len(name))
+    n = 2
+    x = 0.3 + torch.randn(n, cin, *hw)
+    epi = torch.tensor([[hw[1] * 0.7, hw[0] * 1.6], [-300.0, hw[0] / 2.0]])
+    hi = x.permute(0, 2, 3, 1).contiguous().half()
+    xs = hi.float().permute(0, 3, 1, 2)
+    xin = torch.nn.functional.leaky_relu(O.instance_norm(xs), 0.1)
+    ref_y, ref_nc = O.dynamic_conv(xin, pretrained_sd, pre, ks, epi, T)
+    base = torch.rand(n, *hw)
+    acc = cu(base.clone())
+    assert w.bias is not None
+    out, out_lo, ostats, nc, ncsq, ncabs = _run_kh(w, cu(hi.unsqueeze(0)).contiguous(), n, None, cu(_stats(xs)), 1, cu(epi), n, cin, cout, hw,
+                                                   ks, 0, nc_mode=2, ncsq=acc, bias=w.bias)
+    y = (out.float() + out_lo.float()).cpu().permute(0, 3, 1, 2)
+    ey, en = O.rel_l1(y, ref_y), O.rel_l1(nc.cpu().unsqueeze(1), ref_nc)
+    print(f"kh {name} {hw}: out {ey:.2e} curv {en:.2e}")
+    assert not torch.isnan(y).any() and not torch.isnan(nc).any()
+    assert ey < 4e-3 and en < 4e-3
+    torch.testing.assert_close(ostats.cpu(), _stats(y), rtol=2e-3, atol=2e-2 * hw[0] * hw[1] ** 0.5)
+    torch.testing.assert_close(acc.cpu(), (base + nc.cpu() ** 2) / 3.0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(ncabs.cpu(), nc.cpu().abs(), rtol=0, atol=0)
+
+
 def test_kh_rejects_unsupported():
     z = torch.zeros(64, device=DEV)
-    kz = (ctypes.c_int * 2)(1, 3)
-    with pytest.raises(RuntimeError):   # 8 -> 8 (1,3) (out3) is not a trunk layer
+    kz = (ctypes.c_int * 2)(3, 3)
+    with pytest.raises(RuntimeError):   # 8 -> 8 (3,3) is not a layer of the feature extractor
         call("cds_dynamic_conv_kh", ptr(z), 1, None, None, 0, ptr(z), 1.0, ptr(z), None, ptr(z), 1, 8, 8, 16, 16, 2, kz, T, 0, ptr(z),
              None, None, None, None, 0, None, 0, 0)
     assert _lib.LIB.load().cds_dynamic_conv_kh_supported(8, 8, 16, 16, 2, kz) == 0

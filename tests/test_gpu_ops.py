@@ -644,6 +644,58 @@ def test_conv2d_3x3s2_tcgen05_vs_torch(cin, cout, hw):
     torch.testing.assert_close(ostats.cpu(), ref_stats, atol=0.02 * ref[0, :, :, 0].numel() ** 0.5, rtol=5e-3)
 
 
+@pytest.mark.parametrize("cin,cout", [(8, 16), (16, 32)])
+@pytest.mark.parametrize("hw", [(32, 40), (37, 50), (64, 300), (150, 700), (9, 2)], ids=lambda hw: f"{hw[0]}x{hw[1]}")
+@pytest.mark.parametrize("use_lo", [1, 0])
+def test_conv2d_3x3s2_rows_vs_torch(cin, cout, hw, use_lo):
+    """FeatureNet.downsample1/2 as the row-streaming kernel (csrc/conv2d_s2rows.cu): even / odd pixel phases by TMA, each input
+    row normalised once, against torch on the fp32 input (value + residual planes) or its fp16 rounding (value plane only);
+    odd heights, partial strips, several tiles per persistent CTA, statistics."""
+    H, Wd = hw
+    torch.manual_seed(cin + H + Wd)
+    n = 3
+    x = 0.5 + 1.3 * torch.randn(n, cin, H, Wd)
+    wt = torch.randn(cout, cin, 3, 3) / (9 * cin) ** 0.5
+    nhwc = x.permute(0, 2, 3, 1).contiguous()
+    hi = nhwc.half(); lo = (nhwc - hi.float()).half()
+    stored = (hi.float() + lo.float()) if use_lo else hi.float()
+    xs = stored.permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.leaky_relu(O.instance_norm(xs), 0.1), wt, stride=2, padding=1)
+    stats = cu(torch.stack((xs.double().sum((2, 3)), (xs.double() ** 2).sum((2, 3))), -1).contiguous())
+    lib = _lib.LIB.load()
+    assert lib.cds_conv2d_3x3s2_rows_supported(cin, cout, H, Wd) == 1
+    packed = cu(W.pack_conv2d_s2rows(wt.permute(2, 3, 1, 0).reshape(9, cin, cout).contiguous()))
+    assert packed.numel() == lib.cds_conv2d_3x3s2_rows_weight_halfs(cin, cout)
+    Ho, Wo = (H + 1) // 2, Wd // 2
+    out = torch.full((n, Ho, Wo, cout), float("nan"), device=DEV, dtype=torch.float16)
+    out_lo = torch.full_like(out, float("nan"))
+    ostats = torch.zeros(n, cout, 2, device=DEV, dtype=torch.float64)
+    hc, lc = cu(hi), cu(lo)
+    call("cds_conv2d_3x3s2_rows", ptr(hc), ptr(lc) if use_lo else None, ptr(stats), _lib.ACT_LRELU, ptr(packed), n, cin, cout, H, Wd,
+         ptr(out), ptr(out_lo), ptr(ostats))
+    torch.cuda.synchronize()
+    y = (out.float() + out_lo.float()).cpu().permute(0, 3, 1, 2)
+    assert not torch.isnan(y).any()
+    err = O.rel_l1(y, ref)
+    print(f"3x3 s2 rows {cin}->{cout} {hw} lo={use_lo}: {err:.2e}")
+    assert err < 2e-5
+    assert (out_lo.float().abs() <= out.float().abs() * 2.0 ** -11 + 1e-7).all()
+    ref_stats = torch.stack((y.double().sum(dim=(2, 3)), (y.double() ** 2).sum(dim=(2, 3))), dim=-1)
+    torch.testing.assert_close(ostats.cpu(), ref_stats, atol=0.02 * (Ho * Wo) ** 0.5, rtol=2e-3)
+    # and against the gather form of the same layer
+    packed_g = cu(W.pack_conv2d_gtc(wt.permute(2, 3, 1, 0).reshape(9, cin, cout).contiguous()))
+    out_g = torch.empty_like(out); out_g_lo = torch.empty_like(out)
+    call("cds_conv2d_3x3s2_tc", ptr(hc), ptr(lc) if use_lo else None, ptr(stats), _lib.ACT_LRELU, ptr(packed_g), n, cin, cout, H, Wd,
+         ptr(out_g), ptr(out_g_lo), None)
+    torch.cuda.synchronize()
+    assert O.rel_l1(y, (out_g.float() + out_g_lo.float()).cpu().permute(0, 3, 1, 2)) < 2e-6
+
+
+def test_conv2d_3x3s2_rows_rejects_odd_width():
+    assert _lib.LIB.load().cds_conv2d_3x3s2_rows_supported(8, 16, 32, 41) == 0
+    assert _lib.LIB.load().cds_conv2d_3x3s2_rows_supported(8, 8, 32, 40) == 0
+
+
 @pytest.mark.parametrize("ca,cb,cout,a_norm", [(32, 16, 16, True), (16, 8, 8, False)])
 @pytest.mark.parametrize("hw", [(32, 40), (38, 50), (64, 130)])
 def test_conv2d_1x1_cat_tcgen05_vs_torch(ca, cb, cout, a_norm, hw):
