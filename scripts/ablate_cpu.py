@@ -7,6 +7,8 @@ input.  The oracle's feature extractor / stage net are re-run with fp16 rounding
   fea              the three stage features (tanh outputs) are rounded to fp16
   vol              the aggregated cost volume is rounded to fp16
   reg              every regulariser activation is rounded to fp16
+  s1src16 | s1srci16 | s1ref16 | s1refi16   the stage-1 source / reference features as the plane sweep reads them: fp16 or
+                   16-bit fixed point (tanh output in [-1, 1], step 2^-15)
 
 usage: python scripts/ablate_cpu.py [--seeds=0-5] name=spec[,spec...] ...   e.g.  all=store:*,act:*,w:*,fea,vol,reg
 """
@@ -101,10 +103,21 @@ def forward(s, cfg, sp):
     if "vol" in sp.flags or "vol23" in sp.flags:
         skipv = "vol" not in sp.flags
         O.cost_reg_net = lambda x, sd, prefix: orig[3](x if skipv and s1(prefix) else h16(x), sd, prefix)
+    orig_stage = O.stage_net
+    q16 = {"16": h16, "i16": lambda t: torch.round(t * 32768.0).clamp(-32768, 32767) / 32768.0}
+    s1 = {side: q16[f[len("s1" + side):]] for f in sp.flags for side in ("src", "ref") if f.startswith("s1" + side)}
+    if s1:   # stage-1 features as the aggregate sweep sees them: fp16 ("s1src16") or 16-bit fixed point ("s1srci16") per side
+        def stage_net(features, proj, samples, sd, stage_idx, *a, **k):
+            if stage_idx == 0:
+                features = [{side: ((s1[side](f[side][0]) if side in s1 else f[side][0]),) + tuple(f[side][1:]) for side in ("ref", "src")}
+                            for f in features]
+            return orig_stage(features, proj, samples, sd, stage_idx, *a, **k)
+        O.stage_net = stage_net
     try:
         return O.cdsmvsnet_forward(SD, s.imgs, s.proj_matrices, s.depth_values, cfg["ndepths"], cfg["ratios"], 0.01)
     finally:
         O.feature_net, O._cbr3d, O._dbr3d, O.cost_reg_net = orig
+        O.stage_net = orig_stage
 
 
 if __name__ == "__main__":

@@ -11,12 +11,16 @@ timeout 900 python bench.py --steps 20 --warmup 5 --kernel-table $O/${TAG}_kerne
 python - <<PY
 import json
 d=json.load(open("$O/${TAG}_bench_cfg2.json"))
-print("value",d["value"],"ms",d["ms_per_step"],"e2e",d["e2e"]["value"],"seq",d["e2e"]["one_call_at_a_time"]["value"])
+print("value",d["value"],"ms",d["ms_per_step"],"single",d.get("one_map_at_a_time"),"e2e",d["e2e"]["value"],"seq",d["e2e"]["one_call_at_a_time"]["value"])
 print("parity",json.dumps(d["parity"]["stages"]) if d.get("parity") else None)
 print("incumbent",json.dumps(d.get("reference_eager_gpu")))
 print("cpu",json.dumps(d.get("cpu_baseline")))
 PY
 tail -32 $O/${TAG}_bench.err | head -26
+if [ -n "$EXTRA_BENCH" ]; then
+  timeout 600 python bench.py --steps 20 --warmup 5 --no-incumbent --no-cpu-baseline $EXTRA_BENCH > $O/${TAG}_bench_extra.json 2> $O/${TAG}_bench_extra.err
+  python -c "import json; d=json.load(open('$O/${TAG}_bench_extra.json')); print('extra [$EXTRA_BENCH]: value', d['value'], 'e2e', d['e2e']['value'])"
+fi
 OURS='regex:(dynconv|conv3d|deconv3d|entropy|aggregate|visnet|conv1x1|conv3x3|conv2d|instnorm|softmax_regress|regress|hypotheses|nc_mean|camera_setup|image_to|u8_to|prob_conv|homo_warp|warp_coeffs|costvol)'
 N=${NCU_LIST_COUNT:-69}
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s $N -c $N --csv --log-file $O/${TAG}_launches.csv \
