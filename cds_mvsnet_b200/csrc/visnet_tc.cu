@@ -8,9 +8,15 @@
 //                         the layer-1 weights are duplicated for the "lo" channels, so the inputs are exact
 //   a1   [2][TY+4 rows]   layer-1 output (16 ch = 2 slabs), written by the epilogue at pixel j+1
 //   a2   [2][TY+2 rows]   layer-2 output, re-using the in8 region
-// Each layer: M = 128 pixels of a row (output pixel = j+1), N = 16, K = 9 taps x channels; TMEM accumulators are
-// read back by the 4 warps, bias+ReLU, ZEROED outside the image (each layer zero-pads its own input), packed to
-// fp16 and stored as the next layer's operand; layer 3 finishes with the 1x1 conv + sigmoid and writes fp32.
+// Each layer: M = 128 pixels of a row (output pixel = j+1), the kernel ROWS folded into N (as csrc/dynconv_kh.cu): ONE MMA on
+// input row i and horizontal tap step s produces, in N = 48 columns, its contributions to the three output rows i-2, i-1, i
+// (column group g <-> output row i-2+g, kernel row 2-g; ranges clipped at the buffer's first / last rows).  The accumulators of
+// a layer's output rows sit side by side in TMEM (slot = output row, 16 columns each), every MMA accumulates and the slots are
+// handed over ZEROED (tcgen05.st in the epilogue that drained them).  An N = 16 MMA costs 36 cycles of operand fetch for 8 of
+// math; N = 48 costs 44 for three times the work: 62 MMAs per tile instead of 130.  One warp issues a layer's MMAs in program
+// order (fixed accumulation order).  TMEM accumulators are read back by the 8 warps, bias+ReLU, zeroed outside the image
+// (each layer zero-pads its own input), packed to fp16 and stored as the next layer's operand; layer 3 finishes with the 1x1
+// conv + sigmoid and writes fp32.
 #include <algorithm>
 
 #include "cds_common.cuh"
@@ -26,8 +32,9 @@ constexpr int ROW_BYTES = TX * 16;
 constexpr int R_IN = TY + 6, R_A1 = TY + 4, R_A2 = TY + 2;
 constexpr uint32_t X_BYTES = 2 * R_A2 * ROW_BYTES;       // in8 (R_IN rows, 1 slab) then a2 (2 slabs x R_A2 rows)
 constexpr uint32_t Y_BYTES = 2 * R_A1 * ROW_BYTES;       // a1
-constexpr int MMA_L1 = 5, MMA_L23 = 9;
-constexpr uint32_t W_BYTES = (MMA_L1 + 2 * MMA_L23) * 2 * 16 * 16;
+constexpr int MMA_L1 = 2, MMA_L23 = 3;                    // horizontal tap steps per input row: (kw0, kw1), (-, kw2); kw0, kw1, kw2
+constexpr uint32_t W_STEP = 2 * 48 * 16;                  // one step's operand image: [k-chunk 2][48 columns][8 k] fp16
+constexpr uint32_t W_BYTES = (MMA_L1 + 2 * MMA_L23) * W_STEP;
 static_assert(X_BYTES >= R_IN * ROW_BYTES, "in8 must fit in the region a2 re-uses");
 constexpr uint32_t TMEM_COLS = R_A1 * 16 <= 128 ? 128 : 256;   // R_A1 row units x 16 accumulator columns
 static_assert(R_A1 * 16 <= 256, "row units of layer 1 exceed the TMEM budget of two resident CTAs");
@@ -35,7 +42,7 @@ static_assert(R_A1 * 16 <= 256, "row units of layer 1 exceed the TMEM budget of 
 struct VisTcParams {
     const float* entropy;   // [n][H][W]
     const float* curv;      // [n][H][W]
-    const __half* wgt;      // packed fp16: L1 [5], L2 [9], L3 [9] MMAs x [2 k-chunk][2][8 n][8 k]
+    const __half* wgt;      // packed fp16: L1 [2], L2 [3], L3 [3] steps x [2 k-chunk][6][8 n][8 k]
     const float* fparams;   // b1[16] b2[16] b3[16] w4[16] b4[1]
     float* vis;             // [n][H][W]
     int H, W;
@@ -43,43 +50,47 @@ struct VisTcParams {
 
 constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
 
-// layer 1: one slab per tap -> [tap0, pad], [tap1, tap2], ...
-template <int J>
-__device__ __forceinline__ void mma_l1(uint32_t a_base, uint32_t b_base, uint32_t acc, bool elected) {
-    constexpr int t0 = J == 0 ? 0 : 2 * J - 1, t1 = 2 * J;
-    constexpr uint32_t off0 = (uint32_t)((t0 / 3) * ROW_BYTES + (t0 % 3) * 16);
-    constexpr uint32_t lbo = J == 0 ? 16u : (uint32_t)((t1 / 3) * ROW_BYTES + (t1 % 3) * 16) - off0;
-    constexpr uint32_t a_const = (off0 >> 4) | ((lbo >> 4) << 16);
-    constexpr uint32_t b_const = (((uint32_t)J * 512) >> 4) | ((256u >> 4) << 16);
+// One MMA of the row fold: input row I of a buffer of RI rows (outputs RI - 2 rows), tap step S.
+//   layer 1 (L1): one 8-channel slab per pixel; a step pairs two neighbouring pixels (LBO 16 B): step 0 = taps (0, 1), step 1 =
+//                 taps (1, 2) with zero weights for tap 1 (a pad chunk BEHIND tap 2 would read past the staged rows, and
+//                 0 x garbage may be NaN)
+//   layers 2/3:   two slabs (channel chunks, CHUNK bytes apart) per pixel; step S = tap S
+template <int RI, int NSTEP, bool L1, uint32_t CHUNK, int WOFF, int K>
+__device__ __forceinline__ void mma_fold(uint32_t a_base, uint32_t b_base, uint32_t acc, bool elected) {
+    constexpr int I = K / NSTEP, S = K % NSTEP, RO = RI - 2;
+    constexpr int olo = I - 2 > 0 ? I - 2 : 0, ohi = I < RO - 1 ? I : RO - 1;
+    constexpr int g0 = olo - (I - 2), ng = ohi - olo + 1;
+    static_assert(ng >= 1 && ng <= 3 && g0 >= 0 && g0 + ng <= 3, "row range of the fold");
+    constexpr uint32_t a_off = (uint32_t)(I * ROW_BYTES + S * 16);
+    constexpr uint32_t lbo = L1 ? 16u : CHUNK;
+    constexpr uint32_t a_const = (a_off >> 4) | ((lbo >> 4) << 16);
+    constexpr uint32_t b_const = (((uint32_t)(WOFF + S) * W_STEP + (uint32_t)g0 * 256) >> 4) | ((768u >> 4) << 16);
     if (elected)
-        tc::mma_f16(acc, ((uint64_t)kDescHi << 32) | (a_base + a_const), ((uint64_t)kDescHi << 32) | (b_base + b_const),
-                    tc::instr_desc_f16(128, 16), J > 0);
+        tc::mma_f16(acc + (uint32_t)olo * 16, ((uint64_t)kDescHi << 32) | (a_base + a_const), ((uint64_t)kDescHi << 32) | (b_base + b_const),
+                    tc::instr_desc_f16(128, ng * 16), true);
 }
-// layers 2/3: two slabs (channel chunks) per tap; CHUNK = distance between the chunks of the operand buffer
-template <int J, uint32_t CHUNK, int WOFF>
-__device__ __forceinline__ void mma_l23(uint32_t a_base, uint32_t b_base, uint32_t acc, bool elected) {
-    constexpr uint32_t off0 = (uint32_t)((J / 3) * ROW_BYTES + (J % 3) * 16);
-    constexpr uint32_t a_const = (off0 >> 4) | ((CHUNK >> 4) << 16);
-    constexpr uint32_t b_const = (((uint32_t)(WOFF + J) * 512) >> 4) | ((256u >> 4) << 16);
-    if (elected)
-        tc::mma_f16(acc, ((uint64_t)kDescHi << 32) | (a_base + a_const), ((uint64_t)kDescHi << 32) | (b_base + b_const),
-                    tc::instr_desc_f16(128, 16), J > 0);
+template <int RI, int NSTEP, bool L1, uint32_t CHUNK, int WOFF, int... K>
+__device__ __forceinline__ void issue_fold(uint32_t a, uint32_t b, uint32_t acc, bool e, std::integer_sequence<int, K...>) {
+    (mma_fold<RI, NSTEP, L1, CHUNK, WOFF, K>(a, b, acc, e), ...);
 }
-template <int... J>
-__device__ __forceinline__ void issue_l1(uint32_t a, uint32_t b, uint32_t acc, bool e, std::integer_sequence<int, J...>) {
-    (mma_l1<J>(a, b, acc, e), ...);
-}
-template <uint32_t CHUNK, int WOFF, int... J>
-__device__ __forceinline__ void issue_l23(uint32_t a, uint32_t b, uint32_t acc, bool e, std::integer_sequence<int, J...>) {
-    (mma_l23<J, CHUNK, WOFF>(a, b, acc, e), ...);
+// all MMAs of a layer, input rows in order
+template <int RI, int NSTEP, bool L1, uint32_t CHUNK, int WOFF>
+__device__ __forceinline__ void issue_layer(uint32_t a, uint32_t b, uint32_t acc, bool e) {
+    issue_fold<RI, NSTEP, L1, CHUNK, WOFF>(a, b, acc, e, std::make_integer_sequence<int, RI * NSTEP>{});
 }
 
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 // bias + ReLU of one row unit's 16 accumulator columns; result as two packed fp16 slabs (or zero outside the image)
-__device__ __forceinline__ void act16(uint32_t taddr, const float* __restrict__ bias, bool inside, uint4& lo, uint4& hi) {
+__device__ __forceinline__ void act16(uint32_t taddr, const float* __restrict__ bias, bool inside, bool zero_after, uint4& lo, uint4& hi) {
     uint32_t r0[8], r1[8];
     tc::tmem_ld8_nowait(taddr, r0);
     tc::tmem_ld8_nowait(taddr + 8, r1);
     tc::tmem_ld_wait();
+    if (zero_after) tmem_zero16(taddr);   // the next layer accumulates into this slot
     __half2* l = reinterpret_cast<__half2*>(&lo);
     __half2* h = reinterpret_cast<__half2*>(&hi);
 #pragma unroll
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
     if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     if (threadIdx.x == 32) {
         tc::mbar_init(bar_w, 1);
-        for (int i = 0; i < 3; ++i) tc::mbar_init(bar_mma + i, NT / 32);
+        for (int i = 0; i < 3; ++i) tc::mbar_init(bar_mma + i, 1);
         tc::mbar_fence_init();
     }
     if (threadIdx.x < 65) s_f[threadIdx.x] = __ldg(p.fparams + threadIdx.x);
@@ -127,6 +138,11 @@ __global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
     if (threadIdx.x == 0) {
         tc::mbar_expect_tx(bar_w, W_BYTES);
         tc::bulk_copy_g2s(sW_u, p.wgt, W_BYTES, bar_w);
+    }
+    if (warp < 4) {   // every MMA accumulates: the accumulator slots start zeroed
+#pragma unroll
+        for (int c = 0; c < R_A1 * 16; c += 16) tmem_zero16(tmem + ((uint32_t)(warp * 32) << 16) + c);
+        tmem_st_wait();
     }
     // ---- stage the two fp32 input maps as hi/lo fp16 slabs (zero outside the image) -------------------------------
     for (int i = threadIdx.x; i < R_IN * TX; i += NT) {
@@ -148,6 +164,7 @@ __global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
         *reinterpret_cast<uint4*>(sX + (size_t)i * 16) = v;
     }
     tc::fence_proxy_async();
+    tc::tc_fence_before();
     __syncthreads();
     tc::mbar_wait(bar_w, 0);
 
@@ -160,59 +177,59 @@ __global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
 
     // ---- layer 1: in8 -> a1 ------------------------------------------------------------------------------------------
     tc::tc_fence_after();
-#pragma unroll 1
-    for (uint32_t u = warp_u; u < (uint32_t)R_A1; u += NT / 32)
-        issue_l1((sX_u + u * ROW_BYTES) >> 4, sW_u >> 4, tmem_u + u * 16, elected, std::make_integer_sequence<int, MMA_L1>{});
-    if (elected) tc::mma_commit(bar_mma);
-    __syncwarp();
+    if (warp_u == 0) {
+        issue_layer<R_IN, MMA_L1, true, 0, 0>(sX_u >> 4, sW_u >> 4, tmem_u, elected);
+        if (elected) tc::mma_commit(bar_mma);
+        __syncwarp();
+    }
     tc::mbar_wait(bar_mma, 0);
     tc::tc_fence_after();
 #pragma unroll 1
     for (int u = half; u < R_A1; u += 2) {
         const int gy = y0 - 2 + u;
         uint4 lo, hi;
-        act16(lane_addr + u * 16, s_f, gx1 >= 0 && gx1 < p.W && gy >= 0 && gy < p.H, lo, hi);
+        act16(lane_addr + u * 16, s_f, gx1 >= 0 && gx1 < p.W && gy >= 0 && gy < p.H, true, lo, hi);
         if (j < TX - 2) {
             *reinterpret_cast<uint4*>(sY + ((size_t)u * TX + j + 1) * 16) = lo;
             *reinterpret_cast<uint4*>(sY + ((size_t)(R_A1 + u) * TX + j + 1) * 16) = hi;
         }
     }
+    tmem_st_wait();
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
 
     // ---- layer 2: a1 -> a2 (re-using the in8 region) ------------------------------------------------------------------
-#pragma unroll 1
-    for (uint32_t u = warp_u; u < (uint32_t)R_A2; u += NT / 32)
-        issue_l23<R_A1 * ROW_BYTES, MMA_L1>((sY_u + u * ROW_BYTES) >> 4, sW_u >> 4, tmem_u + u * 16, elected,
-                                           std::make_integer_sequence<int, MMA_L23>{});
-    if (elected) tc::mma_commit(bar_mma + 1);
-    __syncwarp();
+    if (warp_u == 0) {
+        issue_layer<R_A1, MMA_L23, false, R_A1 * ROW_BYTES, MMA_L1>(sY_u >> 4, sW_u >> 4, tmem_u, elected);
+        if (elected) tc::mma_commit(bar_mma + 1);
+        __syncwarp();
+    }
     tc::mbar_wait(bar_mma + 1, 0);
     tc::tc_fence_after();
 #pragma unroll 1
     for (int u = half; u < R_A2; u += 2) {
         const int gy = y0 - 1 + u;
         uint4 lo, hi;
-        act16(lane_addr + u * 16, s_f + 16, gx1 >= 0 && gx1 < p.W && gy >= 0 && gy < p.H, lo, hi);
+        act16(lane_addr + u * 16, s_f + 16, gx1 >= 0 && gx1 < p.W && gy >= 0 && gy < p.H, true, lo, hi);
         if (j < TX - 2) {
             *reinterpret_cast<uint4*>(sX + ((size_t)u * TX + j + 1) * 16) = lo;
             *reinterpret_cast<uint4*>(sX + ((size_t)(R_A2 + u) * TX + j + 1) * 16) = hi;
         }
     }
+    tmem_st_wait();
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
 
     // ---- layer 3 + 1x1 + sigmoid ---------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (uint32_t u = warp_u; u < (uint32_t)TY; u += NT / 32)
-        issue_l23<R_A2 * ROW_BYTES, MMA_L1 + MMA_L23>((sX_u + u * ROW_BYTES) >> 4, sW_u >> 4, tmem_u + u * 16, elected,
-                                                     std::make_integer_sequence<int, MMA_L23>{});
-    if (elected) tc::mma_commit(bar_mma + 2);
-    __syncwarp();
+    if (warp_u == 0) {
+        issue_layer<R_A2, MMA_L23, false, R_A2 * ROW_BYTES, MMA_L1 + MMA_L23>(sX_u >> 4, sW_u >> 4, tmem_u, elected);
+        if (elected) tc::mma_commit(bar_mma + 2);
+        __syncwarp();
+    }
     tc::mbar_wait(bar_mma + 2, 0);
     tc::tc_fence_after();
     const bool col_ok = j >= 2 && j < TX - 4 && gx1 < p.W && gx1 >= (int)blockIdx.x * TXO;   // one owner tile per pixel

@@ -220,33 +220,36 @@ def pack_visnet(sd, prefix, device) -> torch.Tensor:
 
 
 def pack_visnet_tc(sd, prefix, device):
-    """Operands for csrc/visnet_tc.cu: (fp16 image [L1 5 MMAs | L2 9 | L3 9] x [k-chunk 2][2][8 n][8 k], fp32 b1 b2 b3 w4 b4).
+    """Operands for csrc/visnet_tc.cu: (fp16 image [L1 2 steps | L2 3 | L3 3] x [k-chunk 2][6][8 n][8 k], fp32 b1 b2 b3 w4 b4).
 
-    Layer 1 sees (entropy_hi, curv_hi, entropy_lo, curv_lo, 0, 0, 0, 0) per pixel, so its weights are duplicated for the
-    "lo" channels; its 9 taps are paired [tap0, zero pad], [tap1, tap2], ...  Layers 2/3: one MMA per tap, the two
-    k-chunks are the two 8-channel halves of the 16 input channels."""
+    The kernel rows are folded into N: column n = g*16 + cout, group g <-> kernel row 2-g (group g of the MMA on input row i
+    feeds output row i-2+g).  Layer 1 sees (entropy_hi, curv_hi, entropy_lo, curv_lo, 0, 0, 0, 0) per pixel, so its weights are
+    duplicated for the "lo" channels; its steps pair neighbouring pixels: step 0 = horizontal taps (0, 1), step 1 = (1, 2)
+    with zeros for tap 1.  Layers 2/3: step = horizontal tap, the two k-chunks are the two 8-channel halves of the input."""
     ws, bs = [], []
     for j in range(3):
         scale, shift = _bn_fold(sd, f"{prefix}.{j}.bn")
         ws.append((sd[f"{prefix}.{j}.conv.weight"].double() * scale.reshape(-1, 1, 1, 1)).cpu())   # [16, Cin, 3, 3]
         bs.append(shift.cpu())
     parts = []
-    slabs = [0, None] + list(range(1, 9))
-    img = torch.zeros(5, 2, 2, 8, 8, dtype=torch.float64)
-    for s, t in enumerate(slabs):
-        if t is None:
-            continue
-        full = torch.zeros(8, 16, dtype=torch.float64)                     # [k, n]
-        wt = ws[0][:, :, t // 3, t % 3]                                    # [16, 2]
-        full[0], full[1], full[2], full[3] = wt[:, 0], wt[:, 1], wt[:, 0], wt[:, 1]
-        img[s // 2, s % 2] = full.t().reshape(2, 8, 8)
+    img = torch.zeros(2, 2, 48, 8, dtype=torch.float64)                       # [step, k-chunk, column, k]
+    for step, taps in enumerate(((0, 1), (None, 2))):
+        for q, kw in enumerate(taps):
+            if kw is None:
+                continue
+            for g in range(3):
+                wt = ws[0][:, :, 2 - g, kw]                                    # [16 cout, 2]
+                img[step, q, g * 16:(g + 1) * 16, 0] = wt[:, 0]
+                img[step, q, g * 16:(g + 1) * 16, 1] = wt[:, 1]
+                img[step, q, g * 16:(g + 1) * 16, 2] = wt[:, 0]
+                img[step, q, g * 16:(g + 1) * 16, 3] = wt[:, 1]
     parts.append(img.reshape(-1))
     for j in (1, 2):
-        img = torch.zeros(9, 2, 2, 8, 8, dtype=torch.float64)
-        for t in range(9):
-            wt = ws[j][:, :, t // 3, t % 3]                                # [16 n, 16 cin]
-            for c in range(2):
-                img[t, c] = wt[:, c * 8:(c + 1) * 8].reshape(2, 8, 8)      # [n-group][n][k]
+        img = torch.zeros(3, 2, 48, 8, dtype=torch.float64)
+        for kw in range(3):
+            for q in range(2):
+                for g in range(3):
+                    img[kw, q, g * 16:(g + 1) * 16] = ws[j][:, q * 8:(q + 1) * 8, 2 - g, kw]   # [16 cout, 8 cin]
         parts.append(img.reshape(-1))
     wgt = torch.cat(parts).to(torch.float16).contiguous().to(device)
     fp = torch.cat((bs[0], bs[1], bs[2], sd[f"{prefix}.3.weight"].double().reshape(-1).cpu(),
