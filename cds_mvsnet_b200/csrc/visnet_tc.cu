@@ -25,7 +25,7 @@
 namespace {
 
 #ifndef CDS_VIS_TY
-#define CDS_VIS_TY 4   // 8-row tiles (2 resident CTAs, 17 % fewer MMAs) measured 0.476 vs 0.466 ms at stage 3: not adopted
+#define CDS_VIS_TY 4   // 8-row tiles (2 resident CTAs, fewer halo MMAs) measured the same (0.381 vs 0.376 ms at stage 3): the tile is not MMA-bound
 #endif
 constexpr int TX = 128, TXO = TX - 6, TY = CDS_VIS_TY;
 constexpr int ROW_BYTES = TX * 16;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void act16(uint32_t taddr, const float* __restrict__ 
     }
 }
 
-constexpr int NT = 256;   // 8 warps: two per TMEM lane quadrant share each layer's epilogue rows; all eight issue MMAs
+constexpr int NT = 256;   // 8 warps: two per TMEM lane quadrant share each layer's epilogue rows; warp 0 issues the MMAs
 
 __global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -145,14 +145,20 @@ __global__ void __launch_bounds__(NT) visnet_tc_kernel(VisTcParams p) {
         tmem_st_wait();
     }
     // ---- stage the two fp32 input maps as hi/lo fp16 slabs (zero outside the image) -------------------------------
-    for (int i = threadIdx.x; i < R_IN * TX; i += NT) {
-        const int px = i % TX, ry = i / TX;
-        const int gx = xs + px, gy = y0 - 3 + ry;
-        float e = 0.f, c = 0.f;
-        if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
-            e = __ldg(p.entropy + n * plane + (size_t)gy * p.W + gx);
-            c = __ldg(p.curv + n * plane + (size_t)gy * p.W + gx);
-        }
+    static_assert((R_IN * TX) % NT == 0, "input staging: whole rounds");
+    float in_e[R_IN * TX / NT], in_c[R_IN * TX / NT];
+#pragma unroll
+    for (int k = 0; k < R_IN * TX / NT; ++k) {   // every load in flight before the first is used
+        const int i = threadIdx.x + k * NT;
+        const int gx = xs + i % TX, gy = y0 - 3 + i / TX;
+        const bool ok = gx >= 0 && gx < p.W && gy >= 0 && gy < p.H;
+        in_e[k] = ok ? __ldg(p.entropy + n * plane + (size_t)gy * p.W + gx) : 0.f;
+        in_c[k] = ok ? __ldg(p.curv + n * plane + (size_t)gy * p.W + gx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < R_IN * TX / NT; ++k) {
+        const int i = threadIdx.x + k * NT;
+        const float e = in_e[k], c = in_c[k];
         __half eh = __float2half_rn(e), ch = __float2half_rn(c);
         __half el = __float2half_rn(e - __half2float(eh)), cl = __float2half_rn(c - __half2float(ch));
         uint4 v;
