@@ -1,5 +1,5 @@
 // FeatureNet.downsample1/2 (3x3 stride-2 pad-1 conv, models/module.py:214,218) as a persistent row-streaming kernel:
-// TMA ring of input rows -> staging warps (the producer's InstanceNorm + LeakyReLU, once per input pixel) -> tcgen05 tap GEMMs
+// ring of raw input rows (bulk copies) -> staging warps (the producer's InstanceNorm + LeakyReLU, once per input pixel) -> tcgen05 tap GEMMs
 // -> TMEM -> epilogue (fp16 value + residual planes, InstanceNorm statistics).
 //
 // csrc/conv2d_gtc.cu computes the same layer by a per-output-pixel gather: 9 (x2 planes) 16-byte loads and 9 normalisations
@@ -35,12 +35,13 @@ constexpr int NPX = 2 * TXO + 1;     // raw pixels 1 .. 255 of the segment start
 constexpr int TXB = 132;             // slab pitch in pixels: 2112 B = 64 (mod 128), so the two phases' writes of a quarter warp miss each other's banks
 constexpr int SLABB = TXB * 16;
 constexpr int NSTGW = 8;             // staging warps (in NGRP groups, each owning every NGRP-th row)
-constexpr int NTHREADS = 512;        // warps: 0 producer, 1 MMA, 2-3 idle, 4-11 staging, 12-15 epilogue
+constexpr int NTHREADS = 448;        // warps: 0 producer, 1 MMA, 2-9 staging, 10-13 epilogue (one per TMEM lane quadrant: warp & 3)
+constexpr int kStgWarp0 = 2, kEpiWarp0 = kStgWarp0 + NSTGW;
 constexpr float kInEps = 1e-5f;
 
-template <int CIN_, int COUT_, int TY_, int NR_, int NRAW_, int NGRP_>
+template <int CIN_, int COUT_, int TY_, int NR_, int NRAW_, int NGRP_, int MINB_>
 struct S2 {
-    static constexpr int CIN = CIN_, COUT = COUT_, C8 = CIN_ / 8, TY = TY_, NR = NR_, NRAW = NRAW_, NGRP = NGRP_;
+    static constexpr int CIN = CIN_, COUT = COUT_, C8 = CIN_ / 8, TY = TY_, NR = NR_, NRAW = NRAW_, NGRP = NGRP_, MINB = MINB_;
     static constexpr int RAWP = NPX * CIN_ * 2;                 // one plane of a raw row segment
     static constexpr int RAWB = 2 * RAWP;
     // A ring slot must always be handled by the SAME staging group (ring depths = multiples of NGRP): a parity wait can only
@@ -135,7 +136,7 @@ __device__ __forceinline__ void issue_dy(uint32_t a_row, uint32_t sB_u, int dy, 
 }
 
 template <class C>
-__global__ void __launch_bounds__(NTHREADS, 1) conv2d_s2rows_kernel(const S2Params p) {
+__global__ void __launch_bounds__(NTHREADS, C::MINB) conv2d_s2rows_kernel(const S2Params p) {
     constexpr int CIN = C::CIN, COUT = C::COUT, C8 = C::C8, TY = C::TY, NR = C::NR, NRAW = C::NRAW, NC = C::NC;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                   // operand ring
@@ -228,13 +229,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv2d_s2rows_kernel(const S2Para
                 __syncwarp();
             }
         }
-    } else if (warp >= 4 && warp < 4 + NSTGW) {
+    } else if (warp >= kStgWarp0 && warp < kEpiWarp0) {
         // ---- staging: InstanceNorm + activation of the producer, value + residual planes ----------------------------------------
         // The warps form NGRP groups; group g owns the rows rc = g (mod NGRP), so NGRP rows are in flight at once (one group over
         // all rows ran them back to back: wait, one round of loads, arithmetic, stores, proxy fence, arrive = ~350 cycles per row of
         // pure latency whatever the thread count) and a thread's pieces of a row are independent work to interleave.
         constexpr int NGRP = C::NGRP, WPG = NSTGW / NGRP;
-        const int sw = warp - 4, grp = sw / WPG, gtid = (sw % WPG) * 32 + lane;
+        const int sw = warp - kStgWarp0, grp = sw / WPG, gtid = (sw % WPG) * 32 + lane;
         float* nm_grp = s_norm + grp * 2 * CIN;
         auto group_sync = [&]() {
             if constexpr (WPG == 1) __syncwarp();
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv2d_s2rows_kernel(const S2Para
                 if (lane == 0) { mbar_arrive(ring_ready + slot); mbar_arrive(raw_empty + rs); }
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= kEpiWarp0) {
         // ---- epilogue: one output pixel per thread ------------------------------------------------------------------------------
         const int lg = warp & 3;
         const int r = lg * 32 + lane;
@@ -440,8 +441,9 @@ int cds_conv2d_3x3s2_rows(const void* in, const void* in_lo, const double* in_st
     // 0.320 / 0.229).  Row-owning groups (NGRP = 8 / 4) or loading straight from global memory were no faster: with every stage
     // stubbed out the barrier hand-offs alone (staging -> issuer -> epilogue, ~500 cycles per input row through the one issuer
     // thread) take 0.13 ms, which is what bounds the kernel -- see DESIGN.md section 5.
-    if (Cin == 8) return launch_s2<S2<8, 16, 8, 4, 16, 1>>(p, stream);
-    return launch_s2<S2<16, 32, 4, 3, 8, 1>>(p, stream);
+    // one CTA per SM: two resident CTAs for Cin 8 (72 registers, raw ring of 6) measured 0.259 ms against 0.242
+    if (Cin == 8) return launch_s2<S2<8, 16, 8, 4, 16, 1, 1>>(p, stream);
+    return launch_s2<S2<16, 32, 4, 3, 8, 1, 1>>(p, stream);
 }
 
 }  // extern "C"
