@@ -150,6 +150,41 @@ def test_depth_map_stream_matches_direct_call(pretrained_sd):
         stream.submit(items[0].imgs.to(DEV), items[0].proj_matrices, items[0].depth_values)
 
 
+def test_maps_in_flight_match_one_at_a_time(pretrained_sd):
+    """DepthMapStream with two / three work items computing at once (one cascade clone and stream per lane) returns, item by
+    item, what one map at a time returns -- including across a change of the input shape mid-stream; the clones share the
+    packed weights and own their buffers."""
+    from cds_mvsnet_b200.streaming import DepthMapStream
+    cfg = dict(W=160, H=128, N=3, ndepths=(16, 8, 8), ratios=(4.0, 1.5, 0.75), B=1, Dtot=192, interval=2.65)
+    cfg_b = dict(cfg, W=192, H=96)
+    model = build(pretrained_sd, cfg["ndepths"], cfg["ratios"], torch.float16)
+    items = [synthetic.make_sample(cfg if i < 5 else cfg_b, "plane" if i % 2 else "noise", seed=i) for i in range(8)]
+    eng = model.engine(torch.device(DEV, 0))
+    twin = eng.clone()
+    assert twin.w is eng.w and twin.buf is not eng.buf
+    res = {}
+    for f in (1, 2, 3):
+        stream = DepthMapStream(model, temperature=T, in_flight=f)
+        assert len(stream.slots) == f + 1
+        pending, got = [], []
+        for s in items:
+            pending.append(stream.submit(s.imgs, s.proj_matrices, s.depth_values))
+            if len(pending) > stream.in_flight:
+                got.append({k: v.clone() for k, v in stream.result(pending.pop(0)).items()})
+        got += [{k: v.clone() for k, v in stream.result(t).items()} for t in pending]
+        res[f] = got
+    for f in (2, 3):
+        assert len(res[f]) == len(items)
+        for one, many in zip(res[1], res[f]):
+            assert one.keys() == many.keys()
+            for k in one:
+                assert one[k].shape == many[k].shape
+                err = O.rel_l1(many[k], one[k])
+                assert err < _tol(k.split(".")[1]), (f, k, err)
+    with pytest.raises(ValueError):
+        DepthMapStream(model, depth=1, in_flight=2)
+
+
 def test_forward_graph_matches_eager(pretrained_sd):
     """The CUDA-graph replay of the cascade returns what the launch-by-launch forward returns (several inputs through one
     captured graph; re-association noise of the atomically accumulated statistics only)."""

@@ -41,6 +41,41 @@ def test_bn_fold_and_layouts(pretrained_sd):
     assert W.pack_dynamic_conv(sd, "feature.out1", 32, 32, (1, 3), "cpu").bias.shape == (2, 32)
 
 
+def test_operand_images_match_the_library_layouts(pretrained_sd):
+    """The host packers and the kernels agree on the size of every tensor-core operand image (asked of the library, no GPU),
+    and the folded layouts put a known weight where the kernels' index arithmetic expects it."""
+    from cds_mvsnet_b200 import _lib
+    lib = _lib.LIB.load()
+    sd = pretrained_sd
+    # strided 3x3 convs on the row-streaming kernel: [kernel row][image][k-chunk][2*Cout][8 k]
+    for name, ci, co in (("downsample1", 8, 16), ("downsample2", 16, 32)):
+        w = sd[f"feature.{name}.conv.weight"]                                   # [Cout, Cin, 3, 3]
+        img = W.pack_conv2d_s2rows(w.permute(2, 3, 1, 0).reshape(9, ci, co).contiguous())
+        assert img.numel() == lib.cds_conv2d_3x3s2_rows_weight_halfs(ci, co)
+        hi = lambda t: t.half().float()
+        if ci == 8:   # image 0 = taps (dx 0, dx 2), image 1 = (dx 1, dx 1)
+            assert img[2, 0, 1, 5 // 8, 5 % 8, 3] == hi(w[5, 3, 2, 2]).half()
+            assert img[1, 1, 0, 9 // 8, 9 % 8, 6] == img[1, 1, 1, 9 // 8, 9 % 8, 6] == hi(w[9, 6, 1, 1]).half()
+            # columns [Cout, 2 Cout): what fp16 rounding of the weight dropped
+            assert img[0, 0, 0, (co + 2) // 8, (co + 2) % 8, 1] == (w[2, 1, 0, 0] - hi(w[2, 1, 0, 0])).half()
+        else:         # image dx, k-chunk = channel chunk
+            assert img[0, 2, 1, 20 // 8, 20 % 8, 4] == hi(w[20, 12, 0, 2]).half()
+    # visibility net: kernel rows folded into N: column group g <-> kernel row 2 - g
+    wgt, fp = W.pack_visnet_tc(sd, "stage_net.vis.2", "cpu")
+    assert wgt.numel() == lib.cds_visnet_tc_weight_halfs() and fp.numel() == 65
+    scale = sd["stage_net.vis.2.1.bn.weight"] / torch.sqrt(sd["stage_net.vis.2.1.bn.running_var"] + 1e-5)
+    l2 = wgt[2 * 2 * 48 * 8:].reshape(-1)[:3 * 2 * 48 * 8].reshape(3, 2, 48, 8)   # layer 2: [kw][k-chunk][column][k]
+    want = (sd["stage_net.vis.2.1.conv.weight"][7, 11, 0, 2].double() * scale[7].double()).half()   # cout 7, cin 11, kh 0, kw 2
+    assert l2[2, 1, 2 * 16 + 7, 3] == want                                                         # group 2 <-> kernel row 0
+    # row-folded DynamicConv images
+    import ctypes
+    for name in ("conv00", "conv01", "conv10", "conv20", "out2", "out3"):
+        ci, co, ks, pre = W.DYN_LAYERS[name]
+        dw = W.pack_dynamic_conv(sd, pre, ci, co, ks, "cpu")
+        kz = (ctypes.c_int * len(ks))(*ks)
+        assert W.pack_dynamic_conv_kh(dw).numel() == lib.cds_dynamic_conv_kh_weight_halfs(max(8, ci), co, len(ks), kz)
+
+
 def test_training_mode_is_refused():
     import pytest
     m = C.CDSMVSNet()
