@@ -401,7 +401,15 @@ class CostRegNet(_CachedModule):
         return self._cache
 
     def forward(self, x):
-        """[B,C,D,H,W] fp32 -> [B,1,D,H,W] fp32 logits (models/module.py:305-315)."""
+        """[B,C,D,H,W] fp32 -> [B,1,D,H,W] fp32 logits (models/module.py:305-315).
+
+        Training mode (``.train()``): BatchNorm3d with batch statistics (running statistics updated) and an autograd node whose
+        backward yields the gradients of the volume and of every parameter (train3d.py / csrc/train3d.cu, fp32)."""
+        if self.training:
+            from .train3d import costreg_train_forward
+            _dev(x)
+            with torch.cuda.device(x.device):
+                return costreg_train_forward(self, x)
         self._require_eval()
         dev = _dev(x)
         B, C, D, H, Wd = x.shape

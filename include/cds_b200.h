@@ -298,6 +298,29 @@ int cds_deconv2d_k3s2_f32(const float* in, const float* wgt, const float* bias, 
 int cds_refine_final(const float* x, const float* res_wgt, const float* depth_n, const float* lo, const float* hi, const float* post,
                      int B, int h, int w, float* out, cudaStream_t stream);
 
+/* ---- next row: CostRegNet in TRAINING mode and its backward (csrc/train3d.cu) ----------------------------
+ * fp32 planar NCDHW tensors, weights tap-major [Cin][27][Cout] (permuted on the device by the host side).  Reference:
+ * models/module.py:80-122 (Conv3d k3 p1 s1|2 -> BatchNorm3d with batch statistics -> ReLU), :125-166 (ConvTranspose3d k3 s2 p1
+ * op1 -> BN -> ReLU), :303-315 (wiring; skips are added after the ReLU); gradients as torch.autograd computes them. */
+/* direct convolution, out [B,Cout,ceil(D/s),ceil(H/s),ceil(W/s)]; also the input gradient of a stride-1 block (flipped /
+ * transposed weights) and of a transposed block (its weight as a stride-2 conv weight) */
+int cds_train_conv3d(const float* x, const float* wgt, int B, int Cin, int Cout, int D, int H, int W, int stride, float* out,
+                     cudaStream_t stream);
+/* direct transposed convolution k3 s2 p1 op1, out [B,Cout,2D,2H,2W]; also the input gradient of a stride-2 block */
+int cds_train_deconv3d(const float* x, const float* wgt, int B, int Cin, int Cout, int D, int H, int W, float* out, cudaStream_t stream);
+/* dw [Cin][27][Cout] = sum_{b,o} g[b,co,o] x[b,ci,o*s-1+tap] (x [B,Cin,D,H,W], g [B,Cout,ceil(D/s),..]); the transposed
+ * block's weight gradient is the same call with input and gradient swapped */
+int cds_train_conv3d_wgrad(const float* x, const float* g, int B, int Cin, int Cout, int D, int H, int W, int stride, float* dw,
+                           cudaStream_t stream);
+/* BatchNorm3d, batch statistics: sums [C][2] fp64 = (sum x, sum x^2) over (b, V voxels) */
+int cds_train_bn_stats(const float* x, int B, int C, long long V, double* sums, cudaStream_t stream);
+/* y = relu?(gamma (x - mean) rstd + beta) (+ skip after the ReLU; skip may be NULL) */
+int cds_train_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* skip,
+                       int relu, int B, int C, long long V, float* y, cudaStream_t stream);
+/* backward of bn_apply w.r.t. x: dx; sums [C][2] fp64 receives (dbeta, dgamma) = (sum dz, sum dz xhat), dz = dy [z > 0] */
+int cds_train_bn_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          int relu, int B, int C, long long V, double* sums, float* dx, cudaStream_t stream);
+
 /* ---- next row (first slice): backward passes of the op-level drop-ins and the stage loss ---------------- */
 /* Adjoint of cds_homo_warp in src_fea (the sampling grid carries no gradient, models/utils/warping.py:79): grad_out
  * [B,C,D,h,w] fp32 is scattered with the forward's bilinear weights into grad_src [B,C,h,w] fp32 (float reductions: the

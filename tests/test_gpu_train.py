@@ -217,3 +217,62 @@ def test_training_chain_vs_cpu_autograd():
     close(lg, lc.detach(), 1e-5, 1e-5)
     assert O.rel_l1(rg.grad.cpu(), rc.grad) < 2e-4
     assert O.rel_l1(sg.grad.cpu(), sc.grad) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------ A4 in training mode
+def _ref_costreg(in_ch, sd_prefix_sd):
+    from oracle import ref_live
+    import contextlib, io
+    _, rmodule, _, _ = ref_live.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = rmodule.CostRegNet(in_channels=in_ch, base_channels=8)
+    ref.load_state_dict(sd_prefix_sd, strict=True)
+    return ref
+
+
+@pytest.mark.parametrize("stage,shape", [(2, (1, 8, 8, 16, 24)), (1, (2, 16, 16, 8, 16)), (0, (1, 32, 8, 24, 8))],
+                         ids=["s3_c8", "s2_c16_b2", "s1_c32"])
+def test_costregnet_training_matches_reference_autograd(pretrained_sd, stage, shape):
+    """CostRegNet in training mode (BatchNorm3d batch statistics) against the live reference's module in training mode:
+    logits, gradient of the input volume, gradients of all 31 parameters, and the updated running statistics."""
+    from oracle import ref_live
+    if not ref_live.available():
+        pytest.skip("oracle/_ref/reference_models.zip not shipped (run build())")
+    pre = f"cost_regularization.{stage}."
+    sd = {k[len(pre):]: v.clone() for k, v in pretrained_sd.items() if k.startswith(pre)}
+    ref = _ref_costreg(shape[1], sd).train()
+    ours = C.CostRegNet(shape[1], 8).to(DEV)
+    ours.load_state_dict(sd, strict=True)
+    ours.train()
+    torch.manual_seed(stage)
+    x = torch.randn(*shape)
+    gout = torch.randn(shape[0], 1, *shape[2:])
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gout)
+    xo = cu(x).requires_grad_(True)
+    yo = ours(xo)
+    assert yo.requires_grad and yo.shape == yr.shape
+    yo.backward(cu(gout))
+    scale = lambda t: t.abs().max().item() + 1e-12
+    assert (yo.detach().cpu() - yr.detach()).abs().max() < 2e-4 * scale(yr)
+    assert (xo.grad.cpu() - xr.grad).abs().max() < 5e-4 * scale(xr.grad)
+    rp, op = dict(ref.named_parameters()), dict(ours.named_parameters())
+    assert rp.keys() == op.keys() and len(rp) == 31
+    for k in rp:
+        assert op[k].grad is not None, k
+        err = (op[k].grad.cpu() - rp[k].grad).abs().max().item()
+        assert err < 1e-3 * scale(rp[k].grad) + 1e-6, (k, err, scale(rp[k].grad))
+    rb, ob = dict(ref.named_buffers()), dict(ours.named_buffers())
+    for k in rb:
+        torch.testing.assert_close(ob[k].cpu().to(rb[k].dtype), rb[k], rtol=1e-4, atol=1e-5)
+    # a second step: gradients accumulate into .grad like any autograd node's, running statistics keep moving
+    ours(xo).backward(cu(gout))
+    k = "conv6.conv.weight"
+    assert (op[k].grad.cpu() - 2 * rp[k].grad).abs().max() < 2e-3 * scale(rp[k].grad)
+    # eval mode afterwards runs the tensor-core inference path on the updated statistics
+    ref(x.clone())                                  # the reference's second training step (running statistics)
+    ours.eval(); ref.eval()
+    with torch.no_grad():
+        ye, yre = ours(cu(x)), ref(x)
+    assert O.rel_l1(ye.cpu(), yre) < 5e-3           # fp16 tensor-core path against fp32
