@@ -264,10 +264,17 @@ class DynamicConv(_CachedModule):
             torch.nn.init.normal_(p, std=0.1)
 
     def forward(self, feature_vol, epipole=None, temperature=0.001):
-        self._require_eval()
-        dev = _dev(feature_vol)
+        """Training mode (``.train()``): the branch convolutions, their input and weight gradients run on csrc/train2d.cu
+        (fp32) behind an autograd node; the gate's BatchNorm2d uses batch statistics (train2d.py)."""
         if epipole is None:
             raise TypeError("DynamicConv.forward needs the epipole (the reference dereferences it unconditionally)")
+        if self.training:
+            from .train2d import dynconv_train_forward
+            _dev(feature_vol)
+            with torch.cuda.device(feature_vol.device):
+                return dynconv_train_forward(self, feature_vol, epipole, temperature)
+        self._require_eval()
+        dev = _dev(feature_vol)
         B, C, H, Wd = feature_vol.shape
         if self._cache is None:
             object.__setattr__(self, "_cache", W.pack_dynamic_conv(self._sd("x."), "x", self.in_c, self.out_c,

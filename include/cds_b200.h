@@ -321,6 +321,13 @@ int cds_train_bn_apply(const float* x, const float* mean, const float* rstd, con
 int cds_train_bn_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           int relu, int B, int C, long long V, double* sums, float* dx, cudaStream_t stream);
 
+/* DynamicConv in TRAINING mode (csrc/train2d.cu): the k x k convolutions of its branches, fp32 planar NCHW, stride 1, pad (k-1)/2,
+ * odd k <= 11; weights tap-major [Cin][k*k][Cout].  Reference: models/dynamic_conv.py:84-88,112-116.  The same call with flipped,
+ * transposed weights is the input gradient. */
+int cds_train_conv2d(const float* x, const float* wgt, int B, int Cin, int Cout, int H, int W, int k, float* out, cudaStream_t stream);
+/* dw [Cin][k*k][Cout] = sum_{b,p} g[b,co,p] x[b,ci,p + tap - (k-1)/2] */
+int cds_train_conv2d_wgrad(const float* x, const float* g, int B, int Cin, int Cout, int H, int W, int k, float* dw, cudaStream_t stream);
+
 /* ---- next row (first slice): backward passes of the op-level drop-ins and the stage loss ---------------- */
 /* Adjoint of cds_homo_warp in src_fea (the sampling grid carries no gradient, models/utils/warping.py:79): grad_out
  * [B,C,D,h,w] fp32 is scattered with the forward's bilinear weights into grad_src [B,C,h,w] fp32 (float reductions: the

@@ -276,3 +276,49 @@ def test_costregnet_training_matches_reference_autograd(pretrained_sd, stage, sh
     with torch.no_grad():
         ye, yre = ours(cu(x)), ref(x)
     assert O.rel_l1(ye.cpu(), yre) < 5e-3           # fp16 tensor-core path against fp32
+
+
+# ------------------------------------------------------------------------------------------ A6 in training mode
+@pytest.mark.parametrize("layer,hw", [("conv00", (24, 40)), ("conv01", (19, 33)), ("conv10", (16, 24)), ("out1", (12, 20))])
+def test_dynamic_conv_training_matches_reference_autograd(pretrained_sd, layer, hw):
+    """DynamicConv in training mode against the live reference's module: outputs, gradient of the input, gradients of every
+    parameter (branch convolutions, curvature convolutions, gate MLP, BatchNorm affine) and the gate's running statistics."""
+    from oracle import ref_live
+    from cds_mvsnet_b200 import weights as W
+    if not ref_live.available():
+        pytest.skip("oracle/_ref/reference_models.zip not shipped (run build())")
+    _, _, rdyn, _ = ref_live.load()
+    cin, cout, ks, pre = W.DYN_LAYERS[layer]
+    sd = {k[len(pre) + 1:]: v.clone() for k, v in pretrained_sd.items() if k.startswith(pre + ".")}
+    has_bias = any(k.endswith("convs.0.bias") for k in sd)
+    ref = rdyn.DynamicConv(cin, cout, size_kernels=ks, bias=has_bias)
+    ref.load_state_dict(sd, strict=True)
+    ref.train()
+    ours = C.DynamicConv(cin, cout, size_kernels=ks, bias=has_bias).to(DEV)
+    ours.load_state_dict(sd, strict=True)
+    ours.train()
+    torch.manual_seed(len(layer) + hw[0])
+    B = 2
+    x = torch.randn(B, cin, *hw)
+    epi = torch.tensor([[hw[1] * 1.3, -hw[0] * 0.4], [-25.0, hw[0] / 2.0]])
+    gy, gn = torch.randn(B, cout, *hw), torch.randn(B, 1, *hw)
+    T = 0.05
+    xr = x.clone().requires_grad_(True)
+    yr, nr = ref(xr, epi, T)
+    (yr * gy).sum().add((nr * gn).sum()).backward()
+    xo = cu(x).requires_grad_(True)
+    yo, no = ours(xo, cu(epi), T)
+    ((yo * cu(gy)).sum() + (no * cu(gn)).sum()).backward()
+    scale = lambda t: t.abs().max().item() + 1e-12
+    # the softmax over the branches at temperature T amplifies 1e-7 differences of the gate logits; outputs agree to ~1e-4
+    assert (yo.detach().cpu() - yr.detach()).abs().max() < 5e-4 * scale(yr)
+    assert (no.detach().cpu() - nr.detach()).abs().max() < 5e-4 * scale(nr)
+    assert (xo.grad.cpu() - xr.grad).abs().max() < 2e-3 * scale(xr.grad)
+    rp, op = dict(ref.named_parameters()), dict(ours.named_parameters())
+    assert rp.keys() == op.keys()
+    for k in rp:
+        assert op[k].grad is not None, k
+        err = (op[k].grad.cpu() - rp[k].grad).abs().max().item()
+        assert err < 2e-3 * scale(rp[k].grad) + 1e-6, (k, err, scale(rp[k].grad))
+    for k, v in ref.named_buffers():
+        torch.testing.assert_close(dict(ours.named_buffers())[k].cpu().to(v.dtype), v, rtol=1e-4, atol=1e-5)
