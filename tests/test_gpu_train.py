@@ -322,3 +322,65 @@ def test_dynamic_conv_training_matches_reference_autograd(pretrained_sd, layer, 
         assert err < 2e-3 * scale(rp[k].grad) + 1e-6, (k, err, scale(rp[k].grad))
     for k, v in ref.named_buffers():
         torch.testing.assert_close(dict(ours.named_buffers())[k].cpu().to(v.dtype), v, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ a whole training step
+def test_training_step_through_patched_reference(pretrained_sd):
+    """The reference's own CDSMVSNet in TRAINING mode (its forward with gt_depths, its StageNet with the feat_distance branch,
+    its FeatureNet / Conv2d) with the leaf operators rebound by ``patch(level="leaf")`` -- DynamicConv and CostRegNet in their
+    training forms, the differentiable warp and regression -- against the same model unpatched: outputs of every stage and the
+    gradient of every one of its parameters after one backward."""
+    from oracle import ref_live
+    if not ref_live.available():
+        pytest.skip("oracle/_ref/reference_models.zip not shipped (run build())")
+    rmodel, rmodule, _, _ = ref_live.load()
+    cfg = dict(W=96, H=64, N=3, ndepths=(8, 8, 8), ratios=(4.0, 2.0, 1.0), B=1, Dtot=48, interval=2.65 * 4)
+    s = synthetic.make_sample(cfg, "plane", seed=3)
+    imgs, dv = cu(s.imgs), cu(s.depth_values)
+    proj = {k: cu(v) for k, v in s.proj_matrices.items()}
+    gt_full = s.gt_depth if getattr(s, "gt_depth", None) is not None else None
+    T = 0.05
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        def step(model):
+            model.train()
+            with torch.no_grad():
+                model.eval()
+                pseudo = model(imgs, proj, dv, temperature=T)
+                gts = {f"stage{i}": pseudo[f"stage{i}"]["depth"].detach() * 1.01 for i in (1, 2, 3)}
+                model.train()
+            out = model(imgs, proj, dv, gt_depths=gts, temperature=T)
+            torch.manual_seed(11)
+            loss = 0.0
+            for i in (1, 2, 3):
+                o = out[f"stage{i}"]
+                loss = loss + (o["depth"] * torch.rand_like(o["depth"])).mean() / 600.0
+                loss = loss + (o["feat_distance"] * torch.rand_like(o["feat_distance"])).mean() + o["norm_curv"].mean()
+            loss.backward()
+            return out, loss.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+        ref = ref_live.build_model(pretrained_sd, cfg["ndepths"], cfg["ratios"], device=DEV, rmodel=rmodel)
+        out_r, loss_r, g_r = step(ref)
+        saved = C.patch(rmodel, rmodule, level="leaf")
+        try:
+            ours = ref_live.build_model(pretrained_sd, cfg["ndepths"], cfg["ratios"], device=DEV, rmodel=rmodel)
+            assert type(ours.cost_regularization[0]).__module__.startswith("cds_mvsnet_b200")
+            out_o, loss_o, g_o = step(ours)
+        finally:
+            C.unpatch(saved)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    for i in (1, 2, 3):
+        for name in ("depth", "feat_distance", "norm_curv"):
+            a, b = out_o[f"stage{i}"][name].detach(), out_r[f"stage{i}"][name].detach()
+            err = O.rel_l1(a.cpu(), b.cpu())
+            print(f"train step stage{i}.{name}: rel-L1 {err:.2e}")
+            assert err < 2e-3, (i, name, err)
+    assert abs(float(loss_o) - float(loss_r)) < 1e-3 * abs(float(loss_r))
+    assert g_o.keys() == g_r.keys() and len(g_r) > 200
+    worst = max(((g_o[k] - g_r[k]).abs().max().item() / (g_r[k].abs().max().item() + 1e-9), k) for k in g_r)
+    print("train step: worst parameter-gradient error (relative to the gradient's max):", worst)
+    assert worst[0] < 5e-2, worst
+    rel = torch.tensor([(g_o[k] - g_r[k]).norm().item() / (g_r[k].norm().item() + 1e-12) for k in g_r])
+    assert rel.median() < 5e-3, rel.median()
