@@ -114,3 +114,9 @@ def final_loss(inputs, depth_gt_ms, mask_ms, **kwargs):
         depth_loss, _ = _StageLossFn.apply(inputs["refined_depth"], None, depth_gt_ms["stage4"], mask_ms["stage4"], depth_interval)
         total_loss = total_loss + 2 * depth_loss
     return total_loss, depth_loss
+
+
+def temperature_for_epoch(epoch: int) -> float:
+    """The DynamicConv softmax temperature of training epoch ``epoch`` (1-based), trainer/trainer.py:45-49: one decade every
+    two epochs from 1.0 (epoch 1) down to 10^-1.5 (epoch 4), then 0.01."""
+    return float(10.0 ** (-(epoch - 1) / 2.0)) if epoch <= 4 else 0.01

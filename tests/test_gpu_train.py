@@ -384,3 +384,50 @@ def test_training_step_through_patched_reference(pretrained_sd):
     assert worst[0] < 5e-2, worst
     rel = torch.tensor([(g_o[k] - g_r[k]).norm().item() / (g_r[k].norm().item() + 1e-12) for k in g_r])
     assert rel.median() < 5e-3, rel.median()
+
+
+def test_optimizer_steps_on_the_patched_reference(pretrained_sd):
+    """A few Adam steps of the reference's training recipe on one sample -- its model (patched at "leaf"), this repository's
+    fused final_loss, the temperature schedule -- reduce the loss; afterwards the SAME module objects in eval mode run the
+    tensor-core inference kernels on the updated weights and running statistics (derived-weight caches follow the optimizer),
+    and agree with the unpatched reference loaded with the trained state dict."""
+    from oracle import ref_live
+    if not ref_live.available():
+        pytest.skip("oracle/_ref/reference_models.zip not shipped (run build())")
+    rmodel, rmodule, _, _ = ref_live.load()
+    cfg = dict(W=96, H=64, N=3, ndepths=(8, 8, 8), ratios=(4.0, 2.0, 1.0), B=1, Dtot=48, interval=2.65 * 4)
+    s = synthetic.make_sample(cfg, "plane", seed=5)
+    imgs, dv = cu(s.imgs), cu(s.depth_values)
+    proj = {k: cu(v) for k, v in s.proj_matrices.items()}
+    gt = cu(s.gt_depth)
+    # the reference's forward always returns refined_depth (= the stage-3 depth without the refinement net), so its loss always
+    # reads a "stage4" ground truth (models/losses.py:42-46)
+    gts = {"stage1": gt[:, ::4, ::4].contiguous(), "stage2": gt[:, ::2, ::2].contiguous(), "stage3": gt, "stage4": gt}
+    masks = {k: torch.ones_like(v) for k, v in gts.items()}
+    saved = C.patch(rmodel, rmodule, level="leaf")
+    try:
+        model = ref_live.build_model(pretrained_sd, cfg["ndepths"], cfg["ratios"], device=DEV, rmodel=rmodel).train()
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+        history = []
+        for it in range(4):
+            opt.zero_grad()
+            out = model(imgs, proj, dv, gt_depths=gts, temperature=losses.temperature_for_epoch(5))
+            total, _ = losses.final_loss(out, gts, masks, dlossw=[0.5, 1.0, 2.0], depth_interval=cu(torch.tensor([cfg["interval"]])))
+            assert torch.isfinite(total)
+            total.backward()
+            opt.step()
+            history.append(float(total))
+        print("training losses:", history)
+        assert history[-1] < history[0]
+        model.eval()
+        with torch.no_grad():
+            ours = model(imgs, proj, dv, temperature=0.01)
+        trained = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    finally:
+        C.unpatch(saved)
+    ref = ref_live.build_model(trained, cfg["ndepths"], cfg["ratios"], device=DEV, rmodel=rmodel)
+    with torch.no_grad():
+        want = ref(imgs, proj, dv, temperature=0.01)
+    for i in (1, 2, 3):
+        err = O.rel_l1(ours[f"stage{i}"]["depth"].cpu(), want[f"stage{i}"]["depth"].cpu())
+        assert err < 1e-3, (i, err)

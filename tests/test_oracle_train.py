@@ -91,3 +91,11 @@ def test_scatter_is_the_adjoint_of_the_gather(seed, h, w, C_, M):
 def test_scatter_of_nothing_is_zero():
     z = O.bilinear_scatter_zeros(torch.randn(1, 2, 3), torch.full((1, 3), -50.0), torch.full((1, 3), 1e6), 4, 5)
     assert z.shape == (1, 2, 4, 5) and z.abs().max() == 0
+
+
+def test_temperature_schedule():
+    """trainer/trainer.py:45-49."""
+    from cds_mvsnet_b200.losses import temperature_for_epoch
+    want = {1: 1.0, 2: 10 ** -0.5, 3: 0.1, 4: 10 ** -1.5, 5: 0.01, 17: 0.01}
+    for e, t in want.items():
+        assert abs(temperature_for_epoch(e) - t) < 1e-12
