@@ -17,8 +17,10 @@ state dict the reference's key names); they are never called.  Every forward run
 of libcds_b200.so through the C ABI and raises if the library or a B200 is missing.  Public tensors
 are fp32 NCHW / NCDHW like the reference's; the fused paths keep channels-last fp16 internally.
 ``CDSMVSNet`` covers ``refine=False`` and ``refine=True`` (``Refinement``, models/module.py:318-370).  The op-level
-``homo_warping_3D`` / ``depth_regression`` are differentiable (their backward kernels live in csrc/train.cu); the fused
-module forwards are inference only (eval mode): training-mode forwards raise NotImplementedError.
+``homo_warping_3D`` / ``depth_regression`` are differentiable (their backward kernels live in csrc/train.cu); ``CostRegNet``
+and ``DynamicConv`` switch to training forms with ``.train()`` (batch-statistics BatchNorm, full backward: train3d.py /
+train2d.py), which is what the reference's training loop needs at ``patch(level="leaf")``; the fused ``FeatureNet`` /
+``StageNet`` / ``CDSMVSNet`` forwards are inference only (eval mode): in training mode they raise NotImplementedError.
 
 ``patch(models_model, models_module, level=...)`` rebinds these names inside an imported reference tree at four depths:
 "leaf" swaps only the leaf operators (DynamicConv, CostRegNet, the warp and regression functions), "ops" also FeatureNet and keeps the reference's own ``CDSMVSNet.forward`` and ``StageNet.forward`` and swaps the operators they call,
@@ -212,8 +214,9 @@ class _CachedModule(nn.Module):
     def _require_eval(self):
         self._check_cache()
         if self.training:
-            raise NotImplementedError(f"{type(self).__name__}: the CUDA path is inference-only; call .eval() first "
-                                      "(training-mode BatchNorm / autograd are out of scope, SURVEY.md 8f-3)")
+            raise NotImplementedError(f"{type(self).__name__}: this fused CUDA path is inference-only; call .eval() first.  "
+                                      "To train, rebind the leaf operators inside the reference's own model classes: "
+                                      "patch(models.model, models.module, level=\"leaf\") (INTEGRATION.md section 7)")
 
     def _sd(self, prefix=""):
         return {prefix + k: v for k, v in self.state_dict().items()}
