@@ -134,12 +134,19 @@ def test_dynamic_conv_golden(golden, pretrained_sd, name, storage, atol):
     assert (y.cpu() - ref_y).abs().max() < 50 * atol
 
 
-def test_dynamic_conv_refuses_training_and_stride():
+def test_dynamic_conv_refuses_stride_and_switches_to_its_training_form():
     with pytest.raises(NotImplementedError):
         C.DynamicConv(8, 8, stride=2)
-    m = C.DynamicConv(8, 8).to(DEV)
+    m = C.DynamicConv(8, 8).to(DEV)          # a fresh module is in training mode: the autograd form (tests/test_gpu_train.py)
+    with torch.enable_grad():
+        y, nc = m(torch.zeros(1, 8, 16, 16, device=DEV), epipole=torch.zeros(1, 2, device=DEV))
+    assert y.requires_grad and y.shape == (1, 8, 16, 16) and nc.shape == (1, 1, 16, 16)
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 8, 16, 16, device=DEV))                       # the epipole is not optional
+    # the fused modules above it stay inference-only
+    f = C.FeatureNet(8).to(DEV)
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 8, 16, 16, device=DEV), epipole=torch.zeros(1, 2, device=DEV))
+        f(torch.zeros(1, 3, 32, 32, device=DEV), epipole=torch.zeros(1, 2, device=DEV))
 
 
 # ---------------------------------------------------------------------------------------- A7

@@ -416,7 +416,7 @@ def test_optimizer_steps_on_the_patched_reference(pretrained_sd):
             assert torch.isfinite(total)
             total.backward()
             opt.step()
-            history.append(float(total))
+            history.append(float(total.detach()))
         print("training losses:", history)
         assert history[-1] < history[0]
         model.eval()
