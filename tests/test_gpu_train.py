@@ -431,3 +431,68 @@ def test_optimizer_steps_on_the_patched_reference(pretrained_sd):
     for i in (1, 2, 3):
         err = O.rel_l1(ours[f"stage{i}"]["depth"].cpu(), want[f"stage{i}"]["depth"].cpu())
         assert err < 1e-3, (i, err)
+
+
+# ------------------------------------------------------------------------------------------ the training kernels, op by op
+@pytest.mark.parametrize("ci,co,shape,stride", [(8, 16, (5, 7, 9), 1), (3, 5, (6, 9, 130), 2), (20, 9, (4, 6, 7), 2), (1, 8, (3, 5, 300), 1)])
+def test_train_conv3d_kernels_vs_torch(ci, co, shape, stride):
+    """cds_train_conv3d / cds_train_conv3d_wgrad on odd shapes and channel counts (ragged channel tiles, partial strips, odd
+    extents under stride 2) against torch in fp64."""
+    from cds_mvsnet_b200 import train3d
+    torch.manual_seed(ci + co)
+    B = 2
+    x, w = torch.randn(B, ci, *shape), torch.randn(co, ci, 3, 3, 3) * 0.2
+    ref = torch.nn.functional.conv3d(x.double(), w.double(), stride=stride, padding=1)
+    got = train3d.conv3d(cu(x), cu(train3d._tap_conv(w)), co, stride)
+    assert got.shape == ref.shape
+    assert (got.cpu().double() - ref).abs().max() < 1e-4 * ref.abs().max()
+    g = torch.randn_like(ref).float()
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    torch.nn.functional.conv3d(xr, wr, stride=stride, padding=1).backward(g.double())
+    dw = train3d.wgrad(cu(x), cu(g), stride).reshape(ci, 3, 3, 3, co).permute(4, 0, 1, 2, 3)
+    assert (dw.cpu().double() - wr.grad).abs().max() < 2e-4 * wr.grad.abs().max()
+    if stride == 1:   # input gradient = the same kernel with flipped, transposed weights
+        dx = train3d.conv3d(cu(g), cu(w.flip(2, 3, 4).permute(0, 2, 3, 4, 1).reshape(co, 27, ci).contiguous()), ci, 1)
+        assert (dx.cpu().double() - xr.grad).abs().max() < 1e-4 * xr.grad.abs().max()
+
+
+@pytest.mark.parametrize("ci,co,shape", [(16, 8, (3, 4, 5)), (5, 12, (2, 3, 70))])
+def test_train_deconv3d_kernels_vs_torch(ci, co, shape):
+    """cds_train_deconv3d (ConvTranspose3d k3 s2 p1 op1), its input gradient (a stride-2 conv with the same weight) and its
+    weight gradient (the wgrad kernel with input and gradient swapped)."""
+    from cds_mvsnet_b200 import train3d
+    torch.manual_seed(ci * co)
+    B = 2
+    x, w = torch.randn(B, ci, *shape), torch.randn(ci, co, 3, 3, 3) * 0.2
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = torch.nn.functional.conv_transpose3d(xr, wr, stride=2, padding=1, output_padding=1)
+    got = train3d.deconv3d(cu(x), cu(train3d._tap_deconv(w)), co)
+    assert got.shape == ref.shape
+    assert (got.cpu().double() - ref.detach()).abs().max() < 1e-4 * ref.abs().max()
+    g = torch.randn_like(ref).float()
+    ref.backward(g.double())
+    dx = train3d.conv3d(cu(g), cu(w.permute(1, 2, 3, 4, 0).reshape(co, 27, ci).contiguous()), ci, 2)
+    assert (dx.cpu().double() - xr.grad).abs().max() < 1e-4 * xr.grad.abs().max()
+    dw = train3d.wgrad(cu(g), cu(x), 2).reshape(co, 3, 3, 3, ci).permute(4, 0, 1, 2, 3)
+    assert (dw.cpu().double() - wr.grad).abs().max() < 2e-4 * wr.grad.abs().max()
+
+
+@pytest.mark.parametrize("ci,co,k,hw", [(3, 11, 11, (20, 33)), (8, 19, 5, (9, 140)), (32, 35, 1, (7, 12)), (16, 4, 7, (11, 5))])
+def test_train_conv2d_kernels_vs_torch(ci, co, k, hw):
+    """Conv2dFn (cds_train_conv2d forward / input gradient, cds_train_conv2d_wgrad) for every kernel size of the feature
+    extractor, images narrower than the kernel included."""
+    from cds_mvsnet_b200.train2d import Conv2dFn
+    torch.manual_seed(k + ci)
+    x, w = torch.randn(2, ci, *hw), torch.randn(co, ci, k, k) / k
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, wr, padding=(k - 1) // 2)
+    xo, wo = cu(x).requires_grad_(True), cu(w).requires_grad_(True)
+    got = Conv2dFn.apply(xo, wo)
+    assert (got.detach().cpu().double() - ref.detach()).abs().max() < 1e-4 * ref.abs().max()
+    g = torch.randn_like(ref).float()
+    ref.backward(g.double())
+    got.backward(cu(g))
+    assert (xo.grad.cpu().double() - xr.grad).abs().max() < 1e-4 * xr.grad.abs().max()
+    assert (wo.grad.cpu().double() - wr.grad).abs().max() < 2e-4 * wr.grad.abs().max()
+    with pytest.raises(RuntimeError):   # even kernel sizes are not part of the layer
+        Conv2dFn.apply(xo, cu(torch.randn(co, ci, 4, 4)))
