@@ -335,7 +335,7 @@ def main():
     s, u8 = bench_sample(cfg, "plane", rank)
     host = {"imgs": u8.pin_memory(), "dv": s.depth_values.pin_memory(),
             "proj": {k: v.pin_memory() for k, v in s.proj_matrices.items()}}
-    d_imgs, d_dv = s.imgs.to(dev), s.depth_values.to(dev)
+    d_imgs, d_dv = u8.to(dev), s.depth_values.to(dev)   # the images as decoded from disk: bytes (conv00 takes them as they are)
     d_proj = {k: v.to(dev) for k, v in host["proj"].items()}
     B = cfg["B"]
     engine = model.engine(dev)
@@ -583,8 +583,9 @@ def main():
         "dtype": "f16" if storage == torch.float16 else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, cfg), "storage": f"{args.storage} activations, fp32 accumulate",
                    "weights": "pretrained both_dtu_blended (tests/golden/weights_both_dtu_blended.npz)",
-                   "images": "synthetic photo-consistent plane views quantised to 8 bits (as the reference's loader reads them): "
-                             "fp32 = u8 / 255 resident in HBM for `value`, uint8 in pinned host memory for `e2e`",
+                   "images": "synthetic photo-consistent plane views quantised to 8 bits (as the reference's loader reads them before "
+                             "np.float32(img) / 255.): uint8 resident in HBM for `value`, uint8 in pinned host memory for `e2e`; the "
+                             "division is folded into conv00 (byte / 256 operands, 256 / 255 in its weights)",
                    "parallelism": f"replicas x{world}, work-list sharding, no collective",
                    "launch": "one CUDA graph per forward" if use_graph else "launch by launch",
                    "maps_in_flight": F,

@@ -57,8 +57,13 @@ constexpr bool KH_TIGHT = true;
 __host__ __device__ constexpr int kh_npad(int cout) { return KH_TIGHT ? (cout + 3 + 3) / 4 * 4 : (cout + 3 + 15) / 16 * 16; }
 __host__ __device__ constexpr int kh_ncols(int cout, int k) { return KH_TIGHT ? (k * kh_npad(cout) + 15) / 16 * 16 + 16 : k * kh_npad(cout); }
 
-template <int K0_, int K1_, int K2_, int CIN_, int COUT_, int TY_, bool SPLIT_>
+// PX2 (the image layer on 8-bit images): a pixel's 8-channel operand slot holds (RGB of the pixel, RGB of its right neighbour,
+// 0, 0) as byte / 256, so ONE K = 16 MMA covers FOUR horizontal taps (two slots two pixels apart) instead of two; the factor
+// 256 / 255 of the loader's normalisation is folded into the weights.  byte / 256 is exact in fp16: no residual channels.
+template <int K0_, int K1_, int K2_, int CIN_, int COUT_, int TY_, bool SPLIT_, bool PX2_ = false>
 struct Kh {
+    static constexpr bool PX2 = PX2_;
+    static_assert(!PX2_ || (CIN_ == 8 && !SPLIT_), "pixel-pair slots exist for the image layer only");
     static constexpr int NK = K2_ > 0 ? 3 : 2;
     static constexpr int CIN = CIN_, COUT = COUT_, C8 = CIN_ / 8, TY = TY_;
     static constexpr bool SPLIT = SPLIT_;
@@ -71,7 +76,7 @@ struct Kh {
     static constexpr int TXO = TX - 2 * HMAX;
     static constexpr int NPAD = kh_npad(COUT_);
     static constexpr int SLOTS = KH_TIGHT ? TY_ + 1 : TY_;      // accumulator slots per branch (+ the spare one)
-    __host__ __device__ static constexpr int nj(int b) { return C8 == 1 ? (kb(b) + 1) / 2 : kb(b) * C8 / 2; }
+    __host__ __device__ static constexpr int nj(int b) { return PX2_ ? (kb(b) + 3) / 4 : (C8 == 1 ? (kb(b) + 1) / 2 : kb(b) * C8 / 2); }
     __host__ __device__ static constexpr int nbf(int b) { return kh_ncols(COUT_, kb(b)); }        // columns of a branch's weight image
     __host__ __device__ static constexpr int reg(int b) { return b * SLOTS * NPAD; }              // TMEM column base
     static constexpr int ACC_COLS = NK * SLOTS * NPAD;
@@ -107,6 +112,7 @@ struct KhParams {
     int in_act, nc_mode, H, W, n_images;
     int n_items;              // plain batch: items; pair batch: see pair_v / pair_b
     int pair_v, pair_b;       // pair batch (conv00): items are (side, v, b); the side-0 items v*pair_b + b of b share one image
+    int x_pad;                // PX2: the image rows carry this many pad pixels on either side (their slots hold the true neighbours)
     int xt, yt, nz;           // tiles along x, y and item groups
     float epi_scale, inv_temperature;
 };
@@ -166,9 +172,9 @@ __device__ __forceinline__ void issue_one(uint32_t a_row16, uint32_t b16, uint32
         constexpr int hb = C::hb(B);
         constexpr uint32_t plane = P == 2 ? 1u : 0u;
         constexpr uint32_t a_start = plane * (C::C8 * (SLAB >> 4)) +
-                                     (C::C8 == 1 ? (uint32_t)(C::HMAX - hb + 2 * J)
+                                     (C::C8 == 1 ? (uint32_t)(C::HMAX - hb + (C::PX2 ? 4 : 2) * J)
                                                  : (uint32_t)(((2 * J) % C::C8) * (SLAB >> 4) + (C::HMAX - hb + (2 * J) / C::C8)));
-        constexpr uint32_t a_lbo = C::C8 == 1 ? 1u : (uint32_t)(SLAB >> 4);
+        constexpr uint32_t a_lbo = C::C8 == 1 ? (C::PX2 ? 2u : 1u) : (uint32_t)(SLAB >> 4);
         constexpr uint32_t b_start = (C::b_off(B, P == 1 ? 1 : 0) + (uint32_t)J * 2 * C::nbf(B) * 16) >> 4;
         constexpr uint32_t b_lbo = (uint32_t)C::nbf(B);                 // (k_b * NPAD columns) * 16 B >> 4
         const uint64_t da = ((uint64_t)desc_hi << 32) | ((a_row16 + a_start) | (a_lbo << 16));
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
 #pragma unroll
                     for (int pl = 0; pl < C::PLANES; ++pl) {
                         if (C8 == 1) {
-                            tc::tma_load_4d(dst + pl * SLAB, &tmap, ring_full + slot, 2 * (q.x0 - HMAX), R, img + pl * p.n_images, 0);
+                            tc::tma_load_4d(dst + pl * SLAB, &tmap, ring_full + slot, 2 * (q.x0 - HMAX + p.x_pad), R, img + pl * p.n_images, 0);
                         } else {
 #pragma unroll
                             for (int c8 = 0; c8 < C8; ++c8)
@@ -661,8 +667,9 @@ int launch_kh(const void* x, KhParams p, cudaStream_t st) {
     const uint64_t H = p.H, W = p.W, NI = (uint64_t)p.n_images * C::PLANES;
     bool ok;
     if (C::C8 == 1) {   // 16-byte pixels viewed as 8-byte elements: a box row is 2 KB (128 pixels)
-        const uint64_t dims[4] = {2 * W, H, NI, 1};
-        const uint64_t strides[4] = {0, W * 16, H * W * 16, NI * H * W * 16};
+        const uint64_t Wp = W + 2 * (uint64_t)p.x_pad;
+        const uint64_t dims[4] = {2 * Wp, H, NI, 1};
+        const uint64_t strides[4] = {0, Wp * 16, H * Wp * 16, NI * H * Wp * 16};
         const uint32_t box[4] = {2 * TX, 1, 1, 1};
         ok = tma::make_u64(&tmap, x, 4, dims, strides, box);
     } else {            // (8 ch, chunk, W, H, image): one box per 8-channel chunk lands as a slab
@@ -703,15 +710,19 @@ int cds_dynamic_conv_kh_supported(int Cin, int Cout, int H, int W, int num_kerne
 }
 
 // fp16 elements of the packed weight image: per branch two images (weights, residuals) of nj steps x 2 k-chunks x k*NPAD columns x 8
-int cds_dynamic_conv_kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks) {
+static int kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks, bool px2) {
     const int c8 = Cin / 8;
     long long n = 0;
     for (int b = 0; b < num_kernels; ++b) {
-        const int nj = c8 == 1 ? (ks[b] + 1) / 2 : ks[b] * c8 / 2;
+        const int nj = px2 ? (ks[b] + 3) / 4 : (c8 == 1 ? (ks[b] + 1) / 2 : ks[b] * c8 / 2);
         n += 2ll * nj * 2 * kh_ncols(Cout, ks[b]) * 8;
     }
     return (int)n;
 }
+int cds_dynamic_conv_kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* ks) { return kh_weight_halfs(Cin, Cout, num_kernels, ks, false); }
+/* the image layer on 8-bit images (pixel-pair slots, see cds_dynamic_conv_kh_u8) */
+int cds_dynamic_conv_kh_u8_weight_halfs(int Cout, int num_kernels, const int* ks) { return kh_weight_halfs(8, Cout, num_kernels, ks, true); }
+int cds_dynamic_conv_kh_u8_pad(void) { return 8; }
 
 // layout of the packed weight images (the host packer asks instead of restating it): columns per kernel-row group, columns
 // of one image of a k x k branch (groups, then zero padding)
@@ -758,6 +769,61 @@ int cds_dynamic_conv_kh(const void* x, int n_images, const int* img_index, const
     if (lid == 7) return launch_kh<Kh<1, 3, 0, 16, 16, TY16, false>, 1>(x, p, stream);
     if (lid == 8) return launch_kh<Kh<1, 3, 0, 8, 8, TY8H, false>, 1>(x, p, stream);
     return launch_kh<Kh<1, 3, 0, 32, 32, TY32, false>, 1>(x, p, stream);
+}
+
+// ---- the image layer on 8-bit images -----------------------------------------------------------------------------------------------
+// img [n_images,3,H,W] uint8 -> px2 [n_images,H,W + 2*pad,8] fp16: slot of padded column xp (x = xp - pad) = (R,G,B of pixel x,
+// R,G,B of pixel x+1, 0, 0) as byte / 256 (exact in fp16; 256 / 255 is folded into the weights), zeros outside the image
+__global__ void __launch_bounds__(256) image_u8_to_px2_kernel(const unsigned char* __restrict__ img, int H, int W, int pad, __half* __restrict__ out) {
+    const int Wp = W + 2 * pad, n = blockIdx.z, y = blockIdx.y, xp = blockIdx.x * 256 + threadIdx.x;
+    if (xp >= Wp) return;
+    const int x = xp - pad;
+    const size_t plane = (size_t)H * W;
+    const unsigned char* base = img + (size_t)n * 3 * plane + (size_t)y * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+        if (x + q >= 0 && x + q < W) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[3 * q + c] = (float)__ldg(base + (size_t)c * plane + x + q) * (1.f / 256.f);
+        }
+    Vec8<__half>::store(out + (((size_t)n * H + y) * Wp + xp) * 8, v);
+}
+
+int cds_image_u8_to_px2(const unsigned char* img, int n_images, int H, int W, void* out, cudaStream_t stream) {
+    CDS_REQUIRE(img && out && n_images > 0 && n_images <= 65535 && H > 0 && H <= 65535 && W > 0, CDS_EARG, "cds_image_u8_to_px2: bad arguments");
+    const int pad = cds_dynamic_conv_kh_u8_pad();
+    image_u8_to_px2_kernel<<<dim3(cds_div_up(W + 2 * pad, 256), H, n_images), 256, 0, stream>>>(img, H, W, pad, (__half*)out);
+    return cds_check_launch("cds_image_u8_to_px2");
+}
+
+// The image layer (3 -> 8 channels, kernel sizes 3, 7, 11; models/module.py:211) on pixel-pair slots built by
+// cds_image_u8_to_px2: half the MMAs of cds_dynamic_conv_kh's image layer.  wgt_packed: cds_dynamic_conv_kh_u8_weight_halfs()
+// halfs with the loader's 1/255 folded in (host: weights.py pack_dynamic_conv_kh(px2=True)).  pair_v > 0: the cascade's pair
+// batch, as cds_dynamic_conv_kh.
+int cds_dynamic_conv_kh_u8(const void* px2, int n_images, const int* img_index, const float* epipole, float epi_scale, const void* wgt_packed,
+                           const float* gate, int n, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
+                           void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs,
+                           int pair_v, int pair_b, cudaStream_t stream) {
+    CDS_REQUIRE(px2 && epipole && wgt_packed && gate && out_raw && kernel_sizes, CDS_EARG, "cds_dynamic_conv_kh_u8: null pointer");
+    CDS_REQUIRE(n > 0 && n <= 65535 && n_images > 0, CDS_ESHAPE, "cds_dynamic_conv_kh_u8: bad batch");
+    CDS_REQUIRE(temperature > 0.f, CDS_EARG, "cds_dynamic_conv_kh_u8: temperature must be positive");
+    CDS_REQUIRE(kh_layer_id(8, Cout, num_kernels, kernel_sizes) == 1 && W >= 8, CDS_EUNSUPPORTED,
+                "cds_dynamic_conv_kh_u8: the image layer only (8 output channels, kernel sizes 3, 7, 11)");
+    constexpr int TY8 = KH_TIGHT ? 13 : 10;
+    KhParams p{};
+    p.img_index = img_index; p.epipole = epipole; p.wgt = (const __half*)wgt_packed; p.gate = gate;
+    p.out_raw = (__half*)out_raw; p.out_lo = (__half*)out_lo; p.out_stats = out_stats; p.norm_curv = norm_curv; p.nc_sq = nc_sq;
+    p.nc_abs = nc_abs; p.nc_mode = nc_mode; p.H = H; p.W = W; p.n_images = n_images; p.n_items = n;
+    p.pair_v = pair_v; p.pair_b = pair_b; p.epi_scale = epi_scale; p.inv_temperature = 1.f / temperature;
+    p.x_pad = cds_dynamic_conv_kh_u8_pad();
+    if (pair_v > 0) {
+        CDS_REQUIRE(img_index && n == 2 * pair_v * pair_b, CDS_EARG, "cds_dynamic_conv_kh_u8: the pair batch needs img_index and n = 2 V B");
+        return launch_kh<Kh<3, 7, 11, 8, 8, TY8, false, true>, 4>(px2, p, stream);
+    }
+    return launch_kh<Kh<3, 7, 11, 8, 8, TY8, false, true>, 1>(px2, p, stream);
 }
 
 }  // extern "C"

@@ -70,6 +70,7 @@ class FeatureExtractor:
         # 2.6e-3 -> 9e-4).  CDS_SPLIT=0 turns it off (diagnostics only).
         self.split_precision = os.environ.get("CDS_SPLIT", "1") != "0"
         self.use_tc2d = use_tc and os.environ.get("CDS_USE_TC", "1") != "0" and os.environ.get("CDS_TC_CONV2D", "1") != "0"
+        self.use_u8 = os.environ.get("CDS_U8_CONV00", "1") != "0"   # 8-bit images straight into conv00 (pixel-pair operand slots)
         self.use_rows = os.environ.get("CDS_S2_ROWS", "1") != "0"   # stride-2 layers on the row-streaming kernel (conv2d_s2rows.cu)
         # inner1/inner2 (1x1 conv over the concatenation): the 2x2-block CUDA-core form (fp32 math, 0.154 / 0.133 ms at cfg2) beats the
         # gather-form tensor-core kernel (0.289 / 0.156 ms) on this 24- / 48-deep contraction; CDS_TC_INNER=1 selects the latter
@@ -86,9 +87,20 @@ class FeatureExtractor:
         e = _esize(self.storage)
         px = n * H * W
         flops = 2.0 * sum(k * k for k in w.ksizes) * w.cin * (w.cout + 3) * px
-        nbytes = px * (w.cin * (4 if in_mode == 1 else e) + w.cout * e + 8)
+        nbytes = px * (w.cin * ((1 if x.dtype == torch.uint8 else 4) if in_mode == 1 else e) + w.cout * e + 8)
         _lib.set_tag("feat." + name, (flops, float(nbytes)))
         ks = _ksizes(w.ksizes)
+        if in_mode == 1 and x.dtype == torch.uint8:
+            # 8-bit images: pixel-pair operand slots, four taps per MMA (csrc/dynconv_kh.cu, cds_dynamic_conv_kh_u8)
+            n_images = x.shape[0]
+            pad = _lib.LIB.load().cds_dynamic_conv_kh_u8_pad()
+            px2 = self._buf.get("f.img_px2", (n_images, H, W + 2 * pad, 8), torch.float16)
+            call("cds_image_u8_to_px2", ptr(x), n_images, H, W, ptr(px2))
+            pv, pb = self.pairs if (self.pairs is not None and self.share_ref) else (0, 0)
+            call("cds_dynamic_conv_kh_u8", ptr(px2), n_images, ptr(img_index), ptr(epi), float(epi_scale), ptr(w.kh_u8), ptr(w.gate),
+                 n, w.cout, H, W, len(w.ksizes), ks, float(T), ptr(out), ptr(out_lo), ptr(out_stats), ptr(norm_curv), ptr(nc_sq),
+                 nc_mode, ptr(nc_abs), pv, pb)
+            return
         if (self.use_tc and w.tc is not None and self.storage == torch.float16
                 and _lib.LIB.load().cds_dynamic_conv_tc_supported(max(8, w.cin), w.cout, H, W, len(w.ksizes), ks)):
             n_images = n
@@ -164,8 +176,14 @@ class FeatureExtractor:
                 return False
         return True
 
+    def u8_ok(self, H, W) -> bool:
+        """conv00 can take the 8-bit images as they are (pixel-pair slots): the row-folded tensor-core path with its operand image."""
+        w = self.fw.dyn["conv00"]
+        return (self.use_u8 and self.use_tc and self.use_kh and self.storage == torch.float16 and w.kh_u8 is not None
+                and bool(_lib.LIB.load().cds_dynamic_conv_kh_supported(8, w.cout, H, W, len(w.ksizes), _ksizes(w.ksizes))))
+
     def run(self, buf: Buffers, imgs, img_index, epipoles, n, H, W, temperature, pairs=None, after_stage1=None):
-        """imgs: planar fp32 [*,3,H,W]; img_index int32 [n]; epipoles fp32 [n,2].
+        """imgs: planar fp32 [*,3,H,W] (or uint8 when ``u8_ok``); img_index int32 [n]; epipoles fp32 [n,2].
         Returns {stage: (fea [n,h,w,C] storage dtype, nc_sq [n,h,w] fp32, nc_abs [n,h,w] fp32)}."""
         st, dt = self.storage, self.dt
         self._buf = buf
@@ -564,14 +582,22 @@ class CascadeEngine:
             raise AssertionError("need at least one source view")
         V = N - 1
         dev = self.device
+        u8_work = None
         if imgs.dtype == torch.uint8:
             # 8-bit images as the data layer reads them (datasets/general_eval.py:74: np.float32(img) / 255.): uploaded as bytes
-            # (a quarter of the PCIe traffic) and divided here -- the IEEE fp32 quotient is bit-identical to the host's
+            # (a quarter of the PCIe traffic).  conv00 takes them as they are (k / 256 in pixel-pair operand slots, 256 / 255 in
+            # its weights); only the Refinement network (refine=True) needs the fp32 image, divided here -- the IEEE fp32
+            # quotient is bit-identical to the host's.
             u8 = imgs.to(device=dev).contiguous()
-            imgs = self.buf.get("in.imgs_f32", tuple(u8.shape), torch.float32)
-            kcall("image_u8_to_f32", 0, 5 * u8.numel(), "cds_image_u8_to_f32", ptr(u8), u8.numel(), ptr(imgs))
             self._keep_u8 = u8
-        imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
+            Hw, Ww = (H // 2, W // 2) if self.refiner is not None else (H, W)
+            if self.features.u8_ok(Hw, Ww):
+                u8_work = u8
+            if u8_work is None or self.refiner is not None:
+                imgs = self.buf.get("in.imgs_f32", tuple(u8.shape), torch.float32)
+                kcall("image_u8_to_f32", 0, 5 * u8.numel(), "cds_image_u8_to_f32", ptr(u8), u8.numel(), ptr(imgs))
+        if imgs.dtype != torch.uint8:
+            imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
         full_imgs, Hf, Wf = imgs, H, W
         if self.refiner is not None:
             # refine=True: the cascade works at half resolution on nearest-subsampled images (models/model.py:145-147: the
@@ -579,9 +605,14 @@ class CascadeEngine:
             if H % 64 or W % 64:
                 raise RuntimeError(f"refine=True needs H and W divisible by 64 (got {H}x{W}); see SURVEY.md 8c fixture 6")
             H, W = H // 2, W // 2
-            half = self.buf.get("rf.imgs_half", (B, N, 3, H, W), torch.float32)
-            half.copy_(imgs[..., ::2, ::2])
-            imgs = half
+            if u8_work is not None:
+                half8 = self.buf.get("rf.imgs_half_u8", (B, N, 3, H, W), torch.uint8)
+                half8.copy_(u8_work[..., ::2, ::2])
+                u8_work = half8
+            else:
+                half = self.buf.get("rf.imgs_half", (B, N, 3, H, W), torch.float32)
+                half.copy_(imgs[..., ::2, ::2])
+                imgs = half
         if H % 32 or W % 32:
             raise RuntimeError(f"H and W must be divisible by 32 (got {H}x{W}); see SURVEY.md 8c fixture 6")
         depth_values = depth_values.to(device=dev, dtype=torch.float32).contiguous()
@@ -610,7 +641,7 @@ class CascadeEngine:
                 stage1["out"] = self.stage(0, feat1, coef[0], depth_values, None, B, V, H, W)
             stage1["main"] = main
 
-        feats = self.features.run(self.buf, imgs, self._imgidx, epi, n, H, W, temperature, pairs=(V, B),
+        feats = self.features.run(self.buf, u8_work if u8_work is not None else imgs, self._imgidx, epi, n, H, W, temperature, pairs=(V, B),
                                   after_stage1=start_stage1 if overlap else None)
         depth = None
         for s in range(len(self.ndepths)):

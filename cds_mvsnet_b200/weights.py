@@ -62,6 +62,7 @@ class DynWeights:
     gate: torch.Tensor     # 4K + 4 + 4K floats
     tc: torch.Tensor | None = None   # fp16 tensor-core operand image of csrc/dynconv_tc.cu (tap GEMM)
     kh: torch.Tensor | None = None   # fp16 operand images of csrc/dynconv_kh.cu (kernel rows folded into N; trunk layers)
+    kh_u8: torch.Tensor | None = None   # conv00 only: the pixel-pair form for 8-bit images (cds_dynamic_conv_kh_u8)
 
 
 def pack_dynamic_conv(sd, prefix, cin, cout, ksizes, device) -> DynWeights:
@@ -159,7 +160,7 @@ def kh_layout(cout: int, k: int) -> tuple[int, int]:
     return int(lib.cds_dynamic_conv_kh_group_cols(cout)), int(lib.cds_dynamic_conv_kh_image_cols(cout, k))
 
 
-def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
+def pack_dynamic_conv_kh(w: DynWeights, px2: bool = False) -> torch.Tensor:
     """fp16 B-operand images for csrc/dynconv_kh.cu (kernel rows folded into N; Cin 3 is padded to 8 with the image's
     residual channels).
 
@@ -168,7 +169,14 @@ def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
     row dy = k-1-g (so that group g feeds output row y = R - h + g of input row R), c < Cout the feature weights, c in
     [Cout, Cout+3) the curvature weights (a, b, c), the rest -- and the columns from k*NPAD to NCOLS -- zero; NPAD and NCOLS
     come from ``kh_layout``.  K: Cin <= 8: step j = horizontal taps (2j, 2j+1) x 8 channels (zero past the kernel); Cin > 8:
-    tap (2j)//C8, channel chunks (2j)%C8 and +1."""
+    tap (2j)//C8, channel chunks (2j)%C8 and +1.
+
+    ``px2`` (the image layer on 8-bit images, cds_dynamic_conv_kh_u8): an operand slot holds (RGB of a pixel, RGB of its right
+    neighbour, 0, 0) as k / 256 for the byte k (exact in fp16), so step j covers the FOUR taps 4j .. 4j+3 -- k-chunk q = taps
+    (4j+2q, 4j+2q+1), K rows 0-2 / 3-5 their RGB weights -- and the factor 256 / 255 that turns k / 256 into the loader's
+    k / 255 is folded into the weights before the hi / lo split."""
+    if px2 and w.cin != 3:
+        raise ValueError("pixel-pair operand slots exist for the 3-channel image layer only")
     cin, cout = w.cin, w.cout
     c8 = max(1, cin // 8)
     att, conv = w.w_att.detach().cpu().double(), w.w_conv.detach().cpu().double()
@@ -181,15 +189,23 @@ def pack_dynamic_conv_kh(w: DynWeights) -> torch.Tensor:
                 src = t0 + dy * k + dx
                 full[dy, dx, :cin, :cout] = conv[src]
                 full[dy, dx, :cin, cout:cout + 3] = att[src][:, :3]
-        if cin == 3:   # channels 3..5 of the operand carry the image's fp16 rounding residual (cds_image_to_nhwc8)
+        if px2:
+            full = full * (256.0 / 255.0)   # the slots hold k / 256 (exact in fp16, weights stay in fp16's normal range)
+        elif cin == 3:   # channels 3..5 of the operand carry the image's fp16 rounding residual (cds_image_to_nhwc8)
             full[:, :, 3:6, :] = full[:, :, 0:3, :]
         t0 += k * k
         hi = full.to(torch.float16).to(torch.float64)
-        nj = (k + 1) // 2 if c8 == 1 else k * c8 // 2
+        nj = (k + 3) // 4 if px2 else ((k + 1) // 2 if c8 == 1 else k * c8 // 2)
         for img_w in (hi, full - hi):
             img = torch.zeros(nj, 2, ncols, 8, dtype=torch.float64)             # [step, k-chunk, column n, 8 k]
             for j in range(nj):
                 for q in range(2):
+                    if px2:
+                        for half, dx in enumerate((4 * j + 2 * q, 4 * j + 2 * q + 1)):
+                            if dx < k:
+                                for g in range(k):
+                                    img[j, q, g * npad:(g + 1) * npad, 3 * half:3 * half + 3] = img_w[k - 1 - g, dx, 0:3, :].t()
+                        continue
                     if c8 == 1:
                         dx, ch = 2 * j + q, 0
                     else:
@@ -506,6 +522,8 @@ def pack_feature(sd, device) -> FeatureWeights:
         dyn[n].tc = pack_dynamic_conv_tc(dyn[n])
         if n in KH_LAYERS:
             dyn[n].kh = pack_dynamic_conv_kh(dyn[n])
+            if dyn[n].cin == 3:
+                dyn[n].kh_u8 = pack_dynamic_conv_kh(dyn[n], px2=True)
     fw = FeatureWeights(dyn, pack_conv2d(sd, "feature.downsample1.conv.weight", device),
                         pack_conv2d(sd, "feature.downsample2.conv.weight", device),
                         pack_conv2d(sd, "feature.inner1.conv.weight", device).reshape(48, 16),

@@ -218,6 +218,17 @@ int cds_dynamic_conv_tc_pairs(const void* x, int n_images, const int* img_index,
  * pack_dynamic_conv_kh): weights AND their fp16 rounding residuals, multiplied as separate accumulating products. */
 int cds_dynamic_conv_kh_supported(int Cin, int Cout, int H, int W, int num_kernels, const int* kernel_sizes);
 int cds_dynamic_conv_kh_weight_halfs(int Cin, int Cout, int num_kernels, const int* kernel_sizes);
+/* The image layer on 8-BIT images (the bytes the reference's loader reads before np.float32(img) / 255.,
+ * datasets/general_eval.py:88-91): cds_image_u8_to_px2 builds pixel-pair operand slots -- (RGB of the pixel, RGB of its right
+ * neighbour, 0, 0) as byte / 256 (exact in fp16), rows padded by cds_dynamic_conv_kh_u8_pad() pixels on either side -- so that one
+ * K = 16 MMA covers four horizontal taps; the factor 256 / 255 is folded into the weights.  Same outputs as the fp32-image path to fp32 rounding. */
+int cds_dynamic_conv_kh_u8_weight_halfs(int Cout, int num_kernels, const int* kernel_sizes);
+int cds_dynamic_conv_kh_u8_pad(void);
+int cds_image_u8_to_px2(const unsigned char* img, int n_images, int H, int W, void* out, cudaStream_t stream);
+int cds_dynamic_conv_kh_u8(const void* px2, int n_images, const int* img_index, const float* epipole, float epi_scale, const void* wgt_packed,
+                           const float* gate, int n, int Cout, int H, int W, int num_kernels, const int* kernel_sizes, float temperature,
+                           void* out_raw, void* out_lo, double* out_stats, float* norm_curv, float* nc_sq, int nc_mode, float* nc_abs,
+                           int pair_v, int pair_b, cudaStream_t stream);
 /* layout of the packed images: columns of one kernel-row group (Cout + 3 curvature columns, rounded up), columns of one image
  * of a k x k branch (k groups + zero padding) */
 int cds_dynamic_conv_kh_group_cols(int Cout);

@@ -164,3 +164,64 @@ def test_kh_rejects_unsupported():
         call("cds_dynamic_conv_kh", ptr(z), 1, None, None, 0, ptr(z), 1.0, ptr(z), None, ptr(z), 1, 8, 8, 16, 16, 2, kz, T, 0, ptr(z),
              None, None, None, None, 0, None, 0, 0)
     assert _lib.LIB.load().cds_dynamic_conv_kh_supported(8, 8, 16, 16, 2, kz) == 0
+
+
+@pytest.mark.parametrize("V,B,hw", [(4, 1, (24, 150)), (2, 2, (33, 130)), (1, 1, (9, 128)), (3, 1, (40, 8)), (4, 1, (105, 1300))],
+                         ids=lambda v: f"{v[0]}x{v[1]}" if isinstance(v, tuple) else str(v))
+def test_kh_image_layer_on_8bit_images(pretrained_sd, V, B, hw):
+    """conv00 on 8-bit images: pixel-pair operand slots (byte / 256, four horizontal taps per MMA, 256 / 255 folded into the
+    weights) against the oracle on float32(byte) / 255 -- the pair batch and the plain batch, value + residual planes -- and
+    against the fp32-image path of the same kernel."""
+    w, cin, cout, ks, pre = _weights(pretrained_sd, "conv00")
+    w.kh_u8 = W.pack_dynamic_conv_kh(w, px2=True)
+    lib = _lib.LIB.load()
+    kz = (ctypes.c_int * len(ks))(*ks)
+    assert w.kh_u8.numel() == lib.cds_dynamic_conv_kh_u8_weight_halfs(cout, len(ks), kz)
+    torch.manual_seed(V * 10 + B + hw[1])
+    N = V + 1
+    u8 = torch.randint(0, 256, (B * N, 3, *hw), dtype=torch.uint8)
+    imgs = u8.float() / 255.0
+    n = 2 * V * B
+    idx = torch.empty(2, V, B, dtype=torch.int32)
+    for v in range(V):
+        for b in range(B):
+            idx[0, v, b], idx[1, v, b] = b * N, b * N + v + 1
+    idx = idx.reshape(-1)
+    epi = torch.randn(n, 2) * hw[1]
+    x_items = torch.stack([imgs[int(i)] for i in idx])
+    ref_y, ref_nc = O.dynamic_conv(x_items, pretrained_sd, pre, ks, epi, T)
+    pad = lib.cds_dynamic_conv_kh_u8_pad()
+    px2 = torch.full((B * N, hw[0], hw[1] + 2 * pad, 8), float("nan"), device=DEV, dtype=torch.float16)
+    uc = cu(u8)
+    call("cds_image_u8_to_px2", ptr(uc), B * N, hw[0], hw[1], ptr(px2))
+    torch.cuda.synchronize()
+    assert not torch.isnan(px2).any()
+    got = px2[:, :, pad:pad + hw[1], :3].float().cpu() * 256.0
+    assert torch.equal(got, u8.permute(0, 2, 3, 1).float())                                  # exact bytes, own pixel
+    assert torch.equal(px2[:, :, pad - 1, 3:6].float().cpu() * 256.0, u8[:, :, :, 0].permute(0, 2, 1).float())   # left pad slot: its right neighbour
+    assert px2[:, :, pad + hw[1] - 1, 3:6].abs().max() == 0 and px2[..., 6:].abs().max() == 0
+    res = []
+    for pv, pb in ((V, B), (0, 0)):
+        out = torch.full((n, *hw, cout), float("nan"), device=DEV, dtype=torch.float16)
+        out_lo = torch.full_like(out, float("nan"))
+        ostats = torch.zeros(n, cout, 2, device=DEV, dtype=torch.float64)
+        nc = torch.full((n, *hw), float("nan"), device=DEV)
+        ncsq = torch.full((n, *hw), float("nan"), device=DEV)
+        ic, ec = cu(idx), cu(epi)
+        call("cds_dynamic_conv_kh_u8", ptr(px2), B * N, ptr(ic), ptr(ec), 1.0, ptr(w.kh_u8), ptr(w.gate), n, cout, hw[0], hw[1], len(ks), kz, T,
+             ptr(out), ptr(out_lo), ptr(ostats), ptr(nc), ptr(ncsq), 0, None, pv, pb)
+        torch.cuda.synchronize()
+        y = (out.float() + out_lo.float()).cpu().permute(0, 3, 1, 2)
+        assert not torch.isnan(y).any() and not torch.isnan(nc).any()
+        ey, en = O.rel_l1(y, ref_y), O.rel_l1(nc.cpu().unsqueeze(1), ref_nc)
+        print(f"kh conv00 u8 pairs={pv > 0} {hw}: out {ey:.2e} curv {en:.2e}")
+        assert ey < 5e-5 and en < 5e-5
+        torch.testing.assert_close(ostats.cpu(), _stats(y), rtol=2e-3, atol=2e-2 * hw[0] * hw[1] ** 0.5)
+        res.append(y)
+    assert O.rel_l1(res[0], res[1]) < 1e-6
+    # the fp32-image path of the same layer
+    img8 = torch.empty(B * N, *hw, 8, device=DEV, dtype=torch.float16)
+    fc = cu(imgs)
+    call("cds_image_to_nhwc8", ptr(fc), B * N, hw[0], hw[1], ptr(img8))
+    out, out_lo, _, _, _, _ = _run_kh(w, img8, B * N, cu(idx), None, 0, cu(epi), n, 8, cout, hw, ks, 0, pv=V, pb=B)
+    assert O.rel_l1((out.float() + out_lo.float()).cpu().permute(0, 3, 1, 2), res[0]) < 5e-5
