@@ -27,7 +27,7 @@ model = C.CDSMVSNet(refine=False, ndepths=cfg["ndepths"], depth_interals_ratio=c
 model.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})
 model = model.cuda().eval()
 s = synthetic.make_sample(cfg, "plane", seed=0)
-imgs, dv = s.imgs.cuda(), s.depth_values.cuda()
+imgs, dv = (s.imgs.clamp(0, 1) * 255.0).round().to(torch.uint8).cuda(), s.depth_values.cuda()   # 8-bit images, as bench.py holds them
 proj = {k: v.cuda() for k, v in s.proj_matrices.items()}
 eng = model.engine(torch.device("cuda", 0))
 for _ in range(args.iters):
