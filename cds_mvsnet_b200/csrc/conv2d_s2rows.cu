@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(NTHREADS, C::MINB) conv2d_s2rows_kernel(const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB), sR_u = tc::smem_u32(sR);
     const int ntiles = p.xt * p.yt * p.n;
+    // a contiguous run of tiles per CTA: one or two image changes (norm coefficients, statistics flush) instead of one every few tiles
+    const int t_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x), t_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     if (threadIdx.x == 32) {
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, C::MINB) conv2d_s2rows_kernel(const 
             tc::mbar_expect_tx(bar_b, C::B_BYTES);
             tc::bulk_copy_g2s(sB_u, p.wgt, C::B_BYTES, bar_b);
             uint32_t rc = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = t_begin; t < t_end; ++t) {
                 const Tile q = tile_of<C>(p, t);
                 // columns gx1 .. gx1 + 254 of the row, clipped to the image (the staging warps zero what lies outside)
                 const int gx1 = 2 * (q.x0 - 1) + 1, gxs = max(gx1, 0), gxe = min(gx1 + NPX, p.W);
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, C::MINB) conv2d_s2rows_kernel(const 
         const uint32_t tmem_u = tc::uniform(tmem);
         uint32_t rc = 0, emp_par = 0;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int t = t_begin; t < t_end; ++t) {
             const Tile q = tile_of<C>(p, t);
 #pragma unroll 1
             for (int R = q.rlo; R <= q.rhi; ++R, ++rc) {
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, C::MINB) conv2d_s2rows_kernel(const 
         uint32_t rc = 0;
         int cur_n = -1;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int t = t_begin; t < t_end; ++t) {
             const Tile q = tile_of<C>(p, t);
             const int gx1 = 2 * (q.x0 - 1) + 1;
 #pragma unroll 1
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, C::MINB) conv2d_s2rows_kernel(const 
         };
         uint32_t full_par = 0;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int t = t_begin; t < t_end; ++t) {
             const Tile q = tile_of<C>(p, t);
             if (q.n != cur_n) { flush(); cur_n = q.n; }
             const int gx = q.x0 + r;

@@ -32,6 +32,7 @@
 //   [k-chunk 2][k_b*NPAD/8][8 n][8 k] fp16;  column n = g*NPAD + c: c < Cout feature, Cout..Cout+2 curvature (a,b,c), rest 0.
 //   C8 = 1: step j = horizontal taps (2j, 2j+1) (zero weights past the kernel); C8 > 1: tap (2j)/C8, channel chunks (2j)%C8, +1.
 #include <algorithm>
+#include <cstdlib>
 #include <utility>
 
 #include "cds_common.cuh"
@@ -112,6 +113,7 @@ struct KhParams {
     int in_act, nc_mode, H, W, n_images;
     int n_items;              // plain batch: items; pair batch: see pair_v / pair_b
     int pair_v, pair_b;       // pair batch (conv00): items are (side, v, b); the side-0 items v*pair_b + b of b share one image
+    int dbg;                  // CDS_KH_DEBUG (timing experiments only): 1 = load one 8-channel chunk per plane instead of all
     int x_pad;                // PX2: the image rows carry this many pad pixels on either side (their slots hold the true neighbours)
     int xt, yt, nz;           // tiles along x, y and item groups
     float epi_scale, inv_temperature;
@@ -251,6 +253,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
     const int ntiles = p.xt * p.yt * p.nz;
+    // A CTA takes a CONTIGUOUS run of tiles (strips of a row block, then row blocks, then items): it changes item once or twice
+    // instead of nearly every tile.  Every item change costs the staging warps a reload of the InstanceNorm coefficients (fp64
+    // loads in the pipeline's critical path) and the epilogue warps a flush of their statistics (320 shuffles + 64 fp64 atomics
+    // per warp at 32 channels) -- with tiles dealt round-robin that was ~20 % of the quarter-resolution layers' time.
+    // (The pair batch keeps round-robin dealing: its shared-image tiles cost several times a single item's, and a contiguous
+    // run would give some CTAs only those.)
+    const bool contiguous = GRP == 1;
+    const int t_begin = contiguous ? (int)((long long)ntiles * blockIdx.x / gridDim.x) : (int)blockIdx.x;
+    const int t_end = contiguous ? (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x) : ntiles;
+    const int t_step = contiguous ? 1 : (int)gridDim.x;
     const bool staged = STAGING && p.in_stats != nullptr;
     constexpr int EPI_ARRIVALS = 4;   // the four warps of the set that zeroes the slot
 
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
             tc::mbar_expect_tx(bar_b, C::B_BYTES);
             tc::bulk_copy_g2s(sB_u, p.wgt, C::B_BYTES, bar_b);
             uint32_t rc = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = t_begin; t < t_end; t += t_step) {
                 const Tile q = tile_of<C>(p, t);
                 int n, cnt, nstr;
                 group_of<GRP>(p, q.z, n, cnt, nstr);
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                 for (int R = r0; R <= r1; ++R, ++rc) {
                     const uint32_t slot = rc % NR;
                     if (rc >= (uint32_t)NR) mbar_wait_relaxed(ring_empty + slot, ((rc / NR) - 1) & 1);
-                    tc::mbar_expect_tx(ring_full + slot, C::ROWB);
+                    tc::mbar_expect_tx(ring_full + slot, (p.dbg & 1) && C8 > 1 ? C::PLANES * SLAB : C::ROWB);
                     const uint32_t dst = sA_u + slot * C::ROWB;
 #pragma unroll
                     for (int pl = 0; pl < C::PLANES; ++pl) {
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
                             tc::tma_load_4d(dst + pl * SLAB, &tmap, ring_full + slot, 2 * (q.x0 - HMAX + p.x_pad), R, img + pl * p.n_images, 0);
                         } else {
 #pragma unroll
-                            for (int c8 = 0; c8 < C8; ++c8)
+                            for (int c8 = 0; c8 < ((p.dbg & 1) ? 1 : C8); ++c8)
                                 tc::tma_load_5d(dst + (pl * C8 + c8) * SLAB, &tmap, ring_full + slot, 0, c8, q.x0 - HMAX, R, img + pl * p.n_images);
                         }
                     }
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
         const uint32_t b16 = sB_u >> 4;
         uint32_t rc = 0, it = 0;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        for (int t = t_begin; t < t_end; t += t_step, ++it) {
             const Tile q = tile_of<C>(p, t);
             const int r0 = max(q.y0 - HMAX, 0), r1 = min(q.y0 + TY - 1 + HMAX, p.H - 1);
             const int ylast = min(q.y0 + TY - 1, p.H - 1);
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
             uint32_t rc = 0;
             int cur_n = -1;
 #pragma unroll 1
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = t_begin; t < t_end; t += t_step) {
                 const Tile q = tile_of<C>(p, t);
                 int n, cnt, nstr;
                 group_of<GRP>(p, q.z, n, cnt, nstr);
@@ -480,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynconv_kh_kernel(const __grid_co
         };
         uint32_t it = 0;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        for (int t = t_begin; t < t_end; t += t_step, ++it) {
             const Tile q = tile_of<C>(p, t);
             if (q.z != cur_z) {
                 flush();
@@ -679,6 +691,8 @@ int launch_kh(const void* x, KhParams p, cudaStream_t st) {
         ok = tma::make_f16(&tmap, x, 5, dims, strides, box);
     }
     if (!ok) return CDS_EUNSUPPORTED;
+    static const int dbg = [] { const char* e = getenv("CDS_KH_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
     p.xt = cds_div_up(p.W, C::TXO);
     p.yt = cds_div_up(p.H, C::TY);
     p.nz = GRP > 1 ? p.pair_b * ((p.pair_v + GRP - 1) / GRP) + p.pair_v * p.pair_b : p.n_items;
