@@ -119,3 +119,79 @@ def test_kh_schedule_reproduces_branch_convolutions(pretrained_sd, layer, hw):
         assert (got[..., :cout].permute(2, 0, 1) - ref_f).abs().max() < 1e-5 * scale + 1e-7
         assert (got[..., cout:cout + 3].permute(2, 0, 1) - ref_a).abs().max() < 1e-5 * ref_a.abs().max() + 1e-7
         assert got[..., cout + 3:].abs().max() == 0
+
+
+def test_kh_schedule_pixel_pair_slots_for_8bit_images(pretrained_sd):
+    """The image layer on 8-bit images (cds_dynamic_conv_kh_u8): operand slots hold (RGB of a pixel, RGB of its right neighbour,
+    0, 0) as byte / 256 on rows padded by the library's pad, one K = 16 step covers the four taps 4j .. 4j+3 (k-chunk q at slot
+    offset 4j + 2q), and the packed images carry 256 / 255: pushed through the kernel's index arithmetic, the accumulators must
+    equal the convolutions of float32(byte) / 255."""
+    from cds_mvsnet_b200 import _lib
+    layer = "conv00"
+    cin, cout, ks, pre = W.DYN_LAYERS[layer]
+    w = W.pack_dynamic_conv(pretrained_sd, pre, cin, cout, ks, "cpu")
+    img = W.pack_dynamic_conv_kh(w, px2=True).double().numpy()
+    pad = _lib.LIB.load().cds_dynamic_conv_kh_u8_pad()
+    TY, (H, Wd) = _ty(layer), (17, 140)
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, size=(3, H, Wd))
+    hmax = (max(ks) - 1) // 2
+    txo = TX - 2 * hmax
+    assert pad >= hmax + 1
+    # padded pixel-pair slots [H][Wd + 2 pad][8]
+    slots = np.zeros((H, Wd + 2 * pad, 8))
+    for xp in range(Wd + 2 * pad):
+        for q in range(2):
+            x = xp - pad + q
+            if 0 <= x < Wd:
+                slots[:, xp, 3 * q:3 * q + 3] = u8[:, :, x].T / 256.0
+    npad = W.kh_layout(cout, ks[0])[0]
+    slots_per = TY + 1
+    imgs, o = [], 0
+    for k in ks:
+        nj, ncols = (k + 3) // 4, W.kh_layout(cout, k)[1]
+        sz = nj * 2 * ncols * 8
+        imgs.append([img[o + t * sz:o + (t + 1) * sz].reshape(nj, 2, ncols, 8) for t in range(2)])
+        o += 2 * sz
+    assert o == img.size
+    out = [np.full((H, Wd, npad), np.nan) for _ in ks]
+    acc = [np.zeros((slots_per * npad, TX)) for _ in ks]
+    for ty in range(-(-H // TY)):
+        for tx in range(-(-Wd // txo)):
+            y0, x0 = ty * TY, max(0, min(tx * txo, Wd - txo))
+            for R in range(max(y0 - hmax, 0), min(y0 + TY - 1 + hmax, H - 1) + 1):
+                # the row segment the TMA box delivers: padded columns x0 - hmax + pad .. + 128 (+ the spill behind it)
+                seg = np.zeros((TX + 16, 8))
+                lo = x0 - hmax + pad
+                hi = min(lo + TX + 16, Wd + 2 * pad)
+                seg[:hi - lo] = slots[R, lo:hi]
+                for b, k in enumerate(ks):
+                    hb = (k - 1) // 2
+                    ylo, yhi = max(y0, R - hb), min(min(y0 + TY - 1, H - 1), R + hb)
+                    if ylo > yhi:
+                        continue
+                    g0, n = (ylo - (R - hb)) * npad, -(-((yhi - ylo + 1) * npad) // 16) * 16
+                    d0 = (ylo - y0) * npad
+                    for prod in range(2):
+                        for j in range((k + 3) // 4):
+                            A = np.concatenate([seg[hmax - hb + 4 * j + 2 * q:hmax - hb + 4 * j + 2 * q + TX] for q in range(2)], axis=1)   # [128, 16]
+                            Bm = imgs[b][prod][j]
+                            Bfull = np.concatenate((Bm[0], Bm[1]), axis=1)
+                            acc[b][d0:d0 + n] += Bfull[g0:g0 + n] @ A.T
+            for b in range(len(ks)):
+                for s in range(TY):
+                    y = y0 + s
+                    if y < H:
+                        for r in range(txo):
+                            gx = x0 + r
+                            if gx < Wd and gx >= tx * txo:
+                                out[b][y, gx] = acc[b][s * npad:(s + 1) * npad, r]
+                    acc[b][s * npad:(s + 1) * npad] = 0
+    xin = torch.from_numpy(u8.astype(np.float64) / 255.0)
+    for b, k in enumerate(ks):
+        ref_f = F.conv2d(xin[None], pretrained_sd[f"{pre}.convs.{b}.weight"].double(), padding=(k - 1) // 2)[0]
+        ref_a = F.conv2d(xin[None], pretrained_sd[f"{pre}.att_convs.{b}.weight"].double(), padding=(k - 1) // 2)[0]
+        got = torch.from_numpy(out[b])
+        assert not torch.isnan(got[..., :cout + 3]).any()
+        assert (got[..., :cout].permute(2, 0, 1) - ref_f).abs().max() < 1e-5 * ref_f.abs().max() + 1e-7
+        assert (got[..., cout:cout + 3].permute(2, 0, 1) - ref_a).abs().max() < 1e-5 * ref_a.abs().max() + 1e-7
