@@ -213,14 +213,41 @@ struct RefChunk<__half, C> {
     }
 };
 
+// fp32 storage, FOUR channels per lane (C / 4 lanes per pixel): one 16-byte load per tap and lane, so a warp-wide load
+// covers whole 128-byte lines when C = 32 (see aggregate_f32q_kernel)
+template <int C>
+struct RefQuad {
+    float2 ref[2];
+    __device__ __forceinline__ void load(const float* p) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        ref[0] = make_float2(a.x, a.y); ref[1] = make_float2(a.z, a.w);
+    }
+    __device__ __forceinline__ float similarity(const float* fea, unsigned pix0, int w, const Foot& f) const {
+        const TapAddr<float, C> ta(fea, pix0, w, f);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(ta.t00()));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ta.t01()));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(ta.t10()));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(ta.t11()));
+        const float2 w00 = make_float2(f.w00, f.w00), w01 = make_float2(f.w01, f.w01);
+        const float2 w10 = make_float2(f.w10, f.w10), w11 = make_float2(f.w11, f.w11);
+        const float2 lo = ffma2(w11, make_float2(d.x, d.y), ffma2(w10, make_float2(c.x, c.y),
+                          ffma2(w01, make_float2(b.x, b.y), fmul2(w00, make_float2(a.x, a.y)))));
+        const float2 hi = ffma2(w11, make_float2(d.z, d.w), ffma2(w10, make_float2(c.z, c.w),
+                          ffma2(w01, make_float2(b.z, b.w), fmul2(w00, make_float2(a.z, a.w)))));
+        const float2 s2 = ffma2(ref[1], hi, fmul2(ref[0], lo));
+        return s2.x + s2.y;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // pass 1: entropy[v, b, y, x] = H(softmax_d(sum_c ref[c] * warp_d[c]))
 // ---------------------------------------------------------------------------------------------
-template <typename T, int C, bool PACKED>
+template <typename T, int C, bool PACKED, int CPL = 8>
 __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ ref_fea, const T* __restrict__ src_fea,
                                                       const float* __restrict__ coef, const float* __restrict__ depth,
                                                       int V, int B, int D, int h, int w, float* __restrict__ entropy) {
-    constexpr int LPP = C / 8;  // lanes per pixel
+    static_assert(CPL == 8 || (CPL == 4 && std::is_same<T, float>::value && !PACKED), "four channels per lane: fp32 storage only");
+    constexpr int LPP = C / CPL;  // lanes per pixel
     // 32-bit indexing (the host checks h*w*C < 2^31): blockIdx.y = (view, batch item), blockIdx.x tiles that image's
     // pixels.  Lanes of one pixel sit in the same warp because LPP divides 32; dead lanes of an image's last block redo
     // its last pixel so that every shuffle below is executed by full warps.
@@ -234,11 +261,11 @@ __global__ void __launch_bounds__(256, 4) entropy_kernel(const T* __restrict__ r
     const int x = pix % w, y = pix / w;
     const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
 
-    const T* rf = ref_fea + (((size_t)v * B + b) * P + (size_t)y * w + x) * C + chunk * 8;
+    const T* rf = ref_fea + (((size_t)v * B + b) * P + (size_t)y * w + x) * C + chunk * CPL;
     // the thread's channel chunk of the source features; the (view, batch item) image starts at pixel pix0 of it
-    const T* sf = src_fea + chunk * 8;
+    const T* sf = src_fea + chunk * CPL;
     const unsigned pix0 = (unsigned)((v * B + b) * P);
-    RefChunk<T, C> ref;
+    typename std::conditional<CPL == 4, RefQuad<C>, RefChunk<T, C>>::type ref;
     ref.load(rf);
     WarpCoef k = load_coef(coef + ((size_t)b * V + v) * 12);
     float rx, ry, rz;
@@ -443,6 +470,119 @@ __global__ void __launch_bounds__(256, MINB) aggregate_kernel(const T* __restric
 #pragma unroll
                     for (int i = 0; i < 8; ++i) res[i] = o[i] - __half2float(__float2half_rn(o[i]));
                     Vec8<__half>::store(vol_lo + oofs + (size_t)d * P * 8, res);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2, fp32 features and the split fp16 volume (stage 1 of the precise cascade), FOUR channels per lane: a pixel's
+// C / 4 lanes read one tap with ONE 16-byte load each, so for C = 32 a load instruction of the warp covers four whole
+// 128-byte lines (4 pixels x 8 lanes) where the 8-channel form touches eight lines with half of each used -- the sweep
+// is bound by L1 wavefronts, and this halves them.  The pixel's 8 lanes share the projections of TWO planes per step
+// (lane c projects view c % 4 at plane d + c / 4), so the per-thread cost of a projection is spread over two planes.
+// Arithmetic per channel is the 8-channel form's (same blend order, same FMA chain over the views), so the volume is
+// bit-identical.
+// ---------------------------------------------------------------------------------------------
+template <int C, int VMAX, int MINB>
+__global__ void __launch_bounds__(256, MINB) aggregate_f32q_kernel(const float* __restrict__ ref_fea, const float* __restrict__ src_fea,
+                                                                   const float* __restrict__ coef, const float* __restrict__ depth,
+                                                                   const float* __restrict__ vis, int V, int B, int D, int h, int w,
+                                                                   __half* __restrict__ vol_hi, __half* __restrict__ vol_lo) {
+    constexpr int LPP = C / 4;
+    static_assert(LPP <= 32 && LPP % VMAX == 0, "one owned (view, plane) per lane");
+    constexpr int PL = LPP / VMAX;   // planes per step: lane `chunk` projects view chunk % VMAX at plane d + chunk / VMAX
+    const int P = h * w;
+    const int b = blockIdx.y;
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    const bool live = gid < P * LPP;
+    const int g = live ? gid : P * LPP - 1;
+    const int chunk = g % LPP;
+    const int pix = g / LPP;
+    const int x = pix % w, y = pix / w;
+    const size_t pofs = (size_t)pix;
+    const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);
+
+    float vsum = 0.f;
+    float vw[VMAX];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        vw[v] = (v < V) ? __ldg(vis + ((size_t)v * B + b) * P + pofs) : 0.f;
+        if (v < V) vsum += vw[v];  // same accumulation order as the reference loop (model.py:59)
+    }
+    const float inv = 1.f / (vsum + 1e-6f);
+    const int own_v = chunk % VMAX, own_p = chunk / VMAX;
+    float orx = 0.f, ory = 0.f, orz = 0.f, otx = 0.f, oty = 0.f, otz = 1.f;
+    if (own_v < V) {
+        WarpCoef k = load_coef(coef + ((size_t)b * V + own_v) * 12);
+        pixel_ray(k, (float)x, (float)y, orx, ory, orz);
+        otx = k.t[0]; oty = k.t[1]; otz = k.t[2] + 1e-6f;
+    }
+    const float* dp = depth + (size_t)b * D * P + pofs;
+    // channel-blocked volume [B][C/8][D][h][w][8]: this lane writes half of an 8-channel slab
+    const size_t oofs = (((size_t)b * (C / 8) + (chunk >> 1)) * D * P + pofs) * 8 + (chunk & 1) * 4;
+    const float* rbase = ref_fea + ((size_t)b * P + pofs) * C + chunk * 4;
+    const char* sbase = reinterpret_cast<const char*>(src_fea + chunk * 4);
+    const size_t vstride = (size_t)B * P * C;
+    const unsigned BP = (unsigned)(B * P), bP = (unsigned)(b * P);
+    constexpr int kPix = C * (int)sizeof(float);
+    // the pixel's reference channels, scaled by vis_v / (sum vis + 1e-6), stay in registers for the whole sweep
+    float2 rv[VMAX][2];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        const float sc = vw[v] * inv;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < V) r = __ldg(reinterpret_cast<const float4*>(rbase + (size_t)v * vstride));
+        rv[v][0] = v < V ? fmul2(make_float2(r.x, r.y), make_float2(sc, sc)) : make_float2(0.f, 0.f);
+        rv[v][1] = v < V ? fmul2(make_float2(r.z, r.w), make_float2(sc, sc)) : make_float2(0.f, 0.f);
+    }
+
+    float dep_next = __ldg(dp + (size_t)min(own_p, D - 1) * P);
+    for (int d0 = 0; d0 < D; d0 += PL) {
+        const float dep = dep_next;
+        dep_next = __ldg(dp + (size_t)min(d0 + PL + own_p, D - 1) * P);   // one step ahead (see entropy_kernel)
+        Foot mine;
+        {
+            float px = orx * dep + otx;
+            float py = ory * dep + oty;
+            float iz = __frcp_rn(orz * dep + otz);
+            mine = make_foot(px * iz, py * iz, w, h);
+            mine.o00 += (int)(bP + (unsigned)own_v * BP);   // offset of the owned view's image
+        }
+#pragma unroll
+        for (int pl = 0; pl < PL; ++pl) {
+            const int d = d0 + pl;
+            if (d >= D) break;   // warp-uniform
+            float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) {
+                if (v < V) {   // warp-uniform
+                    const Foot f = shfl_foot(mine, lane_base + pl * VMAX + v);
+                    const char* r0 = sbase + (size_t)(unsigned)f.o00 * kPix;
+                    const char* r1 = sbase + (size_t)((unsigned)f.o00 + (unsigned)w) * kPix;
+                    const float4 ta = __ldg(reinterpret_cast<const float4*>(r0));
+                    const float4 tb = __ldg(reinterpret_cast<const float4*>(r0 + kPix));
+                    const float4 tc_ = __ldg(reinterpret_cast<const float4*>(r1));
+                    const float4 td = __ldg(reinterpret_cast<const float4*>(r1 + kPix));
+                    const float2 w00 = make_float2(f.w00, f.w00), w01 = make_float2(f.w01, f.w01);
+                    const float2 w10 = make_float2(f.w10, f.w10), w11 = make_float2(f.w11, f.w11);
+                    const float2 lo = ffma2(w11, make_float2(td.x, td.y), ffma2(w10, make_float2(tc_.x, tc_.y),
+                                      ffma2(w01, make_float2(tb.x, tb.y), fmul2(w00, make_float2(ta.x, ta.y)))));
+                    const float2 hi = ffma2(w11, make_float2(td.z, td.w), ffma2(w10, make_float2(tc_.z, tc_.w),
+                                      ffma2(w01, make_float2(tb.z, tb.w), fmul2(w00, make_float2(ta.z, ta.w)))));
+                    acc[0] = ffma2(rv[v][0], lo, acc[0]);
+                    acc[1] = ffma2(rv[v][1], hi, acc[1]);
+                }
+            }
+            if (live) {
+                const float o[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
+                __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+                *reinterpret_cast<uint2*>(vol_hi + oofs + (size_t)d * P * 8) = make_uint2(as_u32(h0), as_u32(h1));
+                if (vol_lo) {
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    __half2 l0 = __floats2half2_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2half2_rn(o[2] - f1.x, o[3] - f1.y);
+                    *reinterpret_cast<uint2*>(vol_lo + oofs + (size_t)d * P * 8) = make_uint2(as_u32(l0), as_u32(l1));
                 }
             }
         }
@@ -831,6 +971,15 @@ int launch_entropy(const void* ref, const void* src, const float* coef, const fl
     if (kHalf && packed) entropy_kernel<T, c, kHalf><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy); \
     else entropy_kernel<T, c, false><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy);                    \
     break;
+    if constexpr (!kHalf) {
+        // fp32 features with 32 channels (stage 1 of the precise cascade): four channels per lane, 8 lanes per pixel
+        static const bool quad = [] { const char* e = getenv("CDS_ENT_QUAD"); return !(e && e[0] == '0'); }();
+        if (quad && C == 32) {
+            dim3 qb(cds_div_up((long long)h * w * (C / 4), 256), V * B);
+            entropy_kernel<float, 32, false, 4><<<qb, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy);
+            return cds_check_launch("cds_costvol_entropy");
+        }
+    }
     switch (C) {
         case 8: CDS_ENT(8)
         case 16: CDS_ENT(16)
@@ -875,6 +1024,17 @@ int launch_aggregate(const void* ref, const void* src, const float* coef, const 
     else if (V <= 4) aggregate_kernel<T, c, 4, 3><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo);   \
     else aggregate_kernel<T, c, kMaxViews, 2><<<blocks, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, o, vol_hi, vol_lo);    \
     break;
+    if constexpr (std::is_same<T, float>::value) {
+        // stage 1 of the precise cascade: fp32 features, split fp16 volume, up to 4 views -> four channels per lane
+        static const int quad = [] { const char* e = getenv("CDS_AGG_QUAD"); return e ? atoi(e) : 3; }();
+        if (quad && vol_hi && !volume && V <= 4 && C == 32) {
+            dim3 qb(cds_div_up((long long)h * w * (C / 4), 256), B);
+            if (quad == 2) aggregate_f32q_kernel<32, 4, 2><<<qb, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, vol_hi, vol_lo);
+            else if (quad == 4) aggregate_f32q_kernel<32, 4, 4><<<qb, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, vol_hi, vol_lo);
+            else aggregate_f32q_kernel<32, 4, 3><<<qb, 256, 0, st>>>(r, s, coef, depth, vis, V, B, D, h, w, vol_hi, vol_lo);
+            return cds_check_launch("cds_costvol_aggregate");
+        }
+    }
     switch (C) {
         case 8: CDS_AGG(8)
         case 16: CDS_AGG(16)

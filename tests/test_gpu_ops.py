@@ -866,10 +866,13 @@ def test_instnorm_act_split_f32():
     assert torch.equal(out16, out.half())
 
 
-def test_costvol_aggregate_split_matches_fp32_form():
-    """fp32 features -> split fp16 volume: value + residual planes reproduce the fp32-storage aggregate."""
+@pytest.mark.parametrize("shape", [(2, 1, 32, 8, 24, 40), (1, 2, 32, 5, 17, 23), (3, 1, 32, 6, 31, 45), (4, 2, 32, 4, 16, 33),
+                                   (5, 1, 32, 4, 16, 24), (2, 1, 16, 8, 24, 40)], ids=lambda v: "x".join(map(str, v)))
+def test_costvol_aggregate_split_matches_fp32_form(shape):
+    """fp32 features -> split fp16 volume: value + residual planes reproduce the fp32-storage aggregate.  C = 32 with up to
+    4 views runs the four-channels-per-lane sweep, the fp32-storage call the eight-channel one: bit-identical volumes."""
     torch.manual_seed(2)
-    V, B, C_, D, h, w = 2, 1, 32, 8, 24, 40
+    V, B, C_, D, h, w = shape
     ref_f = cu(torch.tanh(torch.randn(V, B, h, w, C_))); src_f = cu(torch.tanh(torch.randn(V, B, h, w, C_)))
     s = synthetic.make_sample(dict(W=4 * w, H=4 * h, N=V + 1, ndepths=(D,), ratios=(1.0,), B=B, Dtot=192, interval=2.65))
     pm = cu(s.proj_matrices["stage1"])
