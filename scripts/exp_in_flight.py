@@ -22,6 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--k", type=int, default=2)
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--offset-ms", type=float, default=0.0, help="delay lane 1's first replay by this long (phase experiment)")
 args = ap.parse_args()
 torch.set_grad_enabled(False)
 cfg = dict(synthetic.CONFIGS[args.workload])
@@ -44,12 +45,15 @@ torch.cuda.synchronize()
 ref = outs[0]["stage3"]["depth"].clone()
 
 
-def run(k, steps):
+def run(k, steps, offset_ms=0.0):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
     for st in streams[:k]:
         st.wait_event(ev0)
+    if offset_ms > 0 and k > 1:
+        with torch.cuda.stream(streams[1]):
+            torch.cuda._sleep(int(offset_ms * 1.9e6))   # ~1.9 GHz SM clock
     for i in range(steps):
         j = i % k
         with torch.cuda.stream(streams[j]):
@@ -65,6 +69,11 @@ for k in range(1, args.k + 1):
     run(k, 4)
     ms = run(k, args.steps)
     print(f"in flight {k}: {ms:.3f} ms/map  {1e3 / ms:.2f} maps/s")
+    if k > 1 and args.offset_ms > 0:
+        for off in (args.offset_ms, 2 * args.offset_ms, 3 * args.offset_ms):
+            ms = run(k, args.steps, off)
+            # lane 0 works alone during the delay, so the truth lies between the raw figure and the one with the delay taken out
+            print(f"in flight {k}, lane 1 delayed {off:.1f} ms: {ms:.3f} ms/map raw, {(ms * args.steps - off) / args.steps:.3f} with the delay taken out")
 for o in outs:
     d = o["stage3"]["depth"]
     print("vs first pass of engine 0: max abs", float((d - ref).abs().max()), "mean rel", float(((d - ref).abs() / ref.abs()).mean()))
