@@ -959,13 +959,15 @@ bool s3_tma_applies(int V, int B, int C, int D, int h, int w, int dtype) {
 
 template <typename T>
 int launch_entropy(const void* ref, const void* src, const float* coef, const float* depth, int V, int B, int C, int D,
-                   int h, int w, float* entropy, cudaStream_t st) {
+                   int h, int w, float* entropy, cudaStream_t st, bool fast = false) {
     dim3 blocks(cds_div_up((long long)h * w * (C / 8), 256), V * B);
     const T* r = (const T*)ref;
     const T* s = (const T*)src;
-    // fp16 storage: fp32 tap weights on per-tap FHFMA dot products.  CDS_ENTROPY_PACKED=1 opts into the packed-half blend of
-    // aggregate_f16_kernel (10 % faster, but the entropy's error grows from < 2e-4 to 5e-4, measured on B200)
-    static const bool packed = [] { const char* e = getenv("CDS_ENTROPY_PACKED"); return e && e[0] == '1'; }();
+    // fp16 storage: fp32 tap weights on per-tap FHFMA dot products.  The `fast` entry (cds_costvol_entropy_fast) takes the
+    // packed-half blend of aggregate_f16_kernel: 10-12 % faster, the entropy's error grows from < 2e-4 to 5e-4 (measured on
+    // B200).  CDS_ENTROPY_PACKED=1 / 0 forces it on / off for both entries.
+    static const int forced = [] { const char* e = getenv("CDS_ENTROPY_PACKED"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool packed = forced < 0 ? fast : forced == 1;
     constexpr bool kHalf = std::is_same<T, __half>::value;
 #define CDS_ENT(c)                                                                                                          \
     if (kHalf && packed) entropy_kernel<T, c, kHalf><<<blocks, 256, 0, st>>>(r, s, coef, depth, V, B, D, h, w, entropy); \
@@ -1063,6 +1065,18 @@ int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* c
     if (dtype == CDS_F32) return launch_entropy<float>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream);
     cds_set_error("cds_costvol_entropy: unknown dtype %d", dtype);
     return CDS_EARG;
+}
+
+int cds_costvol_entropy_fast(const void* ref_fea, const void* src_fea, const float* coef, const float* depth, int V, int B,
+                             int C, int D, int h, int w, int dtype, float* entropy, cudaStream_t stream) {
+    if (dtype != CDS_F16 || s3_tma_applies(V, B, C, D, h, w, dtype))
+        return cds_costvol_entropy(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, dtype, entropy, stream);
+    CDS_REQUIRE(ref_fea && src_fea && coef && depth && entropy, CDS_EARG, "cds_costvol_entropy_fast: null pointer");
+    CDS_REQUIRE(V >= 1 && V <= kMaxViews && B > 0 && D > 0 && h > 1 && w > 1, CDS_ESHAPE,
+                "cds_costvol_entropy_fast: bad shape V=%d B=%d D=%d h=%d w=%d (1 <= V <= %d)", V, B, D, h, w, kMaxViews);
+    CDS_REQUIRE((long long)h * w * C < (1ll << 31) && (long long)V * B * h * w < (1ll << 31) && (long long)V * B <= 65535, CDS_ESHAPE,
+                "cds_costvol_entropy_fast: feature map too large for 32-bit offsets");
+    return launch_entropy<__half>(ref_fea, src_fea, coef, depth, V, B, C, D, h, w, entropy, stream, true);
 }
 
 int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float* coef, const float* depth,

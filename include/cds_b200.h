@@ -79,6 +79,11 @@ int cds_depth_hypotheses(const float* depth_values, int Dtot, const float* prev_
  * entropy[v,b,y,x] = H(softmax_d(sum_c ref*warp_d))  (models/model.py:44-50). C in {8,16,32}. */
 int cds_costvol_entropy(const void* ref_fea, const void* src_fea, const float* coef, const float* depth, int V, int B,
                         int C, int D, int h, int w, int dtype, float* entropy, cudaStream_t stream);
+/* Same sweep for a consumer that only needs the entropy to ~5e-4 (the visibility net, models/model.py:51): on fp16 features the
+ * four taps are blended in packed half arithmetic before the dot product (cds_costvol_entropy keeps fp32 tap weights: < 2e-4).
+ * Other dtypes and the TMA-staged last-stage shape run cds_costvol_entropy itself. */
+int cds_costvol_entropy_fast(const void* ref_fea, const void* src_fea, const float* coef, const float* depth, int V, int B,
+                             int C, int D, int h, int w, int dtype, float* entropy, cudaStream_t stream);
 /* volume[b,d,y,x,:] = sum_v vis_v * ref_v (.) warp_{v,d} / (sum_v vis_v + 1e-6), vis [V,B,h,w]
  * (models/model.py:57-59,74); volume [B,C/8,D,h,w,8] channel-blocked. */
 int cds_costvol_aggregate(const void* ref_fea, const void* src_fea, const float* coef, const float* depth,

@@ -296,6 +296,14 @@ def test_costvol_vs_oracle(C_, storage, tol, V):
     dt = _lib.dtype_code(storage)
     call("cds_costvol_entropy", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), V, B, C_, D, h, w, dt, ptr(ent_out))
     close(ent_out, torch.stack(ents), 2e-4, 1e-4)
+    # the visibility net's copy: packed-half blend on fp16 features (entropy to ~5e-4), the same kernel otherwise
+    ent_fast = torch.full_like(ent_out, float("nan"))
+    call("cds_costvol_entropy_fast", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), V, B, C_, D, h, w, dt, ptr(ent_fast))
+    if storage == torch.float16:
+        close(ent_fast, torch.stack(ents), 1e-3, 5e-4)
+        assert (ent_fast - ent_out).abs().max() < 2e-3
+    else:
+        assert torch.equal(ent_fast, ent_out)
     vol_out = torch.empty(B, C_ // 8, D, h, w, 8, device=DEV, dtype=storage)
     call("cds_costvol_aggregate", ptr(rf), ptr(sf), ptr(coef), ptr(dvc), ptr(visc), V, B, C_, D, h, w, dt, ptr(vol_out))
     assert O.rel_l1(from_blocked(vol_out.float().cpu()), vol) < tol
